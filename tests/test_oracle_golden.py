@@ -1,0 +1,100 @@
+"""CPU: the oracle restatement reproduces the golden vectors generated from the unmodified reference."""
+import pytest
+import torch
+
+from oracle import routeformer_oracle as O
+from tests.helpers import case_from_golden, load_golden, rel_err, targets_for
+
+EVAL_CASES = ["gps_only_paper", "full_small_eval", "full_paper_eval", "dreyeve_small", "normalized_small",
+              "no_gaze_small", "no_scene_small", "sparse_small"]
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_eval_forward_matches_reference(name):
+    gold = load_golden(name)
+    cfg, spec, sd, batch = case_from_golden(gold)
+    # state_dict layout pin
+    assert {(k, tuple(v.shape), str(v.dtype)) for k, v in sd.items()} == set(map(tuple, gold["layout"]))
+    torch.manual_seed(12345)
+    draw = O.CpuRandint()
+    with torch.no_grad():
+        out = O.Routeformer(sd, cfg, spec).forward(batch, training=False, draw=draw)
+    # ordered CPU RNG draw sequence pin
+    assert [(lk, (lq, u)) for lk, lq, u in draw.log] == [tuple(d) for d in gold["draws"]]
+    wp, dense = out if isinstance(out, tuple) else (out, None)
+    assert rel_err(wp, gold["waypoints"]) < 2e-6
+    if dense is not None:
+        assert rel_err(dense, gold["dense"]) < 2e-5
+    t_wp, _ = targets_for(cfg, gold["B"], gold["dseed"] + 1000)
+    # 4 decimal places at metric magnitude O(1..10); fp32 resolution scales with the value
+    tol = lambda v: 5e-5 + 2e-7 * abs(v)
+    assert abs(O.ade(wp, t_wp).item() - gold["ade"]) < tol(gold["ade"])
+    assert abs(O.fde(wp[-1:], t_wp[-1:]).item() - gold["fde"]) < tol(gold["fde"])
+    assert abs(O.fde(wp, t_wp).item() - gold["fde_batch"]) < tol(gold["fde_batch"])
+
+
+def test_train_step_matches_reference():
+    gold = load_golden("full_small_train")
+    cfg, spec, sd, batch = case_from_golden(gold)
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and not k.endswith(".pe"))
+              for k, v in sd.items()}
+    model = O.Routeformer(params, cfg, spec)
+    torch.manual_seed(12345)
+    wp, dense = model.forward(batch, training=True)
+    t_wp, t_dense = targets_for(cfg, gold["B"], gold["dseed"] + 1000)
+    loss = O.future_discounted_loss(wp, t_wp) + 0.5 * O.future_discounted_loss(dense, t_dense)
+    assert abs(loss.item() - gold["loss"]) < 1e-5 * max(1.0, abs(gold["loss"]))
+    loss.backward()
+    for k, n in gold["grad_norm"].items():
+        g = params[k].grad
+        assert g is not None, k
+        assert abs(g.norm().item() - n) <= 2e-4 * n + 1e-6, (k, g.norm().item(), n)
+    for k, g in gold["grad_small"].items():
+        # key-projection bias grads are analytically 0 (softmax shift invariance): pure rounding noise
+        assert rel_err(params[k].grad, g) < 2e-4 or (params[k].grad - g).abs().max() < 1e-6, k
+    for k, v in gold["bn"].items():
+        if "num_batches" in k:
+            continue
+        assert torch.allclose(model.bn_updates[k], v, atol=1e-6), k
+
+
+def test_submodules_and_metrics():
+    gold = load_golden("submodules")
+    ref = O.OracleConfig(encoder_layers=2, encoder_d_ff=64, cross_modal_decoder_layers=2, cross_modal_decoder_heads=4)
+    # regenerate the sub-module weights from their key templates (same seeds as make_golden.py)
+    sd = {}
+    O._perceive_encoder_keys(sd, "e", 40, 24, 128, 2, 64)
+    sd = {"e." + k: v for k, v in O.fill_state_dict({k[2:]: v for k, v in sd.items()}, 21).items()}
+    torch.manual_seed(3)
+    y = O.perceive_encoder(sd, "e", gold["perceive_encoder"]["x"], 1, ref, O.CpuRandint())
+    assert rel_err(y, gold["perceive_encoder"]["y"]) < 1e-6
+    sd = {}
+    O._perceive_decoder_keys(sd, "d", 16, 16, 16, 2, 32)
+    sd = O.fill_state_dict({k[2:]: v for k, v in sd.items()}, 22)
+    sd = {"d." + k: v for k, v in sd.items()}
+    torch.manual_seed(4)
+    y = O.perceive_decoder(sd, "d", gold["perceive_decoder"]["x_enc"], gold["perceive_decoder"]["x_dec"], 12, ref, O.CpuRandint())
+    assert rel_err(y, gold["perceive_decoder"]["y"]) < 1e-6
+    m = gold["median"]
+    assert torch.equal(O.median_downsample(m["x"], 20), m["y"])
+    assert torch.equal(O.median_downsample(m["x"][:, :80], 40), m["y2"])
+    g = gold["metrics"]
+    assert abs(O.ade(g["p"], g["t"]) - g["ade"]) < 1e-6
+    assert abs(O.fde(g["p"], g["t"]) - g["fde"]) < 1e-5
+    assert abs(O.fde(g["p"][2:3], g["t"][2:3]) - g["fde_1"]) < 1e-5
+    assert abs(O.future_discounted_loss(g["p"] * 3, g["t"]) - g["loss"]) < 1e-6
+    assert abs(O.future_discounted_loss(g["p"] * 3, g["t"], 0.9, "mse", 0.3) - g["loss_mse"]) < 1e-5
+    assert abs(O.future_discounted_loss(g["p"] * 3, g["t"], 0.9, "mae", 0.3) - g["loss_mae"]) < 1e-6
+    # "FDE" is a whole-horizon Frobenius norm: constant 0.5 offset over 30 steps -> sqrt(30*0.5) = 3.873
+    assert abs(g["const_offset_fde"].item() - 3.8730) < 1e-4
+    assert abs(O.fde(torch.zeros(1, 30, 2) + 0.5, torch.zeros(1, 30, 2)).item() - 3.8730) < 1e-4
+
+
+def test_explicit_circular_conv_matches_aten():
+    g = torch.Generator().manual_seed(0)
+    for L, pad in [(7, 1), (40, 1), (4, 2), (5, 2), (21, 2)]:
+        x, w, b = torch.randn(3, L, 6, generator=g), torch.randn(8, 6, 3, generator=g), torch.randn(8, generator=g)
+        a = O.circular_conv3(x, w, b, pad)
+        e = O.circular_conv3_explicit(x, w, b, pad)
+        assert a.shape == (3, L + 2 * pad - 2, 8)
+        assert torch.allclose(a, e, atol=1e-5)
