@@ -1,0 +1,415 @@
+// TF32 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
+// tcgen05.mma.kind::tf32 (one elected thread) -> fp32 accumulators in TMEM -> tcgen05.ld epilogue.
+//
+//   C[M,N] (+)= epilogue( sum_k A[m,k] * B[n,k] )
+//
+// Either operand may be K-major (reduction dim contiguous) or MN-major (the other dim contiguous), so the
+// same kernel serves forward (x W^T), dgrad (dy W) and wgrad (dy^T x, split over the long reduction with
+// fp32 atomics into the gradient arena).  Operands stay fp32 in HBM; the TMA descriptor (TFLOAT32 type)
+// rounds them to tf32 on the way into shared memory, accumulation is fp32.
+//
+// CTA = 128 threads, one 128 x BLOCK_N output tile, 2 CTAs resident per SM (one CTA's epilogue overlaps
+// the other's main loop):
+//   warp 0 / lane 0 : TMA producer over a STAGES-deep full/empty mbarrier ring
+//   warp 1 / lane 0 : tcgen05.mma issuer, tcgen05.commit releases ring slots and signals the epilogue
+//   warp 2          : TMEM allocate / free
+//   all 4 warps     : epilogue, thread t owns accumulator row t (TMEM lane t)
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace rf {
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;  // 32 fp32 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;    // K of one tcgen05.mma.kind::tf32
+constexpr int STAGES = 3;
+constexpr int NUM_THREADS = 128;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KiB
+constexpr int GROUP_BYTES = 32 * BLOCK_K * 4;   // one MN-major box: 32 k-rows x 128 B
+
+template <int BLOCK_N>
+struct Tile {
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
+};
+
+struct Args {
+  float* C; long long ldc;
+  int M, N, K;
+  int a_mn, b_mn;
+  const float* bias;
+  const float* rowadd; int rowadd_period; long long ld_rowadd;
+  const float* residual; long long ld_res;
+  int act;
+  float* preact; long long ld_pre;
+  const float* dact_aux; long long ld_aux; int dact;
+  int accumulate;
+  int kb_total, kb_per_split;
+  int group_in, group_out, row_offset;
+  int round_f16;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (SWIZZLE_128B, Blackwell version 1).
+//  K-major : rows of 128 B (32 tf32 along K); 8-row groups SBO = 1024 B apart; LBO unused (encoded 1).
+//  MN-major: 128 B = 32 elements along M/N; the 8 k-rows of one MMA are 128 B apart (one swizzle atom);
+//            LBO = stride between 32-element M/N groups (one TMA box = 4096 B), SBO = stride between
+//            8-row k groups (1024 B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == RF_ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == RF_ACT_GELU) return gelu_erf(v);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+  using T = Tile<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * T::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int kb_begin = blockIdx.z * a.kb_per_split;
+  const int kb_end = min(a.kb_total, kb_begin + a.kb_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], T::STAGE_BYTES);
+        uint8_t* sa = smem + s * T::STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        const int k0 = (kb_begin + i) * BLOCK_K;
+        if (!a.a_mn) {
+          tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+        } else {
+#pragma unroll
+          for (int g = 0; g < BLOCK_M / 32; ++g) tma_load_2d(sa + g * GROUP_BYTES, &tmA, &full_bar[s], m0 + 32 * g, k0);
+        }
+        if (!a.b_mn) {
+          tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+        } else {
+#pragma unroll
+          for (int g = 0; g < BLOCK_N / 32; ++g) tma_load_2d(sb + g * GROUP_BYTES, &tmB, &full_bar[s], n0 + 32 * g, k0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) /*D fp32*/ | (2u << 7) /*A tf32*/ | (2u << 10) /*B tf32*/ |
+                             (static_cast<uint32_t>(a.a_mn) << 15) | (static_cast<uint32_t>(a.b_mn) << 16) |
+                             (static_cast<uint32_t>(BLOCK_N >> 3) << 17) | (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + s * T::STAGE_BYTES);
+        const uint32_t b_base = a_base + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+          const uint64_t adesc = a.a_mn ? make_smem_desc(a_base + kk * 1024, GROUP_BYTES, 1024)
+                                        : make_smem_desc(a_base + kk * UMMA_K * 4, 16, 1024);
+          const uint64_t bdesc = a.b_mn ? make_smem_desc(b_base + kk * 1024, GROUP_BYTES, 1024)
+                                        : make_smem_desc(b_base + kk * UMMA_K * 4, 16, 1024);
+          umma_tf32(tmem_base, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+    __syncwarp();
+  }
+
+  // ---------------- epilogue: thread t <-> accumulator row t ---------------------------------
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  const int m = m0 + warp * 32 + lane;
+  const bool row_ok = m < a.M;
+  long long out_row = m;
+  if (a.group_in > 0) out_row = static_cast<long long>(m / a.group_in) * a.group_out + (m % a.group_in) + a.row_offset;
+  float* c_row = a.C + out_row * a.ldc;
+  const float* rowadd_row = a.rowadd ? a.rowadd + static_cast<long long>(m % a.rowadd_period) * a.ld_rowadd : nullptr;
+  const float* res_row = a.residual ? a.residual + static_cast<long long>(m) * a.ld_res : nullptr;
+  float* pre_row = a.preact ? a.preact + static_cast<long long>(m) * a.ld_pre : nullptr;
+  const float* aux_row = a.dact ? a.dact_aux + static_cast<long long>(m) * a.ld_aux : nullptr;
+  const bool vec_ok = ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0) && !a.accumulate;
+
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N; c += 32) {
+    const int nb = n0 + c;
+    if (nb >= a.N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(c), r);
+    tmem_wait_ld();
+    if (!row_ok) continue;
+    const int ncols = min(32, a.N - nb);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(r[j]);
+      if (j < ncols) {
+        const int n = nb + j;
+        if (a.bias) x += __ldg(a.bias + n);
+        if (rowadd_row) x += __ldg(rowadd_row + n);
+        if (res_row) x += res_row[n];
+        if (pre_row) pre_row[n] = x;
+        x = apply_act(x, a.act);
+        if (a.dact) {
+          const float t = aux_row[n];
+          x *= (a.dact == RF_ACT_RELU) ? (t > 0.0f ? 1.0f : 0.0f) : gelu_erf_grad(t);
+        }
+        if (a.round_f16) x = __half2float(__float2half_rn(x));
+      }
+      v[j] = x;
+    }
+    if (a.accumulate) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) atomicAdd(c_row + nb + j, v[j]);
+    } else if (vec_ok && ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(c_row + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) c_row[nb + j] = v[j];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+static bool tf32_round_in_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RF_TMA_TF32_ROUND");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// 2-D fp32 tensor map: dim0 = `inner` contiguous elements, dim1 = `outer` rows of pitch ld; box = 32 x box_rows.
+static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return RF_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, tf32_round_in_tma() ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%lld outer=%lld ld=%lld box_rows=%d", static_cast<int>(r),
+              static_cast<const void*>(base), inner, outer, ld, box_rows);
+    return RF_ERR_CUDA;
+  }
+  return RF_OK;
+}
+
+template <int BLOCK_N>
+static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStream_t stream) {
+  using T = Tile<BLOCK_N>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!p->a_mn_major) rc = make_map(&tmA, p->A, p->K, p->M, p->lda, BLOCK_M);
+  else rc = make_map(&tmA, p->A, p->M, p->K, p->lda, 32);
+  if (rc != RF_OK) return rc;
+  if (!p->b_mn_major) rc = make_map(&tmB, p->B, p->K, p->N, p->ldb, BLOCK_N);
+  else rc = make_map(&tmB, p->B, p->N, p->K, p->ldb, 32);
+  if (rc != RF_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p->M, BLOCK_M), ceil_div(p->N, BLOCK_N), splits);
+  gemm_tf32_kernel<BLOCK_N><<<grid, NUM_THREADS, T::SMEM_BYTES, stream>>>(tmA, tmB, args);
+  RF_LAUNCH_OK();
+  return RF_OK;
+}
+
+}  // namespace gemm
+}  // namespace rf
+
+extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
+  using namespace rf;
+  RF_CHECK_ARG(p != nullptr, "rf_gemm_tf32: null params");
+  RF_CHECK_ARG(p->M > 0 && p->N > 0 && p->K > 0, "rf_gemm_tf32: empty problem M=%d N=%d K=%d", p->M, p->N, p->K);
+  RF_CHECK_ARG(p->A && p->B && p->C, "rf_gemm_tf32: null operand");
+  RF_CHECK_ARG((p->lda % 4) == 0 && (p->ldb % 4) == 0, "rf_gemm_tf32: lda=%lld ldb=%lld must be multiples of 4 (TMA 16 B pitch)",
+               p->lda, p->ldb);
+  RF_CHECK_ARG((reinterpret_cast<uintptr_t>(p->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->B) & 15) == 0,
+               "rf_gemm_tf32: A/B must be 16-byte aligned");
+  RF_CHECK_ARG(p->lda >= (p->a_mn_major ? p->M : p->K) && p->ldb >= (p->b_mn_major ? p->N : p->K) && p->ldc >= p->N,
+               "rf_gemm_tf32: leading dimension smaller than the row length");
+  RF_CHECK_ARG(!p->rowadd || p->rowadd_period > 0, "rf_gemm_tf32: rowadd needs rowadd_period > 0");
+  RF_CHECK_ARG(!p->dact || p->dact_aux, "rf_gemm_tf32: dact needs dact_aux");
+  const int kb_total = ceil_div(p->K, gemm::BLOCK_K);
+  const bool plain = !p->bias && !p->rowadd && !p->residual && p->act == RF_ACT_NONE && !p->preact && !p->dact && !p->round_f16;
+  int splits = p->split_k;
+  const bool n64 = p->N <= 64;
+  const int tiles = ceil_div(p->M, gemm::BLOCK_M) * ceil_div(p->N, n64 ? 64 : 128);
+  if (splits <= 0) {
+    splits = 1;
+    if (p->accumulate && plain) {
+      const int want = ceil_div(2 * num_sms(), tiles);       // ~2 CTAs per SM
+      splits = max(1, min(want, kb_total / 4));              // keep >= 4 k-blocks per split
+    }
+  }
+  RF_CHECK_ARG(splits == 1 || (p->accumulate && plain), "rf_gemm_tf32: split_k>1 needs accumulate=1 and a plain epilogue");
+  int kb_per_split = ceil_div(kb_total, splits);
+  splits = ceil_div(kb_total, kb_per_split);
+  gemm::Args a;
+  a.C = p->C; a.ldc = p->ldc; a.M = p->M; a.N = p->N; a.K = p->K;
+  a.a_mn = p->a_mn_major ? 1 : 0; a.b_mn = p->b_mn_major ? 1 : 0;
+  a.bias = p->bias; a.rowadd = p->rowadd; a.rowadd_period = p->rowadd_period; a.ld_rowadd = p->ld_rowadd;
+  a.residual = p->residual; a.ld_res = p->ld_res; a.act = p->act; a.preact = p->preact; a.ld_pre = p->ld_pre;
+  a.dact_aux = p->dact_aux; a.ld_aux = p->ld_aux; a.dact = p->dact; a.accumulate = p->accumulate;
+  a.kb_total = kb_total; a.kb_per_split = kb_per_split;
+  a.group_in = p->out_group_in; a.group_out = p->out_group_out; a.row_offset = p->out_row_offset;
+  a.round_f16 = p->round_f16;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return n64 ? gemm::launch<64>(p, a, splits, s) : gemm::launch<128>(p, a, splits, s);
+}

@@ -1,0 +1,352 @@
+"""Raw (non-autograd) tensor-level wrappers of the C ABI: one function per entry point.
+
+PyTorch supplies device memory and the stream; all arithmetic happens in the CUDA library.  Every wrapper
+raises if a tensor is not a CUDA tensor -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+F32, F16, BF16, U8 = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+ATTN_PROB, ATTN_PROB_MASKED, ATTN_FULL = 0, 1, 2
+LAYOUT_BLHD, LAYOUT_BHLD = 0, 1
+ACT_CODES = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU}
+
+_DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16, torch.uint8: U8}
+
+# number of kernels enqueued through this module (bench.py reports it as `gpu_launches`)
+launch_count = 0
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("routeformer_b200 ops need CUDA tensors (no CPU fallback exists)")
+    return t.data_ptr()
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t
+
+
+def _row_pitch(t: torch.Tensor, name: str) -> int:
+    """Leading dimension of a 2-D view with unit inner stride."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError(f"{name} must be 2-D with a contiguous inner dimension, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+# ---------------------------------------------------------------------------------------------
+def fov_crop(frames: torch.Tensor, centers: torch.Tensor, windows: torch.Tensor, out_size: int, mean, std,
+             patch: int = 0, frame_ids: Optional[torch.Tensor] = None, n_frames: Optional[int] = None,
+             out_dtype=torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """frames [*,3,H,W] (fp16/fp32/u8, contiguous) -> [n,3,S,S] or patch-major [n*G*G, 3*p*p]."""
+    lib = _lib.load()
+    assert frames.is_contiguous() and frames.shape[-3] == 3
+    H, W = frames.shape[-2:]
+    n = int(n_frames if n_frames is not None else (frame_ids.numel() if frame_ids is not None else frames.numel() // (3 * H * W)))
+    centers = _f32(centers, "centers").contiguous()
+    windows = _f32(windows, "windows").contiguous()
+    assert centers.shape == (n, 2) and windows.shape == (n, 2)
+    if frame_ids is not None:
+        assert frame_ids.dtype == torch.int32 and frame_ids.is_contiguous()
+    if out is None:
+        if patch > 0:
+            G = out_size // patch
+            out = torch.empty(n * G * G, 3 * patch * patch, device=frames.device, dtype=out_dtype)
+        else:
+            out = torch.empty(n, 3, out_size, out_size, device=frames.device, dtype=out_dtype)
+    p = _lib.RfFovCropParams()
+    p.frames, p.src_dtype, p.frame_ids = _ptr(frames), _DTYPES[frames.dtype], _ptr(frame_ids)
+    p.n_frames, p.H, p.W = n, H, W
+    p.centers, p.windows = _ptr(centers), _ptr(windows)
+    for c in range(3):
+        p.mean[c] = float(mean[c])
+        p.inv_std[c] = 1.0 / float(std[c])
+    p.out_size, p.patch, p.out, p.out_dtype = out_size, patch, _ptr(out), _DTYPES[out.dtype]
+    p.out_ld = out.stride(0) if patch > 0 else 0
+    check(lib.rf_fov_crop(C.byref(p), _stream()), "rf_fov_crop")
+    _count()
+    return out
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
+         bias: Optional[torch.Tensor] = None, rowadd: Optional[torch.Tensor] = None, rowadd_period: int = 0,
+         residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, preact: Optional[torch.Tensor] = None,
+         dact_aux: Optional[torch.Tensor] = None, dact: int = ACT_NONE, accumulate: bool = False, split_k: int = 0,
+         out_group=(0, 0, 0), round_f16: bool = False, M: Optional[int] = None) -> torch.Tensor:
+    """out[M,N] (+)= epilogue(A . B^T) on the tcgen05 TF32 kernel.  A, B, out are 2-D fp32 views.
+
+    a_mn=False: A is [M,K] memory; True: A is [K,M] memory (logical A^T).  Same for B with N.
+    """
+    lib = _lib.load()
+    _f32(A, "A"), _f32(B, "B"), _f32(out, "out")
+    if a_mn:
+        K, Ma = A.shape
+    else:
+        Ma, K = A.shape
+    if b_mn:
+        Kb, N = B.shape
+    else:
+        N, Kb = B.shape
+    if K != Kb:
+        raise ValueError(f"gemm: reduction mismatch {K} vs {Kb}")
+    Mv = Ma if M is None else M
+    p = _lib.RfGemmParams()
+    p.A, p.lda, p.a_mn_major = _ptr(A), _row_pitch(A, "A"), int(a_mn)
+    p.B, p.ldb, p.b_mn_major = _ptr(B), _row_pitch(B, "B"), int(b_mn)
+    p.C, p.ldc = _ptr(out), _row_pitch(out, "out")
+    p.M, p.N, p.K = Mv, N, K
+    p.bias = _ptr(bias)
+    if rowadd is not None:
+        p.rowadd, p.rowadd_period, p.ld_rowadd = _ptr(rowadd), rowadd_period, _row_pitch(rowadd, "rowadd")
+    if residual is not None:
+        p.residual, p.ld_res = _ptr(residual), _row_pitch(residual, "residual")
+    p.act = act
+    if preact is not None:
+        p.preact, p.ld_pre = _ptr(preact), _row_pitch(preact, "preact")
+    if dact != ACT_NONE:
+        p.dact_aux, p.ld_aux, p.dact = _ptr(dact_aux), _row_pitch(dact_aux, "dact_aux"), dact
+    p.accumulate, p.split_k = int(accumulate), split_k
+    p.out_group_in, p.out_group_out, p.out_row_offset = out_group
+    p.round_f16 = int(round_f16)
+    check(lib.rf_gemm_tf32(C.byref(p), _stream()), "rf_gemm_tf32")
+    _count()
+    return out
+
+
+def conv3_assemble_fwd(z, y, n_seq, L, D, pad, bias=None, pe=None, wtime=None):
+    lib = _lib.load()
+    p = _lib.RfConv3AssembleParams()
+    p.z, p.ldz, p.y, p.ldy = _ptr(z), _row_pitch(z, "z"), _ptr(y), _row_pitch(y, "y")
+    p.n_seq, p.L, p.D, p.pad = n_seq, L, D, pad
+    p.bias, p.wtime = _ptr(bias), _ptr(wtime)
+    if pe is not None:
+        p.pe, p.ld_pe = _ptr(pe), _row_pitch(pe, "pe")
+    check(lib.rf_conv3_assemble_fwd(C.byref(p), _stream()), "rf_conv3_assemble_fwd")
+    _count()
+    return y
+
+
+def conv3_assemble_bwd(dy, dz, n_seq, L, D, pad, dbias=None, dwtime=None):
+    lib = _lib.load()
+    p = _lib.RfConv3AssembleBwdParams()
+    p.dy, p.ldy, p.dz, p.ldz = _ptr(dy), _row_pitch(dy, "dy"), _ptr(dz), _row_pitch(dz, "dz")
+    p.n_seq, p.L, p.D, p.pad = n_seq, L, D, pad
+    p.dbias, p.dwtime = _ptr(dbias), _ptr(dwtime)
+    check(lib.rf_conv3_assemble_bwd(C.byref(p), _stream()), "rf_conv3_assemble_bwd")
+    _count(1 + (dbias is not None) + (dwtime is not None))
+    return dz
+
+
+def conv3_pack_weight(w: torch.Tensor, wcat: torch.Tensor):
+    D, Cin, _ = w.shape
+    check(_lib.load().rf_conv3_pack_weight(_ptr(w), _ptr(wcat), D, Cin, wcat.stride(0), _stream()), "rf_conv3_pack_weight")
+    _count()
+    return wcat
+
+
+def conv3_unpack_grad(dwcat: torch.Tensor, dw: torch.Tensor):
+    D, Cin, _ = dw.shape
+    check(_lib.load().rf_conv3_unpack_grad(_ptr(dwcat), _ptr(dw), D, Cin, dwcat.stride(0), _stream()), "rf_conv3_unpack_grad")
+    _count()
+    return dw
+
+
+def _attn_params(q, k, v, B, H, Lq, Lk, dh, mode, layout, idx, idx_group, U, u, out, top, measure, forced_top):
+    """q/k/v: fp32 tensors whose element (b,l,h,e) sits at base + b*bs + l*ls + h*dh + e; given as (tensor, bs, ls)."""
+    p = _lib.RfAttnParams()
+    (qt, p.q_bs, p.q_ls), (kt, p.k_bs, p.k_ls), (vt, p.v_bs, p.v_ls) = q, k, v
+    p.q, p.k, p.v = _ptr(qt), _ptr(kt), _ptr(vt)
+    p.B, p.H, p.Lq, p.Lk, p.dh = B, H, Lq, Lk, dh
+    p.mode, p.out_layout = mode, layout
+    p.idx, p.idx_group, p.U, p.u = _ptr(idx), idx_group, U, u
+    p.out, p.top, p.measure, p.forced_top = _ptr(out), _ptr(top), _ptr(measure), _ptr(forced_top)
+    return p
+
+
+def attention_fwd(q, k, v, B, H, Lq, Lk, dh, mode, layout, idx, idx_group, U, u, out, top, measure=None, forced_top=None):
+    p = _attn_params(q, k, v, B, H, Lq, Lk, dh, mode, layout, idx, idx_group, U, u, out, top, measure, forced_top)
+    check(_lib.load().rf_attention_fwd(C.byref(p), _stream()), "rf_attention_fwd")
+    _count()
+    return out
+
+
+def attention_bwd(q, k, v, B, H, Lq, Lk, dh, mode, layout, U, u, top, dout, dq, dk, dv):
+    bp = _lib.RfAttnBwdParams()
+    bp.f = _attn_params(q, k, v, B, H, Lq, Lk, dh, mode, layout, None, 0, U, u, None, top, None, None)
+    bp.dout, bp.dq, bp.dk, bp.dv = _ptr(dout), _ptr(dq), _ptr(dk), _ptr(dv)
+    check(_lib.load().rf_attention_bwd(C.byref(bp), _stream()), "rf_attention_bwd")
+    _count()
+
+
+def layernorm_fwd(x, gamma, beta, y, mean, rstd):
+    M, D = x.shape
+    check(_lib.load().rf_layernorm_fwd(_ptr(x), _row_pitch(x, "x"), _ptr(gamma), _ptr(beta), _ptr(y), _row_pitch(y, "y"),
+                                       _ptr(mean), _ptr(rstd), M, D, _stream()), "rf_layernorm_fwd")
+    _count()
+    return y
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta):
+    M, D = x.shape
+    check(_lib.load().rf_layernorm_bwd(_ptr(dy), _row_pitch(dy, "dy"), _ptr(x), _row_pitch(x, "x"), _ptr(gamma), _ptr(mean),
+                                       _ptr(rstd), _ptr(dx), _row_pitch(dx, "dx"), _ptr(dgamma), _ptr(dbeta), M, D, _stream()),
+          "rf_layernorm_bwd")
+    _count()
+    return dx
+
+
+def distil_fwd(z, B, Lz, D, gamma, beta, running_mean, running_var, training, mean, rstd, out, argmax, momentum=0.1, eps=1e-5):
+    p = _lib.RfDistilParams()
+    p.z, p.B, p.Lz, p.D = _ptr(z), B, Lz, D
+    p.gamma, p.beta, p.running_mean, p.running_var = _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var)
+    p.training, p.momentum, p.eps = int(training), momentum, eps
+    p.mean, p.rstd, p.out, p.argmax = _ptr(mean), _ptr(rstd), _ptr(out), _ptr(argmax)
+    check(_lib.load().rf_distil_fwd(C.byref(p), _stream()), "rf_distil_fwd")
+    _count(3 if training else 2)
+    return out
+
+
+def distil_bwd(z, B, Lz, D, gamma, beta, mean, rstd, training, argmax, dout, dz, dgamma, dbeta, scratch):
+    p = _lib.RfDistilBwdParams()
+    p.z, p.B, p.Lz, p.D = _ptr(z), B, Lz, D
+    p.gamma, p.beta, p.mean, p.rstd, p.training = _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), int(training)
+    p.argmax, p.dout, p.dz, p.dgamma, p.dbeta, p.scratch = _ptr(argmax), _ptr(dout), _ptr(dz), _ptr(dgamma), _ptr(dbeta), _ptr(scratch)
+    check(_lib.load().rf_distil_bwd(C.byref(p), _stream()), "rf_distil_bwd")
+    _count(2)
+    return dz
+
+
+def motion_features(gps, visual, x, origin, E, rotate, normalize, mean, std):
+    B, T, _ = gps.shape
+    ld_vis = visual.stride(1) if visual is not None else 0
+    check(_lib.load().rf_motion_features(_ptr(gps), _ptr(visual), ld_vis, _ptr(x), x.stride(1), _ptr(origin), B, T, E, int(rotate),
+                                         int(normalize), float(mean), float(std), _stream()), "rf_motion_features")
+    _count()
+    return x
+
+
+def decoder_input_fwd(x, xdec, P, smart):
+    B, T, ld = x.shape
+    check(_lib.load().rf_decoder_input_fwd(_ptr(x), _ptr(xdec), B, T, P, ld, int(smart), _stream()), "rf_decoder_input_fwd")
+    _count()
+    return xdec
+
+
+def decoder_input_bwd(dxdec, dx, P, smart):
+    B, T, ld = dx.shape
+    check(_lib.load().rf_decoder_input_bwd(_ptr(dxdec), _ptr(dx), B, T, P, ld, int(smart), _stream()), "rf_decoder_input_bwd")
+    _count()
+    return dx
+
+
+def stream_tokens_fwd(src, F, first, step, dense, emb, tokens, B, T, E, tokens_per_clip, t_off):
+    check(_lib.load().rf_stream_tokens_fwd(_ptr(src), F, first, step, int(dense), _ptr(emb), _ptr(tokens), B, T, E, tokens_per_clip,
+                                           t_off, _stream()), "rf_stream_tokens_fwd")
+    _count()
+    return tokens
+
+
+def stream_tokens_bwd(dtokens, dsrc, F, first, step, dense, demb, B, T, E, tokens_per_clip, t_off):
+    check(_lib.load().rf_stream_tokens_bwd(_ptr(dtokens), _ptr(dsrc), F, first, step, int(dense), _ptr(demb), B, T, E,
+                                           tokens_per_clip, t_off, _stream()), "rf_stream_tokens_bwd")
+    _count((dsrc is not None) + (demb is not None))
+
+
+def decode_waypoints_fwd(out, origin, last_gps, waypoints, motion, rotate, normalize, mean, std):
+    B, P, _ = out.shape
+    check(_lib.load().rf_decode_waypoints_fwd(_ptr(out), out.stride(1), _ptr(origin), _ptr(last_gps), _ptr(waypoints), _ptr(motion), B, P,
+                                              int(rotate), int(normalize), float(mean), float(std), _stream()), "rf_decode_waypoints_fwd")
+    _count()
+
+
+def decode_waypoints_bwd(dwaypoints, origin, dout, rotate, normalize, std):
+    B, P, _ = dout.shape
+    check(_lib.load().rf_decode_waypoints_bwd(_ptr(dwaypoints), _ptr(origin), _ptr(dout), dout.stride(1), B, P, int(rotate),
+                                              int(normalize), float(std), _stream()), "rf_decode_waypoints_bwd")
+    _count()
+
+
+def median_downsample(x: torch.Tensor, target: int) -> torch.Tensor:
+    B, S, Cc = x.shape
+    x = _f32(x, "x").contiguous()
+    y = torch.empty(B, target, Cc, device=x.device, dtype=torch.float32)
+    check(_lib.load().rf_median_downsample(_ptr(x), _ptr(y), B, S, Cc, target, _stream()), "rf_median_downsample")
+    _count()
+    return y
+
+
+def ade_fde(pred: torch.Tensor, truth: torch.Tensor, per_sample: bool = False):
+    B, T, _ = pred.shape
+    pred, truth = _f32(pred, "pred").contiguous(), _f32(truth, "truth").contiguous()
+    result = torch.empty(2, device=pred.device, dtype=torch.float32)
+    ps = torch.empty(B, 2, device=pred.device, dtype=torch.float32) if per_sample else None
+    check(_lib.load().rf_ade_fde(_ptr(pred), _ptr(truth), B, T, _ptr(result), _ptr(ps), _stream()), "rf_ade_fde")
+    _count()
+    return result, ps
+
+
+LOSS_KINDS = {"smooth_l1": 0, "mse": 1, "mae": 2}
+
+
+def discounted_loss_fwd(pred, truth, gamma, epsilon, kind):
+    B, T = pred.shape[:2]
+    Cc = pred[0, 0].numel()
+    p2, t2 = pred.reshape(B * T, Cc), truth.reshape(B * T, Cc)
+    loss = torch.empty(1, device=pred.device, dtype=torch.float32)
+    check(_lib.load().rf_discounted_loss_fwd(_ptr(p2), _row_pitch(p2, "pred"), _ptr(t2), _row_pitch(t2, "truth"), B, T, Cc, float(gamma),
+                                             float(epsilon), LOSS_KINDS[kind], _ptr(loss), _stream()), "rf_discounted_loss_fwd")
+    _count()
+    return loss
+
+
+def discounted_loss_bwd(pred, truth, gamma, epsilon, kind, dloss, scale, dpred, accumulate=False):
+    B, T = pred.shape[:2]
+    Cc = pred[0, 0].numel()
+    p2, t2, d2 = pred.reshape(B * T, Cc), truth.reshape(B * T, Cc), dpred.reshape(B * T, Cc)
+    check(_lib.load().rf_discounted_loss_bwd(_ptr(p2), _row_pitch(p2, "pred"), _ptr(t2), _row_pitch(t2, "truth"), B, T, Cc, float(gamma),
+                                             float(epsilon), LOSS_KINDS[kind], _ptr(dloss), float(scale), _ptr(d2),
+                                             _row_pitch(d2, "dpred"), int(accumulate), _stream()), "rf_discounted_loss_bwd")
+    _count()
+    return dpred
+
+
+def colsum_accumulate(src: torch.Tensor, dst: torch.Tensor):
+    M, N = src.shape
+    check(_lib.load().rf_colsum_accumulate(_ptr(src), _row_pitch(src, "src"), M, N, _ptr(dst), _stream()), "rf_colsum_accumulate")
+    _count()
+    return dst
+
+
+def sumsq_accumulate(x: torch.Tensor, out: torch.Tensor):
+    check(_lib.load().rf_sumsq_accumulate(_ptr(x), x.numel(), _ptr(out), _stream()), "rf_sumsq_accumulate")
+    _count()
+    return out
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, gnorm_sq=None,
+               max_norm=0.0):
+    check(_lib.load().rf_adamw_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr), float(beta1),
+                                    float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), _ptr(gnorm_sq),
+                                    float(max_norm), _stream()), "rf_adamw_step")
+    _count()

@@ -1,0 +1,52 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/routeformer_b200.h declares."""
+import ctypes
+import os
+import re
+
+from routeformer_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "routeformer_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 28
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    # and the binding covers every declared entry point
+    bound = set(_lib.SIGNATURES) | {"rf_abi_version", "rf_last_error"}
+    assert set(names) == bound, set(names) ^ bound
+
+
+def test_abi_version_and_struct_mirrors():
+    lib = _lib.load()
+    assert lib.rf_abi_version() == 1
+    for which, struct in _lib.STRUCTS.items():
+        assert lib.rf_struct_size(which) == ctypes.sizeof(struct), struct.__name__
+    assert lib.rf_struct_size(99) == -1
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    """Validation happens before any CUDA call: a bad argument returns RF_ERR_INVALID_ARGUMENT with a message."""
+    lib = _lib.load()
+    p = _lib.RfGemmParams()
+    assert lib.rf_gemm_tf32(ctypes.byref(p), None) == -1
+    assert b"rf_gemm_tf32" in lib.rf_last_error()
+    assert lib.rf_median_downsample(None, None, 1, 10, 2, 10, None) == -1
+
+
+def test_only_sm100a_code_is_shipped():
+    import subprocess, shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        return
+    out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs

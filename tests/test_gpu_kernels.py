@@ -1,0 +1,438 @@
+"""GPU parity tests, one per C-ABI entry point: CUDA kernel (through ctypes) vs the CPU oracle / plain PyTorch.
+
+Tolerances: integer/index results bit-exact; fp32 elementwise kernels 1e-5; TF32 tensor-core GEMM 2e-3 relative
+(10-bit mantissa operands, fp32 accumulate -- SURVEY 7, hard part 7).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import routeformer_oracle as O
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from routeformer_b200 import ops as _ops
+
+    return _ops
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (300, 200, 96), (1000, 384, 1024), (70, 66, 832), (4480, 832, 200), (513, 64, 64)])
+def test_gemm_layouts(ops, a_mn, b_mn, M, N, K):
+    if (a_mn and M % 4) or (b_mn and N % 4):
+        pytest.skip("MN-major operand needs a pitch that is a multiple of 4")
+    gen = g(M + N + K)
+    A = torch.randn(M, K, generator=gen)
+    B = torch.randn(N, K, generator=gen)
+    ref = (A.double() @ B.double().t()).float()
+    Ad = (A.t().contiguous() if a_mn else A).to(DEV)
+    Bd = (B.t().contiguous() if b_mn else B).to(DEV)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(Ad, Bd, out, a_mn=a_mn, b_mn=b_mn)
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu(), ref) < 2e-3
+
+
+def test_gemm_epilogue_forward(ops):
+    gen = g(1)
+    M, N, K, period = 260, 136, 72, 65
+    A, B = torch.randn(M, K, generator=gen), torch.randn(N, K, generator=gen) / math.sqrt(K)
+    bias, pe, res = torch.randn(N, generator=gen), torch.randn(period, N, generator=gen), torch.randn(M, N, generator=gen)
+    pre_ref = (A.double() @ B.double().t()).float() + bias + pe.repeat(M // period, 1) + res
+    for act, fn in [(ops.ACT_GELU, F.gelu), (ops.ACT_RELU, F.relu), (ops.ACT_NONE, lambda x: x)]:
+        out = torch.empty(M, N, device=DEV)
+        pre = torch.empty(M, N, device=DEV)
+        ops.gemm(A.to(DEV), B.to(DEV), out, bias=bias.to(DEV), rowadd=pe.to(DEV), rowadd_period=period, residual=res.to(DEV),
+                 act=act, preact=pre)
+        assert rel_err(pre.cpu(), pre_ref) < 2e-3
+        assert rel_err(out.cpu(), fn(pre_ref)) < 2e-3
+
+
+def test_gemm_strided_rows_and_row_remap(ops):
+    gen = g(2)
+    n, K, N = 6, 96, 40
+    # A = last token of each 9-token frame: rows strided by 9*K
+    tok = torch.randn(n * 9, K, generator=gen)
+    W = torch.randn(N, K, generator=gen)
+    Ad = tok.to(DEV)
+    view = Ad.view(n, 9, K)[:, 8, :]
+    out = torch.empty(n, N, device=DEV)
+    ops.gemm(view, W.to(DEV), out)
+    assert rel_err(out.cpu(), tok.view(n, 9, K)[:, 8] @ W.t()) < 2e-3
+    # row remap: 8 rows per group in, 9 per group out (the appended "-1 token" row stays untouched)
+    A = torch.randn(n * 8, K, generator=gen)
+    buf = torch.full((n * 9, N), -1.0, device=DEV)
+    ops.gemm(A.to(DEV), W.to(DEV), buf, out_group=(8, 9, 0), round_f16=True)
+    ref = (A @ W.t()).half().float().view(n, 8, N)
+    got = buf.cpu().view(n, 9, N)
+    assert rel_err(got[:, :8], ref) < 2e-3
+    assert torch.equal(got[:, 8], torch.full((n, N), -1.0))
+    assert torch.equal(got[:, :8].half().float(), got[:, :8])  # representable in fp16
+
+
+def test_gemm_dact_and_accumulate(ops):
+    gen = g(3)
+    M, N, K = 5000, 96, 160
+    dY, X = torch.randn(M, N, generator=gen), torch.randn(M, K, generator=gen)
+    # wgrad: dW[N,K] += dY^T X, split over the long reduction, atomically accumulated
+    dW = torch.ones(N, K, device=DEV)
+    ops.gemm(dY.to(DEV), X.to(DEV), dW, a_mn=True, b_mn=True, accumulate=True)
+    assert rel_err(dW.cpu(), 1.0 + (dY.double().t() @ X.double()).float()) < 2e-3
+    # dgrad with activation derivative in the epilogue
+    W = torch.randn(N, K, generator=gen)
+    pre = torch.randn(M, K, generator=gen)
+    pg = pre.clone().requires_grad_()
+    F.gelu(pg).sum().backward()
+    for code, grad in [(ops.ACT_RELU, (pre > 0).float()), (ops.ACT_GELU, pg.grad)]:
+        out = torch.empty(M, K, device=DEV)
+        ops.gemm(dY.to(DEV), W.to(DEV), out, b_mn=True, dact=code, dact_aux=pre.to(DEV))
+        assert rel_err(out.cpu(), (dY.double() @ W.double()).float() * grad) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ FoV crop
+@pytest.mark.parametrize("H,W,S,patch", [(324, 326, 224, 28), (86, 384, 256, 32), (36, 34, 32, 8), (240, 320, 64, 0)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.uint8])
+def test_fov_crop(ops, H, W, S, patch, dtype):
+    gen = g(H + W)
+    n = 5
+    if dtype == torch.uint8:
+        frames = torch.randint(0, 256, (n + 2, 3, H, W), generator=gen, dtype=torch.uint8)
+        ref_frames = frames.float() / 255.0
+    else:
+        frames = torch.rand(n + 2, 3, H, W, generator=gen).to(dtype)
+        ref_frames = frames.float()
+    ids = torch.tensor([6, 0, 3, 3, 5], dtype=torch.int32)
+    centers = (0.5 + 0.25 * torch.randn(n, 2, generator=gen)).clamp(0, 1)
+    cx, cy, fw, fh = O.frame_window(H, W)  # the reference-like "pad to square and resize" window
+    windows = torch.tensor([[0.5, 0.5], [1.0, 1.0], [fw, fh], [0.3, 0.7], [1.4, 0.2]])
+    centers[2, 0], centers[2, 1] = cx, cy
+    spec = O.BackboneSpec()
+    ref = O.fov_crop(ref_frames[ids.long()], centers, windows, S, spec.mean, spec.std)
+    out = ops.fov_crop(frames.to(DEV), centers.to(DEV), windows.to(DEV), S, spec.mean, spec.std, patch=patch, frame_ids=ids.to(DEV))
+    got = out.cpu()
+    if patch:
+        G = S // patch
+        ref = ref.view(n, 3, G, patch, G, patch).permute(0, 2, 4, 1, 3, 5).reshape(n * G * G, 3 * patch * patch)
+    assert (got - ref).abs().max() < 2e-4
+    bf = ops.fov_crop(frames.to(DEV), centers.to(DEV), windows.to(DEV), S, spec.mean, spec.std, patch=patch, frame_ids=ids.to(DEV),
+                      out_dtype=torch.bfloat16)
+    assert (bf.float().cpu() - ref).abs().max() < 3e-2
+
+
+# ------------------------------------------------------------------------------------------------ circular conv
+@pytest.mark.parametrize("n,L,C,D,pad", [(3, 65, 48, 128, 1), (4, 40, 8, 64, 1), (2, 21, 64, 64, 2), (2, 5, 32, 32, 2), (2, 4, 32, 32, 2)])
+def test_conv3_assemble(ops, n, L, C, D, pad):
+    gen = g(L + D)
+    x = torch.randn(n, L, C, generator=gen)
+    w = torch.randn(D, C, 3, generator=gen) / math.sqrt(3 * C)
+    bias, wt = torch.randn(D, generator=gen), torch.randn(D, generator=gen)
+    L_out = L + 2 * pad - 2
+    pe = O.pe_table(L_out + 3, D)
+    xr, wr, br, wtr = x.clone().requires_grad_(), w.clone().requires_grad_(), bias.clone().requires_grad_(), wt.clone().requires_grad_()
+    t = torch.arange(L_out, dtype=torch.float32).view(1, L_out, 1)
+    ref = O.circular_conv3(xr, wr, br, pad) + pe[:L_out] + t * wtr
+    dy = torch.randn(n, L_out, D, generator=gen)
+    ref.backward(dy)
+    # CUDA: pack weight -> GEMM -> assemble
+    Cp = (C + 3) // 4 * 4
+    wcat = torch.empty(3 * D, Cp, device=DEV)
+    ops.conv3_pack_weight(w.to(DEV), wcat)
+    assert torch.equal(wcat.cpu()[:, :C].view(3, D, C), w.permute(2, 0, 1))
+    xd = torch.zeros(n * L, Cp, device=DEV)
+    xd[:, :C] = x.view(n * L, C).to(DEV)
+    z = torch.empty(n * L, 3 * D, device=DEV)
+    ops.gemm(xd, wcat, z)
+    y = torch.empty(n * L_out, D, device=DEV)
+    ops.conv3_assemble_fwd(z, y, n, L, D, pad, bias=bias.to(DEV), pe=pe.to(DEV), wtime=wt.to(DEV))
+    assert rel_err(y.cpu().view(n, L_out, D), ref.detach()) < 2e-3
+    # backward
+    dz = torch.empty(n * L, 3 * D, device=DEV)
+    dbias, dwt = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    ops.conv3_assemble_bwd(dy.view(n * L_out, D).to(DEV), dz, n, L, D, pad, dbias=dbias, dwtime=dwt)
+    assert rel_err(dbias.cpu(), br.grad) < 1e-5 and rel_err(dwt.cpu(), wtr.grad) < 1e-5
+    dx = torch.empty(n * L, Cp, device=DEV)
+    ops.gemm(dz, wcat, dx, b_mn=True)
+    assert rel_err(dx.cpu()[:, :C].reshape(n, L, C), xr.grad) < 2e-3
+    dwcat = torch.zeros(3 * D, Cp, device=DEV)
+    ops.gemm(dz, xd, dwcat, a_mn=True, b_mn=True, accumulate=True)
+    dw = torch.zeros(D, C, 3, device=DEV)
+    ops.conv3_unpack_grad(dwcat, dw)
+    assert rel_err(dw.cpu(), wr.grad) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ attention
+ATTN_CASES = [
+    # B, H, Lq, Lk, dh, factor, mode, layout
+    (6, 8, 65, 65, 16, 5, "prob", "blhd"),
+    (3, 8, 160, 160, 16, 5, "prob", "blhd"),
+    (4, 8, 40, 40, 8, 5, "prob_masked", "blhd"),
+    (3, 8, 40, 40, 104, 4, "prob", "bhld"),
+    (3, 8, 70, 70, 104, 4, "prob_masked", "bhld"),
+    (3, 8, 70, 4, 104, 4, "prob", "bhld"),
+    (2, 4, 7, 7, 16, 4, "prob", "bhld"),
+    (3, 8, 40, 30, 8, 5, "full", "blhd"),
+]
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,dh,factor,mode,layout", ATTN_CASES)
+def test_attention_forward_backward(ops, B, H, Lq, Lk, dh, factor, mode, layout):
+    gen = g(Lq * 7 + Lk + dh)
+    D = H * dh
+    # q/k/v live inside fused [rows, 3D] buffers exactly as the modules produce them
+    qkv_q = torch.randn(B * Lq, 3 * D, generator=gen)
+    qkv_k = qkv_q if Lq == Lk and mode != "full" else torch.randn(B * Lk, 3 * D, generator=gen)
+    q = qkv_q[:, :D].reshape(B, Lq, H, dh).clone().requires_grad_()
+    k = qkv_k[:, D:2 * D].reshape(B, Lk, H, dh).clone().requires_grad_()
+    v = qkv_k[:, 2 * D:].reshape(B, Lk, H, dh).clone().requires_grad_()
+    U, u = O.sparse_budget(Lk, factor), O.sparse_budget(Lq, factor)
+    groups = 3 if B % 3 == 0 else 1
+    idx = torch.randint(Lk, (groups, Lq, U), generator=gen)
+    if mode == "full":
+        ref = O.full_attention(q, k, v)  # [B,Lq,H,dh]
+        tops = None
+    else:
+        outs, tops, meas = [], [], []
+        per = B // groups
+        for gi in range(groups):
+            sl = slice(gi * per, (gi + 1) * per)
+            c, t, m = O.prob_attention(q[sl], k[sl], v[sl], idx[gi], factor, mode == "prob_masked")
+            outs.append(c), tops.append(t), meas.append(m)
+        ctx, tops, meas = torch.cat(outs), torch.cat(tops), torch.cat(meas)
+        ref = ctx.contiguous() if layout == "bhld" else ctx.transpose(1, 2).contiguous()
+    dout = torch.randn(ref.shape, generator=gen)
+    ref.backward(dout)
+
+    qd, kd = qkv_q.to(DEV), qkv_k.to(DEV)
+    qa = (qd, Lq * 3 * D, 3 * D)
+    ka = (kd[:, D:], Lk * 3 * D, 3 * D)
+    va = (kd[:, 2 * D:], Lk * 3 * D, 3 * D)
+    out = torch.full(ref.shape, float("nan"), device=DEV)
+    top = torch.zeros(B, H, max(u, 1), dtype=torch.int32, device=DEV)
+    measure = torch.empty(B, H, Lq, device=DEV)
+    code = {"prob": ops.ATTN_PROB, "prob_masked": ops.ATTN_PROB_MASKED, "full": ops.ATTN_FULL}[mode]
+    lay = ops.LAYOUT_BHLD if layout == "bhld" else ops.LAYOUT_BLHD
+    idx_d = idx.to(torch.int32).to(DEV)
+    ops.attention_fwd(qa, ka, va, B, H, Lq, Lk, dh, code, lay, idx_d, B // groups if groups > 1 else 0, U, u, out, top, measure)
+    torch.cuda.synchronize()
+    if mode != "full":
+        assert rel_err(measure.cpu(), meas) < 1e-5
+        assert torch.equal(top.cpu().long().sort(-1).values, tops.sort(-1).values)  # same selected set (index work: exact)
+    assert rel_err(out.cpu(), ref.detach()) < 1e-5
+    dqkv_q = torch.zeros_like(qd)
+    dqkv_k = dqkv_q if qkv_k is qkv_q else torch.zeros_like(kd)
+    ops.attention_bwd(qa, ka, va, B, H, Lq, Lk, dh, code, lay, U, u, top, dout.to(DEV), dqkv_q, dqkv_k[:, D:], dqkv_k[:, 2 * D:])
+    torch.cuda.synchronize()
+    assert rel_err(dqkv_q.cpu()[:, :D].reshape(B, Lq, H, dh), q.grad) < 2e-5
+    assert rel_err(dqkv_k.cpu()[:, D:2 * D].reshape(B, Lk, H, dh), k.grad) < 2e-5
+    assert rel_err(dqkv_k.cpu()[:, 2 * D:].reshape(B, Lk, H, dh), v.grad) < 2e-5
+
+
+def test_attention_forced_selection(ops):
+    B, H, L, dh, factor = 2, 4, 21, 16, 4
+    gen = g(5)
+    q, k, v = (torch.randn(B, L, H, dh, generator=gen) for _ in range(3))
+    U, u = O.sparse_budget(L, factor), O.sparse_budget(L, factor)
+    idx = torch.randint(L, (L, U), generator=gen)
+    forced = torch.stack([torch.randperm(L, generator=gen)[:u] for _ in range(B * H)]).view(B, H, u)
+    ctx, _, _ = O.prob_attention(q, k, v, idx, factor, False, forced_top=forced)
+    out = torch.empty(B, H, L, dh, device=DEV)
+    top = torch.empty(B, H, u, dtype=torch.int32, device=DEV)
+    D = H * dh
+    mk = lambda t: (t.reshape(B * L, D).to(DEV), L * D, D)
+    ops.attention_fwd(mk(q), mk(k), mk(v), B, H, L, L, dh, ops.ATTN_PROB, ops.LAYOUT_BHLD, idx.int().to(DEV), 0, U, u, out, top,
+                      forced_top=forced.int().to(DEV))
+    assert torch.equal(top.cpu().long(), forced)
+    assert rel_err(out.cpu(), ctx) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("M,D", [(1000, 128), (77, 64), (300, 832), (33, 30)])
+def test_layernorm(ops, M, D):
+    gen = g(M + D)
+    x = (torch.randn(M, D, generator=gen) * 3 + 1).requires_grad_()
+    gamma, beta = (1 + 0.1 * torch.randn(D, generator=gen)).requires_grad_(), torch.randn(D, generator=gen).requires_grad_()
+    ref = F.layer_norm(x, (D,), gamma, beta, 1e-5)
+    dy = torch.randn(M, D, generator=gen)
+    ref.backward(dy)
+    y, mean, rstd = torch.empty(M, D, device=DEV), torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    xd, gd, bd = x.detach().to(DEV), gamma.detach().to(DEV), beta.detach().to(DEV)
+    ops.layernorm_fwd(xd, gd, bd, y, mean, rstd)
+    assert (y.cpu() - ref.detach()).abs().max() < 2e-5
+    dx, dg, db = torch.empty(M, D, device=DEV), torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    ops.layernorm_bwd(dy.to(DEV), xd, gd, mean, rstd, dx, dg, db)
+    assert rel_err(dx.cpu(), x.grad) < 1e-5 and rel_err(dg.cpu(), gamma.grad) < 1e-5 and rel_err(db.cpu(), beta.grad) < 1e-5
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("B,Lz,D", [(4, 42, 64), (3, 23, 832), (5, 7, 32), (2, 6, 32)])
+def test_distil_tail(ops, B, Lz, D, training):
+    gen = g(B + Lz + D)
+    z = torch.randn(B, Lz, D, generator=gen).requires_grad_()
+    gamma, beta = (1 + 0.1 * torch.randn(D, generator=gen)).requires_grad_(), (0.1 * torch.randn(D, generator=gen)).requires_grad_()
+    rm, rv = 0.1 * torch.randn(D, generator=gen), 0.5 + torch.rand(D, generator=gen)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    zt = F.batch_norm(z.transpose(1, 2), rm_ref, rv_ref, gamma, beta, training, 0.1, 1e-5)
+    ref = F.max_pool1d(F.elu(zt), 3, 2, 1).transpose(1, 2)
+    Lp = ref.shape[1]
+    dout = torch.randn(B, Lp, D, generator=gen)
+    ref.backward(dout)
+    zd, gd, bd, rmd, rvd = z.detach().to(DEV), gamma.detach().to(DEV), beta.detach().to(DEV), rm.to(DEV), rv.to(DEV)
+    mean, rstd = torch.empty(D, device=DEV), torch.empty(D, device=DEV)
+    out, arg = torch.empty(B * Lp, D, device=DEV), torch.empty(B * Lp, D, dtype=torch.int8, device=DEV)
+    ops.distil_fwd(zd.view(B * Lz, D), B, Lz, D, gd, bd, rmd, rvd, training, mean, rstd, out, arg)
+    assert (out.cpu().view(B, Lp, D) - ref.detach()).abs().max() < 2e-5
+    assert torch.allclose(rmd.cpu(), rm_ref, atol=1e-5) and torch.allclose(rvd.cpu(), rv_ref, atol=1e-5)
+    dz, dg, db = torch.empty(B * Lz, D, device=DEV), torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    ops.distil_bwd(zd.view(B * Lz, D), B, Lz, D, gd, bd, mean, rstd, training, arg, dout.view(B * Lp, D).to(DEV), dz, dg, db,
+                   torch.empty(2 * D, device=DEV))
+    assert rel_err(dz.cpu().view(B, Lz, D), z.grad) < 2e-4
+    assert rel_err(dg.cpu(), gamma.grad) < 1e-4 and rel_err(db.cpu(), beta.grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ glue
+@pytest.mark.parametrize("rotate,normalize", [(False, False), (True, False), (False, True), (True, True)])
+def test_motion_features_and_decode(ops, rotate, normalize):
+    gen = g(11)
+    B, T, E, P = 7, 40, 64, 30
+    gps = torch.cumsum(1.83 + 0.91 * torch.randn(B, T, 2, generator=gen), 1)
+    visual = torch.randn(B, T, E, generator=gen)
+    mean, std = 1.83, 0.91
+    motion = gps[:, 1:] - gps[:, :-1]
+    if normalize:
+        motion = (motion - mean) / std
+    motion = F.pad(motion, (0, 0, 1, 0))
+    feats, origin = O.motion_features(motion, rotate)
+    ld = 72
+    x = torch.full((B, T, ld), float("nan"), device=DEV)
+    org = torch.empty(B, device=DEV)
+    ops.motion_features(gps.to(DEV), visual.to(DEV), x, org, E, rotate, normalize, mean, std)
+    got = x.cpu()
+    assert (got[:, :, :5] - feats).abs().max() < 2e-5
+    assert torch.equal(got[:, :, 5:5 + E], visual) and torch.equal(got[:, :, 5 + E:], torch.zeros(B, T, ld - 5 - E))
+    assert (org.cpu() - origin.view(B)).abs().max() < 1e-6
+    # decode
+    out = torch.randn(B, P, 68, generator=gen).requires_grad_()
+    o = out[:, :, :66]
+    if rotate:
+        o = torch.cat([O.rotate2d(o[:, :, :2], origin), o[:, :, 2:]], -1)
+    mv = o[:, :, :2]
+    if normalize:
+        mv = mv * std + mean
+    wp = gps[:, -1:, :] + torch.cumsum(mv, 1)
+    dwp = torch.randn(B, P, 2, generator=gen)
+    wp.backward(dwp)
+    wpd, mvd = torch.empty(B, P, 2, device=DEV), torch.empty(B, P, 2, device=DEV)
+    ops.decode_waypoints_fwd(out.detach().to(DEV), org, gps[:, -1, :].contiguous().to(DEV), wpd, mvd, rotate, normalize, mean, std)
+    assert rel_err(wpd.cpu(), wp.detach()) < 1e-6 and rel_err(mvd.cpu(), mv.detach()) < 1e-5
+    dout = torch.zeros(B, P, 68, device=DEV)
+    ops.decode_waypoints_bwd(dwp.to(DEV), org, dout, rotate, normalize, std)
+    assert rel_err(dout.cpu(), out.grad) < 1e-5
+
+
+@pytest.mark.parametrize("smart", [True, False])
+def test_decoder_input(ops, smart):
+    gen = g(12)
+    B, T, P, ld = 5, 40, 30, 72
+    x = torch.randn(B, T, ld, generator=gen).requires_grad_()
+    ref = torch.cat([x, x[:, -1:].repeat(1, P, 1) if smart else torch.zeros(B, P, ld)], 1)
+    d = torch.randn(B, T + P, ld, generator=gen)
+    ref.backward(d)
+    xdec = torch.empty(B, T + P, ld, device=DEV)
+    ops.decoder_input_fwd(x.detach().to(DEV), xdec, P, smart)
+    assert torch.equal(xdec.cpu(), ref.detach())
+    dx = torch.ones(B, T, ld, device=DEV)
+    ops.decoder_input_bwd(d.to(DEV), dx, P, smart)
+    assert rel_err(dx.cpu(), 1 + x.grad) < 1e-6
+
+
+def test_stream_tokens(ops):
+    gen = g(13)
+    B, T, E, F_ = 4, 40, 32, 8
+    idx = O.frame_indices(T, 5)
+    left = torch.randn(B, F_, E, generator=gen).requires_grad_()
+    gaze = torch.randn(B, T, E, generator=gen).requires_grad_()
+    el, eg, eo = (torch.randn(1, 1, E, generator=gen).requires_grad_() for _ in range(3))
+    full = torch.zeros(B, T, E).index_copy(1, idx, left)
+    tokens = torch.cat([full + el, gaze + eg, torch.zeros(B, T, E) + eo], 1)
+    d = torch.randn(B, 3 * T, E, generator=gen)
+    tokens.backward(d)
+    tok = torch.full((B, 3 * T, E), float("nan"), device=DEV)
+    first, step = int(idx[0]), int(idx[1] - idx[0])
+    ops.stream_tokens_fwd(left.detach().to(DEV), F_, first, step, False, el.detach().view(E).to(DEV), tok, B, T, E, 3 * T, 0)
+    ops.stream_tokens_fwd(gaze.detach().to(DEV), 0, 0, 1, True, eg.detach().view(E).to(DEV), tok, B, T, E, 3 * T, T)
+    ops.stream_tokens_fwd(None, 0, 0, 1, False, eo.detach().view(E).to(DEV), tok, B, T, E, 3 * T, 2 * T)
+    assert torch.equal(tok.cpu(), tokens.detach())
+    dd = d.to(DEV)
+    dleft, dgaze = torch.empty(B, F_, E, device=DEV), torch.empty(B, T, E, device=DEV)
+    del_, deg, deo = (torch.zeros(E, device=DEV) for _ in range(3))
+    ops.stream_tokens_bwd(dd, dleft, F_, first, step, False, del_, B, T, E, 3 * T, 0)
+    ops.stream_tokens_bwd(dd, dgaze, 0, 0, 1, True, deg, B, T, E, 3 * T, T)
+    ops.stream_tokens_bwd(dd, None, 0, 0, 1, False, deo, B, T, E, 3 * T, 2 * T)
+    assert torch.equal(dleft.cpu(), left.grad) and torch.equal(dgaze.cpu(), gaze.grad)
+    for got, ref in ((del_, el), (deg, eg), (deo, eo)):
+        assert rel_err(got.cpu(), ref.grad.view(E)) < 1e-5
+
+
+def test_median_metrics_loss(ops):
+    gen = g(14)
+    x = torch.randn(6, 1600, 2, generator=gen)
+    assert torch.equal(ops.median_downsample(x.to(DEV), 40).cpu(), O.median_downsample(x, 40))
+    x2 = torch.randn(3, 83, 2, generator=gen)
+    assert torch.equal(ops.median_downsample(x2.to(DEV), 20).cpu(), O.median_downsample(x2, 20))
+    assert torch.equal(ops.median_downsample(x2[:, :80].contiguous().to(DEV), 40).cpu(), O.median_downsample(x2[:, :80], 40))
+    with pytest.raises(Exception):
+        ops.median_downsample(x2.to(DEV), 83)
+    p, t = torch.randn(9, 30, 2, generator=gen) * 3, torch.randn(9, 30, 2, generator=gen)
+    res, ps = ops.ade_fde(p.to(DEV), t.to(DEV), per_sample=True)
+    assert abs(res[0].item() - O.ade(p, t).item()) < 1e-5 and abs(res[1].item() - O.fde(p, t).item()) < 1e-4
+    for b in range(9):
+        assert abs(ps[b, 0].item() - O.ade(p[b:b + 1], t[b:b + 1]).item()) < 1e-5
+        assert abs(ps[b, 1].item() - O.fde(p[b:b + 1], t[b:b + 1]).item()) < 1e-4
+    pred, truth = (torch.randn(5, 30, 66, generator=gen) * 2).requires_grad_(), torch.randn(5, 30, 66, generator=gen)
+    for kind, eps in (("smooth_l1", 1.0), ("mse", 0.3), ("mae", 0.3)):
+        pred.grad = None
+        ref = O.future_discounted_loss(pred, truth, 0.97, kind, eps)
+        (ref * 1.7).backward()
+        loss = ops.discounted_loss_fwd(pred.detach().to(DEV), truth.to(DEV), 0.97, eps, kind)
+        assert abs(loss.item() - ref.item()) < 1e-5 * max(1, abs(ref.item()))
+        dp = torch.empty(5, 30, 66, device=DEV)
+        ops.discounted_loss_bwd(pred.detach().to(DEV), truth.to(DEV), 0.97, eps, kind, torch.tensor([1.7], device=DEV), 1.0, dp)
+        assert rel_err(dp.cpu(), pred.grad) < 1e-5
+
+
+def test_reductions_and_adamw(ops):
+    gen = g(15)
+    src = torch.randn(3000, 200, generator=gen)
+    dst = torch.ones(200, device=DEV)
+    ops.colsum_accumulate(src.to(DEV), dst)
+    assert rel_err(dst.cpu(), 1 + src.double().sum(0).float()) < 1e-5
+    acc = torch.zeros(1, device=DEV)
+    ops.sumsq_accumulate(src.to(DEV), acc)
+    assert abs(acc.item() / (src.double() ** 2).sum().item() - 1) < 1e-5
+    n = 10007
+    p0, g0 = torch.randn(n, generator=gen), torch.randn(n, generator=gen) * 5
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    pd, m, v = p0.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        grad = g0 * step
+        ref_p.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 2.5)
+        opt.step()
+        gn = torch.zeros(1, device=DEV)
+        gd = grad.to(DEV)
+        ops.sumsq_accumulate(gd, gn)
+        ops.adamw_step(pd, gd, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-2, step, 1.0, gn, 2.5)
+        assert rel_err(pd.cpu(), ref_p.detach()) < 1e-5
