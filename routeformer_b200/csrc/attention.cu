@@ -266,13 +266,13 @@ static size_t bwd_smem(const RfAttnParams* p) {
   return fwd_smem(p) + sizeof(float) * (static_cast<size_t>(p->Lq) * pitch + static_cast<size_t>(u) * p->Lk);
 }
 
-static int validate(const RfAttnParams* p, const char* who) {
+static int validate(const RfAttnParams* p, const char* who, bool forward) {
   RF_CHECK_ARG(p->q && p->k && p->v, "%s: null q/k/v", who);
   RF_CHECK_ARG(p->B > 0 && p->H > 0 && p->Lq > 0 && p->Lk > 0 && p->dh > 0, "%s: bad shape", who);
   RF_CHECK_ARG(p->mode >= 0 && p->mode <= 2, "%s: bad mode %d", who, p->mode);
   if (p->mode != RF_ATTN_FULL) {
     RF_CHECK_ARG(p->u > 0 && p->u <= p->Lq && p->U > 0 && p->U <= p->Lk, "%s: bad budgets u=%d U=%d", who, p->u, p->U);
-    RF_CHECK_ARG(p->idx || p->forced_top, "%s: idx table missing", who);
+    RF_CHECK_ARG(!forward || p->idx || p->forced_top, "%s: idx table missing", who);
     RF_CHECK_ARG(p->top, "%s: top buffer missing", who);
   }
   RF_CHECK_ARG(p->mode != RF_ATTN_PROB_MASKED || p->Lq == p->Lk, "%s: masked ProbSparse attention requires Lq == Lk", who);
@@ -286,7 +286,7 @@ static int validate(const RfAttnParams* p, const char* who) {
 extern "C" int rf_attention_fwd(const RfAttnParams* p, void* stream) {
   using namespace rf;
   RF_CHECK_ARG(p && p->out, "rf_attention_fwd: null pointer");
-  int rc = attn::validate(p, "rf_attention_fwd");
+  int rc = attn::validate(p, "rf_attention_fwd", true);
   if (rc != RF_OK) return rc;
   const size_t smem = attn::fwd_smem(p);
   RF_CHECK_ARG(smem <= 220 * 1024, "rf_attention_fwd: problem needs %zu B of shared memory (> 220 KiB)", smem);
@@ -303,7 +303,7 @@ extern "C" int rf_attention_fwd(const RfAttnParams* p, void* stream) {
 extern "C" int rf_attention_bwd(const RfAttnBwdParams* p, void* stream) {
   using namespace rf;
   RF_CHECK_ARG(p && p->dout && p->dq && p->dk && p->dv, "rf_attention_bwd: null pointer");
-  int rc = attn::validate(&p->f, "rf_attention_bwd");
+  int rc = attn::validate(&p->f, "rf_attention_bwd", false);
   if (rc != RF_OK) return rc;
   const size_t smem = attn::bwd_smem(&p->f);
   RF_CHECK_ARG(smem <= 220 * 1024, "rf_attention_bwd: problem needs %zu B of shared memory (> 220 KiB)", smem);

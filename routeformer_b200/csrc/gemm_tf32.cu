@@ -129,18 +129,20 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Shared-memory matrix descriptor (SWIZZLE_128B, Blackwell version 1).
-//  K-major : rows of 128 B (32 tf32 along K); 8-row groups SBO = 1024 B apart; LBO unused (encoded 1).
-//  MN-major: 128 B = 32 elements along M/N; the 8 k-rows of one MMA are 128 B apart (one swizzle atom);
-//            LBO = stride between 32-element M/N groups (one TMA box = 4096 B), SBO = stride between
-//            8-row k groups (1024 B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (Blackwell version 1).
+//  K-major : SWIZZLE_128B (TMA SWIZZLE_128B).  Rows of 128 B (32 tf32 along K); 8-row groups SBO = 1024 B
+//            apart; LBO unused (encoded 1).
+//  MN-major: for 32-bit operands the only legal layout is SWIZZLE_128B_BASE32B (Swizzle<2,5,2>: 32 B chunks
+//            XOR-ed over 4-row atoms; TMA SWIZZLE_128B_ATOM_32B writes exactly this).  128 B = 32 elements
+//            along M/N; consecutive k-rows are 128 B apart; SBO = stride between 4-row k atoms (512 B),
+//            LBO = stride between 32-element M/N groups (one TMA box = 32 rows x 128 B = 4096 B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version (sm_100)
-  d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout_type) << 61;  // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -227,10 +229,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t b_base = a_base + A_BYTES;
 #pragma unroll
         for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-          const uint64_t adesc = a.a_mn ? make_smem_desc(a_base + kk * 1024, GROUP_BYTES, 1024)
-                                        : make_smem_desc(a_base + kk * UMMA_K * 4, 16, 1024);
-          const uint64_t bdesc = a.b_mn ? make_smem_desc(b_base + kk * 1024, GROUP_BYTES, 1024)
-                                        : make_smem_desc(b_base + kk * UMMA_K * 4, 16, 1024);
+          const uint64_t adesc = a.a_mn ? make_smem_desc(a_base + kk * 1024, GROUP_BYTES, 512, 1)
+                                        : make_smem_desc(a_base + kk * UMMA_K * 4, 16, 1024, 2);
+          const uint64_t bdesc = a.b_mn ? make_smem_desc(b_base + kk * 1024, GROUP_BYTES, 512, 1)
+                                        : make_smem_desc(b_base + kk * UMMA_K * 4, 16, 1024, 2);
           umma_tf32(tmem_base, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
@@ -327,7 +329,7 @@ static bool tf32_round_in_tma() {
 }
 
 // 2-D fp32 tensor map: dim0 = `inner` contiguous elements, dim1 = `outer` rows of pitch ld; box = 32 x box_rows.
-static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_rows) {
+static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_rows, bool mn_major) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -339,7 +341,8 @@ static int make_map(CUtensorMap* map, const float* base, long long inner, long l
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, tf32_round_in_tma() ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%lld outer=%lld ld=%lld box_rows=%d", static_cast<int>(r),
               static_cast<const void*>(base), inner, outer, ld, box_rows);
@@ -353,11 +356,11 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
   using T = Tile<BLOCK_N>;
   CUtensorMap tmA, tmB;
   int rc;
-  if (!p->a_mn_major) rc = make_map(&tmA, p->A, p->K, p->M, p->lda, BLOCK_M);
-  else rc = make_map(&tmA, p->A, p->M, p->K, p->lda, 32);
+  if (!p->a_mn_major) rc = make_map(&tmA, p->A, p->K, p->M, p->lda, BLOCK_M, false);
+  else rc = make_map(&tmA, p->A, p->M, p->K, p->lda, 32, true);
   if (rc != RF_OK) return rc;
-  if (!p->b_mn_major) rc = make_map(&tmB, p->B, p->K, p->N, p->ldb, BLOCK_N);
-  else rc = make_map(&tmB, p->B, p->N, p->K, p->ldb, 32);
+  if (!p->b_mn_major) rc = make_map(&tmB, p->B, p->K, p->N, p->ldb, BLOCK_N, false);
+  else rc = make_map(&tmB, p->B, p->N, p->K, p->ldb, 32, true);
   if (rc != RF_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {

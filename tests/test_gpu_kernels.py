@@ -125,7 +125,9 @@ def test_fov_crop(ops, H, W, S, patch, dtype):
     if patch:
         G = S // patch
         ref = ref.view(n, 3, G, patch, G, patch).permute(0, 2, 4, 1, 3, 5).reshape(n * G * G, 3 * patch * patch)
-    assert (got - ref).abs().max() < 2e-4
+    # white-noise frames are the worst case: |dI/dx| ~ 1/std per pixel, so a 1e-4 px difference in the fp32
+    # sample position (ATen builds the grid with linspace + matmul) moves the value by ~5e-4
+    assert (got - ref).abs().max() < 1e-3 and (got - ref).abs().mean() < 2e-5
     bf = ops.fov_crop(frames.to(DEV), centers.to(DEV), windows.to(DEV), S, spec.mean, spec.std, patch=patch, frame_ids=ids.to(DEV),
                       out_dtype=torch.bfloat16)
     assert (bf.float().cpu() - ref).abs().max() < 3e-2
