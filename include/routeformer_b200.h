@@ -208,10 +208,12 @@ int rf_distil_bwd(const RfDistilBwdParams* p, void* stream);
 /* replaces: routeformer.py:279-292 (first difference, normalise, zero pad) + :209-235 (angle, norm,
  * acceleration, optional rotation, concat with the visual features).  gps [B,T,2] -> x [B,T,ldx]:
  * cols 0..4 motion features, cols 5..5+E-1 visual (copied from `visual` [B,T,E], or zeros if NULL/only_motion),
- * remaining cols (padding up to ldx) zero.  origin [B] receives the per-clip origin angle. */
+ * remaining cols (padding up to ldx) zero.  origin [B] receives the per-clip origin angle.
+ * input_is_motion=1: `gps` already holds the motion dynamics [B,T,2] (differenced, normalised, zero row first) --
+ * the autoregressive re-entry of routeformer.py:176-190. */
 int rf_motion_features(const float* gps, const float* visual, long long ld_vis, float* x, long long ldx,
                        float* origin, int B, int T, int E, int rotate, int normalize, float mean, float std,
-                       void* stream);
+                       int input_is_motion, void* stream);
 /* replaces: gps_backbone/Informer.py:125-149. x [B,T,ld] -> xdec [B,T+P,ld]; smart: repeat last row, else zeros */
 int rf_decoder_input_fwd(const float* x, float* xdec, int B, int T, int P, long long ld, int smart, void* stream);
 int rf_decoder_input_bwd(const float* dxdec, float* dx, int B, int T, int P, long long ld, int smart, void* stream); /* dx += */

@@ -122,25 +122,24 @@ class CpuRandint:
 class Replay:
     """Replays a pre-drawn list of index tensors in order (shape-checked)."""
 
-    def __init__(self, tensors: List[Tensor], tops: Optional[List[Tensor]] = None):
+    def __init__(self, tensors: List[Tensor], tops=None):
         self.tensors = list(tensors)
         self.pos = 0
-        self.tops = None if tops is None else list(tops)
+        self.tops = tops if (tops is None or isinstance(tops, dict)) else list(tops)
         self.top_pos = 0
 
-    def next_top(self) -> Optional[Tensor]:
-        """Forced top-u selection for the next ProbSparse call (test hook, see prob_attention)."""
+    def next_top(self, where: str = "") -> Optional[Tensor]:
+        """Forced top-u selection for the next ProbSparse call (test hook, see prob_attention).
+
+        ``tops`` is either a list consumed in call order or a dict {module path: [tensor, ...]} consumed per path."""
         if self.tops is None:
             return None
-        t = self.tops[self.top_pos]
-        self.top_pos += 1
+        if isinstance(self.tops, dict):
+            t = self.tops[where].pop(0)
+        else:
+            t = self.tops[self.top_pos]
+            self.top_pos += 1
         return t.long().cpu()
-
-    def __call__(self, L_K: int, L_Q: int, U: int) -> Tensor:
-        idx = self.tensors[self.pos]
-        self.pos += 1
-        assert tuple(idx.shape) == (L_Q, U) and int(idx.max()) < L_K
-        return idx.long().cpu()
 
 
 # --------------------------------------------------------------------------------------
@@ -283,7 +282,7 @@ def attention_layer(
         out = full_attention(q, k, v)
     else:
         idx = draw(S, L, sparse_budget(S, factor))
-        forced = draw.next_top() if hasattr(draw, "next_top") else None
+        forced = draw.next_top(p) if hasattr(draw, "next_top") else None
         ctx, top, measure = prob_attention(q, k, v, idx, factor, kind == "prob_masked", forced)
         if tops is not None:
             tops.append({"where": p, "top": top, "measure": measure.detach()})

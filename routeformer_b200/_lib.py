@@ -111,7 +111,7 @@ SIGNATURES = {
     "rf_layernorm_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _L, _P, _P, _I, _I, _P],
     "rf_distil_fwd": [C.POINTER(RfDistilParams), _P],
     "rf_distil_bwd": [C.POINTER(RfDistilBwdParams), _P],
-    "rf_motion_features": [_P, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _F, _P],
+    "rf_motion_features": [_P, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _F, _I, _P],
     "rf_decoder_input_fwd": [_P, _P, _I, _I, _I, _L, _I, _P],
     "rf_decoder_input_bwd": [_P, _P, _I, _I, _I, _L, _I, _P],
     "rf_stream_tokens_fwd": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P],

@@ -125,12 +125,17 @@ __global__ void unpack_grad_kernel(const float* __restrict__ dwcat, float* __res
 // ---------------------------------------------------------------------------------------------
 __global__ void motion_features_kernel(const float* __restrict__ gps, const float* __restrict__ visual, long long ld_vis,
                                        float* __restrict__ x, long long ldx, float* __restrict__ origin, int T, int E,
-                                       int rotate, int normalize, float mean, float inv_std) {
+                                       int rotate, int normalize, float mean, float inv_std, int input_is_motion) {
   const int b = blockIdx.x;
   const float* g = gps + static_cast<long long>(b) * T * 2;
   float* xb = x + static_cast<long long>(b) * T * ldx;
   __shared__ float s_origin;
   auto motion = [&](int t, float& mx, float& my) {
+    if (input_is_motion) {  // already differenced / normalised / zero-padded (autoregressive re-entry, routeformer.py:176-190)
+      if (t < 0) { mx = 0.f; my = 0.f; return; }
+      mx = g[2 * t]; my = g[2 * t + 1];
+      return;
+    }
     if (t <= 0) { mx = 0.f; my = 0.f; return; }
     mx = g[2 * t] - g[2 * t - 2];
     my = g[2 * t + 1] - g[2 * t - 1];
@@ -491,10 +496,11 @@ extern "C" int rf_conv3_unpack_grad(const float* dwcat, float* dw, int D, int C,
 }
 
 extern "C" int rf_motion_features(const float* gps, const float* visual, long long ld_vis, float* x, long long ldx, float* origin,
-                                  int B, int T, int E, int rotate, int normalize, float mean, float std, void* stream) {
+                                  int B, int T, int E, int rotate, int normalize, float mean, float std, int input_is_motion,
+                                  void* stream) {
   RF_CHECK_ARG(gps && x && origin && B > 0 && T > 0 && ldx >= 5 + (visual ? E : 0), "rf_motion_features: bad arguments");
   motion_features_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(gps, visual, ld_vis, x, ldx, origin, T, E, rotate, normalize,
-                                                                          mean, 1.0f / std);
+                                                                          mean, 1.0f / std, input_is_motion);
   RF_LAUNCH_OK();
   return RF_OK;
 }

@@ -394,11 +394,11 @@ class MotionFeatures(Function):
     """gps [B,T,2] (+ visual [B,T,E]) -> Informer input [B,T,ld] and the per-clip origin angle (routeformer.py:209-235,279-292)."""
 
     @staticmethod
-    def forward(ctx, gps, visual, E, ld, rotate, normalize, mean, std, zero_visual):
+    def forward(ctx, gps, visual, E, ld, rotate, normalize, mean, std, zero_visual, input_is_motion):
         B, T, _ = gps.shape
         x = torch.empty(B, T, ld, device=gps.device, dtype=torch.float32)
         origin = torch.empty(B, device=gps.device, dtype=torch.float32)
-        ops.motion_features(gps, None if zero_visual else visual, x, origin, E, rotate, normalize, mean, std)
+        ops.motion_features(gps, None if zero_visual else visual, x, origin, E, rotate, normalize, mean, std, input_is_motion)
         ctx.E = E
         ctx.zero_visual = zero_visual
         ctx.mark_non_differentiable(origin)
@@ -409,7 +409,7 @@ class MotionFeatures(Function):
         dvis = None
         if ctx.needs_input_grad[1] and not ctx.zero_visual:
             dvis = dx[:, :, 5:5 + ctx.E].contiguous()
-        return None, dvis, None, None, None, None, None, None, None
+        return None, dvis, None, None, None, None, None, None, None, None
 
 
 class DecoderInput(Function):

@@ -237,11 +237,11 @@ def distil_bwd(z, B, Lz, D, gamma, beta, mean, rstd, training, argmax, dout, dz,
     return dz
 
 
-def motion_features(gps, visual, x, origin, E, rotate, normalize, mean, std):
+def motion_features(gps, visual, x, origin, E, rotate, normalize, mean, std, input_is_motion=False):
     B, T, _ = gps.shape
     ld_vis = visual.stride(1) if visual is not None else 0
     check(_lib.load().rf_motion_features(_ptr(gps), _ptr(visual), ld_vis, _ptr(x), x.stride(1), _ptr(origin), B, T, E, int(rotate),
-                                         int(normalize), float(mean), float(std), _stream()), "rf_motion_features")
+                                         int(normalize), float(mean), float(std), int(input_is_motion), _stream()), "rf_motion_features")
     _count()
     return x
 

@@ -1,0 +1,378 @@
+"""Routeformer on the CUDA library -- drop-in for routeformer/models/routeformer.py:20-533.
+
+Same constructor (`Routeformer(configs, gps_backbone=Informer, video_backbone=None)`), same public methods
+(`forward`, `preprocess_batch`, `postprocess_batch`), same sub-module names and state_dict layout, same CPU-RNG
+consumption (ProbSparse key sampling with torch.randint, view/gaze dropout with torch.rand) in the same order.
+
+What is different underneath:
+  * all CPU random draws of a forward are made up-front, in reference order, and uploaded with ONE copy;
+  * the three camera views (right, left, front) share the frame encoder, so their frames are encoded in ONE
+    batched pass (per-view sampled-key tables are kept apart through the kernel's `idx_group`);
+  * the visual backbone runs as FoV-crop kernel -> tcgen05 patch-embedding GEMM writing the token buffer of
+    the frame encoder directly (no permute / cat / scatter copies).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Type
+
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+from . import ops
+from .backbone import PatchEmbedBackbone, VideoBackboneModule
+from .config import RouteformerConfig
+from .informer import Informer
+from .layers import LiveIndexSource, PerceiveDecoder, PerceiveEncoder, PlannedIndexSource, sparse_budget
+
+
+def frame_indices(T: int, rel: int) -> torch.Tensor:
+    """Sub-sampled frame times: every `rel`-th frame counted back from the last one, frame 0 excluded (routeformer.py:415-419)."""
+    return torch.flip(torch.arange(T - 1, 0, -rel).long(), dims=[0])
+
+
+class Routeformer(nn.Module):
+    current_epoch = 0  # LightningModule attribute read by callers / backbones
+
+    def __init__(self, configs: RouteformerConfig, gps_backbone: Optional[Type[nn.Module]] = Informer,
+                 video_backbone: Optional[Type[VideoBackboneModule]] = None):
+        super().__init__()
+        self.configs = configs.copy()
+        c = self.configs
+        self.with_video = c.with_video if c.with_video is not None else video_backbone is not None
+        self.with_scene = c.with_scene
+        self.with_gaze = c.with_gaze
+        if not self.with_video and self.with_gaze:
+            raise ValueError("Current gaze backbone requires a video backbone, but video backbone is not provided.")
+        if self.with_video:
+            self.video_backbone = video_backbone(configs=c.video_backbone_config)
+            E = c.image_embedding_size
+            self.frame_encoder = PerceiveEncoder(
+                in_channels=self.video_backbone.output_feature_shape[0], out_len=1, out_channels=E, n_heads=c.encoder_heads,
+                layers=c.encoder_layers, d_ff=c.encoder_d_ff, dropout=c.feature_dropout)
+            self.left_video_embedding = nn.Parameter(torch.randn(1, 1, E))
+            self.right_video_embedding = nn.Parameter(torch.randn(1, 1, E))
+            self.gaze_video_embedding = nn.Parameter(torch.randn(1, 1, E))
+            self.video_output_embedding = nn.Parameter(torch.randn(1, 1, E))
+            self.video_encoder = PerceiveEncoder(
+                in_channels=E, out_len=c.gps_backbone_config.seq_len, out_channels=c.encoder_hidden_size, n_heads=c.encoder_heads,
+                layers=c.encoder_layers, d_ff=c.encoder_d_ff, dropout=c.feature_dropout)
+            if self.with_gaze:
+                self.gaze_encoder = PerceiveEncoder(
+                    in_channels=2, out_len=c.gps_backbone_config.seq_len, out_channels=c.encoder_hidden_size, n_heads=c.encoder_heads,
+                    layers=c.encoder_layers, d_ff=c.encoder_d_ff, dropout=c.feature_dropout)
+                self.gaze_video_decoder = PerceiveDecoder(
+                    query_channels=c.encoder_hidden_size, value_channels=c.encoder_hidden_size, out_channels=c.encoder_hidden_size,
+                    out_len=c.gps_backbone_config.seq_len, dropout=c.feature_dropout, d_ff=c.encoder_d_ff,
+                    n_heads=c.cross_modal_decoder_heads, layers=c.cross_modal_decoder_layers, mix=False)
+        self.gps_backbone = gps_backbone(configs=c.gps_backbone_config)
+        self.view_dropout = c.view_dropout
+        self.motion_noise = c.motion_noise
+        self.gaze_dropout = c.gaze_dropout
+        self.feature_dropout = c.feature_dropout
+        # test hook: when set to a list, every ProbSparse call appends {"where", "top", "measure"} (the oracle replays them)
+        self.record_tops: Optional[list] = None
+        self.last_draw_log: List[tuple] = []
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    # ------------------------------------------------------------------------------------------
+    # CPU-RNG plan: every torch.rand / torch.randint of one preprocess+forward, in reference order
+    # ------------------------------------------------------------------------------------------
+    def _plan_visual(self, batch, training: bool) -> dict:
+        c = self.configs
+        plan = {"drop_left": False, "drop_right": False, "drop_gaze": False, "entries": {}}
+        draws: List[torch.Tensor] = []
+        log: List[tuple] = []
+
+        def draw(L_K, L_Q):
+            U = sparse_budget(L_K, self.frame_encoder.encoder.attn_layers[0].attention.inner_attention.factor)
+            t = torch.randint(L_K, (L_Q, U))
+            draws.append(t)
+            log.append((L_K, L_Q, U))
+            return len(draws) - 1
+
+        n_layers = c.encoder_layers
+        S = self.video_backbone.output_feature_shape[1] * self.video_backbone.output_feature_shape[2] + 1
+        frame_sets = {}
+        n_streams = 1
+        if self.with_scene:
+            left = batch["left_video"]
+            has_right = "right_video" in batch
+            drop_left = drop_right = False
+            if self.view_dropout > 0.0 and training:  # routeformer.py:405-410
+                one = bool(torch.rand(1) < self.view_dropout)
+                drop_left = one and bool(torch.rand(1) < 0.5)
+                drop_right = (one and not drop_left) or not has_right
+            else:
+                drop_right = not has_right
+            plan["drop_left"], plan["drop_right"] = drop_left and training, drop_right and training
+            if not plan["drop_right"]:  # RIGHT is encoded before LEFT (routeformer.py:427-428)
+                frame_sets["right"] = [draw(S, S) for _ in range(n_layers)]
+            if not plan["drop_left"]:
+                frame_sets["left"] = [draw(S, S) for _ in range(n_layers)]
+            T_vid = left.shape[1]
+            n_streams += 2
+        if self.with_gaze:
+            if self.gaze_dropout > 0.0 and training:  # routeformer.py:300-301
+                plan["drop_gaze"] = bool(torch.rand(1) < self.gaze_dropout)
+            T_vid = batch["front_video"].shape[1]
+            n_streams += 1
+            if not plan["drop_gaze"]:
+                frame_sets["front"] = [draw(S, S) for _ in range(n_layers)]
+                Lg = c.gps_backbone_config.seq_len
+                plan["entries"]["gaze_encoder"] = [draw(Lg, Lg) for _ in range(n_layers)]
+                plan["entries"]["gaze_video_decoder"] = [draw(Lg, Lg) for _ in range(c.cross_modal_decoder_layers)]
+        Lv = n_streams * T_vid
+        plan["entries"]["video_encoder"] = [draw(Lv, Lv) for _ in range(n_layers)]
+        plan["frame_sets"], plan["draws"], plan["log"], plan["T_vid"] = frame_sets, draws, log, T_vid
+        return plan
+
+    def _plan_backbone(self, T: int, P: int):
+        """Informer draws: encoder layers over the distilled lengths, decoder self, decoder cross."""
+        gb = self.gps_backbone
+        if not isinstance(gb, Informer):
+            return [], []
+        f = gb.encoder.attn_layers[0].attention.inner_attention.factor
+        draws, log = [], []
+
+        def draw(L_K, L_Q):
+            U = sparse_budget(L_K, f)
+            draws.append(torch.randint(L_K, (L_Q, U)))
+            log.append((L_K, L_Q, U))
+
+        L = T
+        n = len(gb.encoder.attn_layers)
+        for i in range(n):
+            draw(L, L)
+            if gb.encoder.conv_layers is not None and i < n - 1:
+                L = (L + 1) // 2 + 1
+        for _ in gb.decoder.layers:
+            draw(T + P, T + P)
+            draw(L, T + P)
+        return draws, log
+
+    @staticmethod
+    def _upload(tables: List[torch.Tensor], device) -> List[torch.Tensor]:
+        """One pinned staging buffer, one H2D copy, device views [1, L_Q, U] int32."""
+        if not tables:
+            return []
+        flat = torch.cat([t.reshape(-1) for t in tables]).to(torch.int32)
+        if device.type == "cuda":
+            flat = flat.pin_memory().to(device, non_blocking=True)
+        out, off = [], 0
+        for t in tables:
+            out.append(flat[off:off + t.numel()].view(1, *t.shape))
+            off += t.numel()
+        return out
+
+    def _source(self, keys_tables, groups=0):
+        return PlannedIndexSource([(k, t, groups) for k, t in keys_tables])
+
+    # ------------------------------------------------------------------------------------------
+    # visual streams
+    # ------------------------------------------------------------------------------------------
+    def _encode_frames(self, batch, plan, dev_tables, training) -> dict:
+        """All active camera views through backbone + frame encoder in one batched pass -> {view: [B,F,E]}."""
+        c = self.configs
+        order = [v for v in ("right", "left", "front") if v in plan["frame_sets"]]
+        if not order:
+            return {}
+        vb = self.video_backbone
+        views, n_per_view = [], None
+        for name in order:
+            if name == "front":
+                video, rel = batch["front_video"], c.output_fps // c.gaze_fps
+            else:
+                video = batch["left_video"] if name == "left" else batch.get("right_video", batch["left_video"])
+                rel = c.output_fps // c.video_fps
+            assert rel > 0, "Video FPS must be a divisor of the output FPS"
+            B, T = video.shape[:2]
+            t_idx = frame_indices(T, rel)
+            centers = None
+            if name == "front" and isinstance(vb, PatchEmbedBackbone) and vb.configs.fov == "gaze":
+                gaze = batch["gaze"].to(torch.float32)
+                g = ops.median_downsample(gaze, T) if gaze.shape[1] > T else gaze
+                centers = g[:, t_idx.to(g.device)].reshape(-1, 2).clamp(0.0, 1.0)
+            views.append({"name": name, "video": video, "t_idx": t_idx, "centers": centers, "B": B, "T": T})
+            n = B * len(t_idx)
+            n_per_view = n if n_per_view is None else n_per_view
+            if n != n_per_view:
+                raise ValueError("all camera views must provide the same number of encoded frames per clip")
+        S = vb.output_feature_shape[1] * vb.output_feature_shape[2] + 1
+        if isinstance(vb, PatchEmbedBackbone):
+            tokens = vb.encode_views([{**v, "video": v["video"].contiguous()} for v in views])
+        else:  # foreign VideoBackboneModule plugin: generic (slower) path of routeformer.py:472-487
+            feats = []
+            for v in views:
+                frames = v["video"][:, v["t_idx"].to(v["video"].device)].flatten(0, 1)
+                f = vb(frames).to(torch.float32)
+                f = f.permute(0, 2, 3, 1).reshape(f.shape[0], -1, f.shape[1])
+                feats.append(torch.cat([f, -torch.ones_like(f)[:, :1, :]], dim=1))
+            tokens = torch.cat(feats, 0).reshape(-1, feats[0].shape[-1]).contiguous()
+        n_layers = c.encoder_layers
+        keys_tables = []
+        for layer in range(n_layers):
+            ids = [plan["frame_sets"][name][layer] for name in order]
+            keys_tables.append((plan["log"][ids[0]], torch.cat([dev_tables[i] for i in ids], 0).contiguous()))
+        src = self._source(keys_tables, groups=n_per_view if len(order) > 1 else 0)
+        n_total = n_per_view * len(order)
+        feats = self.frame_encoder.encode(tokens, n_total, S, src, self.record_tops, "frame_encoder")  # [n_total, E]
+        E = c.image_embedding_size
+        out = {}
+        for i, v in enumerate(views):
+            out[v["name"]] = feats[i * n_per_view:(i + 1) * n_per_view].view(v["B"], len(v["t_idx"]), E)
+        return out
+
+    def _visual_features(self, batch, training: bool, plan, dev_tables) -> torch.Tensor:
+        c = self.configs
+        E, T = c.image_embedding_size, plan["T_vid"]
+        dev = self.device
+        rel_v, rel_g = c.output_fps // c.video_fps, c.output_fps // c.gaze_fps
+        feats = self._encode_frames(batch, plan, dev_tables, training)
+        streams, srcs, embs = [], [], []
+        B = (batch["left_video"] if self.with_scene else batch["front_video"]).shape[0]
+
+        def frames_stream(name, rel):
+            idx = frame_indices(T, rel)
+            F_, first, step = len(idx), int(idx[0]), (int(idx[1] - idx[0]) if len(idx) > 1 else 1)
+            if name in feats:
+                streams.append((True, False, F_, first, step))
+                srcs.append(feats[name].contiguous())
+            else:  # dropped view: zeros (routeformer.py:464-470)
+                streams.append((False, False, F_, first, step))
+                srcs.append(None)
+
+        if self.with_scene:
+            frames_stream("left", rel_v)
+            embs.append(self.left_video_embedding)
+            frames_stream("right", rel_v)
+            embs.append(self.right_video_embedding)
+        if self.with_gaze:
+            if plan["drop_gaze"]:
+                streams.append((False, True, 0, 0, 1))
+                srcs.append(None)
+            else:
+                Lg = c.gps_backbone_config.seq_len
+                gaze = batch["gaze"].to(torch.float32).contiguous()
+                gaze_ds = ops.median_downsample(gaze, Lg)  # utils/filter.py:5-43 (raises if Lg >= samples)
+                idx = frame_indices(T, rel_g)
+                meta = dict(B=B, T=T, E=E, streams=[(True, False, len(idx), int(idx[0]), int(idx[1] - idx[0]) if len(idx) > 1 else 1)])
+                front_full = Fn.TokenStreams.apply(meta, feats["front"].contiguous(), torch.zeros(E, device=dev))  # [B,T,E]
+                ent = plan["entries"]
+                src = self._source([(plan["log"][i], dev_tables[i]) for i in ent["gaze_encoder"]])
+                gq = self.gaze_encoder.encode(torch.nn.functional.pad(gaze_ds.view(B * Lg, 2), (0, 2)), B, Lg, src, self.record_tops,
+                                              "gaze_encoder")  # [B*Lg, E]
+                src = self._source([(plan["log"][i], dev_tables[i]) for i in ent["gaze_video_decoder"]])
+                g = self.gaze_video_decoder.decode(front_full.view(B * T, E), gq, B, T, Lg, src, self.record_tops, "gaze_video_decoder")
+                g = g.view(B, Lg, -1)[:, :T].contiguous()  # routeformer.py:327
+                streams.append((True, True, 0, 0, 1))
+                srcs.append(g)
+            embs.append(self.gaze_video_embedding)
+        streams.append((False, True, 0, 0, 1))  # the T "output" tokens carry only their embedding (routeformer.py:340-342)
+        srcs.append(None)
+        embs.append(self.video_output_embedding)
+        meta = dict(B=B, T=T, E=E, streams=streams)
+        tokens = Fn.TokenStreams.apply(meta, *srcs, *embs)  # [B, n_streams*T, E]
+        n_streams = len(streams)
+        src = self._source([(plan["log"][i], dev_tables[i]) for i in plan["entries"]["video_encoder"]])
+        vis = self.video_encoder.encode(tokens.view(B * n_streams * T, E), B, n_streams * T, src, self.record_tops, "video_encoder")
+        return vis.view(B, -1, c.encoder_hidden_size)
+
+    # ------------------------------------------------------------------------------------------
+    # public API
+    # ------------------------------------------------------------------------------------------
+    def preprocess_batch(self, batch, training: bool = None):
+        """-> (motion_dynamics [B,T,2], visual_features [B,T,E] or [])   (routeformer.py:254-348)."""
+        if training is None:
+            training = self.training
+        c = self.configs
+        gps = batch["gps"].to(torch.float32)
+        if not gps.is_cuda:
+            raise RuntimeError("routeformer_b200 runs on CUDA tensors only: move the batch to the GPU (there is no CPU fallback)")
+        if self.motion_noise > 0.0 and self.training:
+            gps = gps + torch.randn_like(gps) * self.motion_noise
+        B, T, _ = gps.shape
+        x8, _ = Fn.MotionFeatures.apply(gps.contiguous(), None, 0, 8, False, c.normalize_motion, c.motion_mean, c.motion_std, True, False)
+        motion = x8[:, :, :2]
+        visual: object = []
+        if self.with_video:
+            plan = self._plan_visual(batch, training)
+            tables = self._upload(plan["draws"], gps.device)
+            self.last_draw_log = list(plan["log"])
+            visual = self._visual_features(batch, training, plan, tables)
+        else:
+            self.last_draw_log = []
+        return motion, visual
+
+    def _forward(self, motion_dynamics, visual_features):
+        """-> (raw backbone output [B,P,c_out], origin angles [B])   (routeformer.py:204-252; the rotate-back of :250 is
+        folded into postprocess_batch's decode kernel)."""
+        c = self.configs
+        gb = self.gps_backbone
+        B, T, _ = motion_dynamics.shape
+        has_vis = self.with_video and not isinstance(visual_features, list)
+        E = c.encoder_hidden_size if has_vis else 0
+        enc_in = 5 + E
+        ld = (enc_in + 3) // 4 * 4
+        x, origin = Fn.MotionFeatures.apply(motion_dynamics.contiguous(), visual_features if has_vis else None, E, ld, c.rotate_motion,
+                                            False, 0.0, 1.0, bool(c._only_motion) or not has_vis, True)
+        if isinstance(gb, Informer):
+            draws, log = self._plan_backbone(T, gb.pred_len)
+            tables = self._upload(draws, x.device)
+            self.last_draw_log += log
+            out = gb.run(x, PlannedIndexSource([(k, t, 0) for k, t in zip(log, tables)]), self.record_tops)
+        else:  # foreign GPS backbone plugin (routeformer.py:241)
+            out = gb(x[:, :, :enc_in])
+        if c.decoder_mode == "recursive":
+            out = out + (x[:, -1:, :out.shape[-1]] if c.dense_prediction else x[:, -1:, :2])
+        return out, origin
+
+    def postprocess_batch(self, last_input_gps, output, origin=None):
+        """-> (future_motion_vector, future_gps_positions, future_visual_features)   (routeformer.py:350-395)."""
+        c = self.configs
+        E = c.image_embedding_size
+        rotate = bool(c.rotate_motion) and origin is not None
+        wp, motion = Fn.DecodeWaypoints.apply(output.contiguous(), origin, last_input_gps.to(torch.float32).reshape(-1, 2).contiguous(),
+                                              rotate, c.normalize_motion, c.motion_mean, c.motion_std)
+        wp = wp.to(last_input_gps.dtype)
+        rest = output[:, :, 2:]
+        dense = None
+        if self.with_video and c.dense_prediction:
+            assert rest.shape[-1] >= E, f"Output shape for left/right vid. must be at least {E}, but is {rest.shape}."
+            dense = rest[:, :, :E]
+            rest = rest[:, :, E:]
+        assert rest.shape[-1] == 0, f"Output should be empty at this point, but is {rest.shape}."
+        return motion, wp, dense
+
+    def forward(self, batch, target_batch=None):
+        c = self.configs
+        motion, visual = self.preprocess_batch(batch)
+        last_gps = batch["gps"][:, -1:, :]
+        if not (not self.training and c.autoregressive):
+            out, origin = self._forward(motion, visual)
+            _, wp, dense = self.postprocess_batch(last_gps, out, origin)
+        else:  # autoregressive windows (routeformer.py:164-197)
+            outputs, done = [], 0
+            step = c.autoregressive_step_size
+            pred_len = self.gps_backbone.pred_len
+            self.gps_backbone.pred_len = step
+            try:
+                while done < pred_len:
+                    out, origin = self._forward(motion, visual)
+                    mv, wp_s, dense_s = self.postprocess_batch(last_gps, out, origin)
+                    outputs.append((wp_s, dense_s))
+                    motion = torch.cat([motion[:, step:], mv], dim=1)
+                    last_gps = wp_s[:, -1:, :]
+                    if self.with_video:
+                        visual = torch.cat([visual[:, step:], dense_s], dim=1)
+                    done += step
+            finally:
+                self.gps_backbone.pred_len = pred_len
+            wp = torch.cat([o[0] for o in outputs], dim=1)[:, :pred_len]
+            dense = torch.cat([o[1] for o in outputs], dim=1)[:, :pred_len] if self.with_video else None
+        if c.dense_prediction:
+            return wp, dense
+        return wp

@@ -29,3 +29,69 @@ def targets_for(cfg, B, seed):
 
 def rel_err(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def build_product(cfg, spec, fov="frame", **overrides):
+    """routeformer_b200.Routeformer for an OracleConfig / BackboneSpec pair."""
+    import routeformer_b200 as R
+
+    g = R.GPSBackboneConfig(seq_len=cfg.seq_len, label_len=cfg.seq_len, pred_len=cfg.pred_len, factor=cfg.factor, distil=cfg.distil,
+                            dropout=0.0, activation=cfg.activation, d_model=cfg.d_model, n_heads=cfg.n_heads, e_layers=cfg.e_layers,
+                            d_layers=cfg.d_layers, d_ff=cfg.d_ff)
+    vb = None
+    if spec is not None:
+        vb = R.PatchBackboneConfig(image_size=spec.image_size, patch=spec.patch, channels=spec.channels, fov=fov, window=spec.window)
+    kw = dict(gps_backbone_config=g, video_backbone_config=vb, decoder_mode=cfg.decoder_mode, with_video=cfg.with_video,
+              with_scene=cfg.with_scene, with_gaze=cfg.with_gaze, dense_prediction=cfg.dense_prediction,
+              image_embedding_size=cfg.image_embedding_size, encoder_hidden_size=cfg.encoder_hidden_size,
+              encoder_heads=cfg.encoder_heads, encoder_layers=cfg.encoder_layers, encoder_d_ff=cfg.encoder_d_ff,
+              cross_modal_decoder_heads=cfg.cross_modal_decoder_heads, cross_modal_decoder_layers=cfg.cross_modal_decoder_layers,
+              rotate_motion=cfg.rotate_motion, normalize_motion=cfg.normalize_motion, motion_mean=cfg.motion_mean,
+              motion_std=cfg.motion_std, video_fps=cfg.video_fps, gaze_fps=cfg.gaze_fps, output_fps=cfg.output_fps,
+              view_dropout=cfg.view_dropout, gaze_dropout=cfg.gaze_dropout)
+    kw.update(overrides)
+    rc = R.RouteformerConfig(**kw)
+    return R.Routeformer(rc, gps_backbone=R.Informer, video_backbone=R.PatchEmbedBackbone if spec is not None else None)
+
+
+def to_device(batch, device):
+    return {k: v.to(device) for k, v in batch.items()}
+
+
+def tops_for_oracle(recorded, view_order):
+    """Product-recorded ProbSparse selections -> {module path: [top, ...]} in the ORACLE's call order.
+
+    The product encodes the camera views in one batched frame-encoder pass (`view_order`, e.g. [right, left, front]);
+    the oracle (like the reference) calls the frame encoder once per view in that same order."""
+    out = {}
+    for rec in recorded:
+        top = rec["top"].cpu().long()
+        if rec["where"].startswith("frame_encoder") and len(view_order) > 1:
+            out.setdefault(rec["where"], []).extend(list(top.chunk(len(view_order), dim=0)))
+        else:
+            out.setdefault(rec["where"], []).append(top)
+    return out
+
+
+def selection_violations(recorded, oracle_tops, view_order, rel_tol=2e-2):
+    """Counts product selections that are NOT explained by a near-tie in the oracle's sparsity measure."""
+    import torch
+
+    bad = total = 0
+    queues = {}
+    for t in oracle_tops:
+        queues.setdefault(t["where"], []).append(t["measure"])
+    for rec in recorded:
+        ms = queues[rec["where"]]
+        if rec["where"].startswith("frame_encoder") and len(view_order) > 1:
+            m = torch.cat([ms.pop(0) for _ in view_order], 0)
+        else:
+            m = ms.pop(0)
+        top = rec["top"].cpu().long()
+        u = top.shape[-1]
+        kth = m.topk(u, dim=-1).values[..., -1:]                    # u-th largest measure per (b,h)
+        tol = rel_tol * m.abs().amax(dim=-1, keepdim=True).clamp_min(1.0)
+        sel = torch.zeros_like(m, dtype=torch.bool).scatter(-1, top, True)
+        bad += int(((m < kth - tol) & sel).sum() + ((m > kth + tol) & ~sel).sum())
+        total += sel.numel()
+    return bad, total
