@@ -24,9 +24,12 @@ def grad_buffer(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 def _adjacent(*ts: torch.Tensor) -> bool:
-    """True if the (contiguous) tensors sit back to back in memory, i.e. can be addressed as one matrix."""
+    """True if the (contiguous) tensors sit back to back in ONE storage (the arena), i.e. can be addressed as one matrix."""
+    base = ts[0].untyped_storage().data_ptr()
     for a, b in zip(ts[:-1], ts[1:]):
-        if not (a.is_contiguous() and b.is_contiguous()) or a.data_ptr() + a.numel() * 4 != b.data_ptr():
+        if not (a.is_contiguous() and b.is_contiguous()) or b.untyped_storage().data_ptr() != base:
+            return False
+        if a.data_ptr() + a.numel() * 4 != b.data_ptr():
             return False
     return True
 
@@ -35,11 +38,10 @@ def _fused(*ts: torch.Tensor) -> Optional[torch.Tensor]:
     """One [sum rows, cols] view over adjacent row-major matrices / vectors (None if they are not adjacent)."""
     if not _adjacent(*ts):
         return None
-    first = ts[0]
+    first = ts[0].detach()
     rows = sum(t.shape[0] for t in ts)
     shape = (rows,) + tuple(first.shape[1:])
-    stride = first.stride()
-    return torch.as_strided(first, shape, stride)
+    return first.as_strided(shape, first.stride(), first.storage_offset())
 
 
 def _fused_grads(*ps: torch.Tensor) -> Optional[torch.Tensor]:

@@ -20,6 +20,7 @@ import torch.nn as nn
 
 from . import functional as Fn
 from . import ops
+from .arena import Arena
 from .backbone import PatchEmbedBackbone, VideoBackboneModule
 from .config import RouteformerConfig
 from .informer import Informer
@@ -292,6 +293,7 @@ class Routeformer(nn.Module):
         gps = batch["gps"].to(torch.float32)
         if not gps.is_cuda:
             raise RuntimeError("routeformer_b200 runs on CUDA tensors only: move the batch to the GPU (there is no CPU fallback)")
+        self.arena = Arena.ensure(self)
         if self.motion_noise > 0.0 and self.training:
             gps = gps + torch.randn_like(gps) * self.motion_noise
         B, T, _ = gps.shape
