@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Routeformer fwd+bwd training-step benchmark (BASELINE.json metric: clips/s at 1/2/4/8 B200).
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                   (the reference algorithm's CPU path on this box's host cores)
+
+One "step" = forward + loss + backward + gradient all-reduce + clip + AdamW of the full-modality Routeformer (GPS + scene
+video + gaze FoV, paper configuration of experiments/full_comparison.py:159-296 with the build-defined random-init patch
+backbone, dropouts 0) on a synthetic GEM-shaped batch of 64 clips per GPU (weak scaling: 512 clips on 8 GPUs).
+`value` times the step with the batch resident in HBM; `e2e` times the same step through the public API from pinned host
+buffers (consumed frames staged H2D every step, loss read back every step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PAPER = dict(with_video=True, with_gaze=True, dense_prediction=True)  # + OracleConfig defaults = paper configuration
+BACKBONE = dict(image_size=256, patch=32, channels=1024, window=0.5)
+
+
+def build_case(B: int, seed: int, fov: str):
+    from oracle import routeformer_oracle as O  # synthetic-batch / config description only (shared with the tests)
+
+    cfg = O.OracleConfig(**PAPER)
+    spec = O.BackboneSpec(**BACKBONE)
+    batch = O.synthetic_batch(B, cfg, "gem", seed=seed)
+    g = torch.Generator().manual_seed(seed + 1000)
+    targets = (batch["gps"][:, -1:, :] + torch.cumsum(1.83 + 0.91 * torch.randn(B, cfg.pred_len, 2, generator=g), 1),
+               torch.randn(B, cfg.pred_len, cfg.image_embedding_size, generator=g))
+    return cfg, spec, batch, targets
+
+
+def build_model(cfg, spec, fov):
+    import routeformer_b200 as R
+
+    g = R.GPSBackboneConfig(seq_len=cfg.seq_len, label_len=cfg.seq_len, pred_len=cfg.pred_len, factor=cfg.factor, distil=True,
+                            dropout=0.0, activation="relu", d_model=cfg.d_model, n_heads=cfg.n_heads, e_layers=cfg.e_layers,
+                            d_layers=cfg.d_layers, d_ff=cfg.d_ff)
+    vb = R.PatchBackboneConfig(image_size=spec.image_size, patch=spec.patch, channels=spec.channels, fov=fov, window=spec.window)
+    rc = R.RouteformerConfig(gps_backbone_config=g, video_backbone_config=vb, decoder_mode="smart", with_video=True, with_gaze=True,
+                             dense_prediction=True, dense_loss_ratio=0.5, image_embedding_size=64, encoder_hidden_size=64,
+                             encoder_heads=8, encoder_layers=8, encoder_d_ff=256, cross_modal_decoder_heads=8,
+                             cross_modal_decoder_layers=2, view_dropout=0.0, gaze_dropout=0.0, feature_dropout=0.0)
+    return R.Routeformer(rc, gps_backbone=R.Informer, video_backbone=R.PatchEmbedBackbone)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(2)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    import routeformer_b200 as R
+    from routeformer_b200 import ops
+    from routeformer_b200.parallel import DataParallelTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch_per_gpu
+    cfg, spec, host_batch, host_targets = build_case(B, seed=100 + rank, fov=args.fov)
+    torch.manual_seed(0)
+    model = build_model(cfg, spec, args.fov).to(dev).train()
+    lossf = R.FutureDiscountedLoss({0: 0.97}, epsilon=1.0, loss_function="smooth_l1")
+
+    def loss_fn(out, tgt):
+        wp, dense = out
+        return lossf(wp, tgt[0]) + 0.5 * lossf(dense, tgt[1])
+
+    trainer = DataParallelTrainer(model, loss_fn, lr=1e-5, weight_decay=1e-4, max_grad_norm=2.5)
+    trainer.broadcast_parameters()
+    batch = {k: v.to(dev) for k, v in host_batch.items()}
+    targets = tuple(t.to(dev) for t in host_targets)
+    in_bytes = sum(v.numel() * v.element_size() for v in batch.values())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(args.warmup):
+        trainer.step(batch, targets)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(batch, targets)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = (ops.launch_count - launches0) // max(args.steps, 1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API: pinned host batch -> stage -> step -> loss.item() ----
+    pinned = {k: v.contiguous().pin_memory() for k, v in host_batch.items()}
+    pinned_t = tuple(t.contiguous().pin_memory() for t in host_targets)
+    e2e_steps = max(2, min(args.steps, 5))
+    staged = model.stage_batch(pinned, dev)
+    h2d = sum(v.numel() * v.element_size() for v in staged.values()) + sum(t.numel() * t.element_size() for t in pinned_t)
+    for _ in range(2):
+        trainer.step(model.stage_batch(pinned, dev), tuple(t.to(dev, non_blocking=True) for t in pinned_t)).item()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        st = model.stage_batch(pinned, dev)
+        tg = tuple(t.to(dev, non_blocking=True) for t in pinned_t)
+        loss_host = trainer.step(st, tg).item()
+    e1.record()
+    barrier()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(ms_e2e.item()) / 1e3)
+
+    # ---- roofline of the dominant kernel family (tcgen05 GEMM): one instrumented step, CUDA events per launch ----
+    roofline = cpu_baseline = None
+    kernels = {}
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        rec = []
+        orig_gemm, orig_crop, orig_af, orig_ab = ops.gemm, ops.fov_crop, ops.attention_fwd, ops.attention_bwd
+
+        def timed(fn, tag, work):
+            def wrapper(*a, **k):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                r = fn(*a, **k)
+                e.record()
+                rec.append((tag, s, e, work(*a, **k)))
+                return r
+            return wrapper
+
+        def gemm_work(A, Bm, out, **k):
+            Kd = A.shape[0] if k.get("a_mn") else A.shape[1]
+            Md = A.shape[1] if k.get("a_mn") else A.shape[0]
+            Nd = Bm.shape[1] if k.get("b_mn") else Bm.shape[0]
+            return 2.0 * Md * Nd * Kd
+
+        def crop_work(frames, centers, windows, S, mean, std, **k):
+            n = centers.shape[0]
+            H, W = frames.shape[-2:]
+            win = windows[0].tolist()
+            src = 3 * min(H, win[1] * H + 2) * min(W, win[0] * W + 2) * frames.element_size()
+            return n * (src + 3 * S * S * 4)
+
+        ops.gemm = timed(orig_gemm, "gemm", gemm_work)
+        ops.fov_crop = timed(orig_crop, "fov_crop", crop_work)
+        ops.attention_fwd = timed(orig_af, "attention", lambda *a, **k: 0.0)
+        ops.attention_bwd = timed(orig_ab, "attention", lambda *a, **k: 0.0)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        trainer.step(batch, targets)
+        ev1.record()
+        torch.cuda.synchronize()
+        ops.gemm, ops.fov_crop, ops.attention_fwd, ops.attention_bwd = orig_gemm, orig_crop, orig_af, orig_ab
+        step_ms = ev0.elapsed_time(ev1)
+        for tag in ("gemm", "fov_crop", "attention"):
+            rows = [(s.elapsed_time(e), w) for t_, s, e, w in rec if t_ == tag]
+            if rows:
+                kernels[tag] = {"launches": len(rows), "ms": round(sum(r[0] for r in rows), 3), "work": sum(r[1] for r in rows),
+                                "share_of_step": round(sum(r[0] for r in rows) / step_ms, 3)}
+        gm = kernels["gemm"]
+        achieved = gm["work"] / (gm["ms"] / 1e3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        roofline = {"kernel": "gemm_tf32_kernel (tcgen05.mma kind::tf32, all GEMM launches of one step)", "bound": "tensor",
+                    "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": None,
+                    "peak_source": f"{peak_src} bf16 dense sustained (TF32 operands run at half the bf16 rate)",
+                    "launches": gm["launches"], "avg_launch_us": round(1e3 * gm["ms"] / gm["launches"], 2)}
+        if "fov_crop" in kernels:
+            c = kernels["fov_crop"]
+            gbs = c["work"] / (c["ms"] / 1e3) / 1e9
+            kernels["fov_crop"].update({"achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4)})
+        for k in kernels.values():
+            k.pop("work", None)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_baseline = cpu_reference(cfg, spec, sample_clips=8, steps=2, warmup=1)
+
+    if rank == 0:
+        line = {
+            "metric": "routeformer_fwd_bwd_clips_per_sec", "value": round(value, 2), "unit": "clips/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "Routeformer GPS+scene video+gaze FoV training step (fwd+loss+bwd+allreduce+clip+AdamW), "
+                                   "paper config, random-init patch backbone 256^2/p32/C1024, GEM-shaped clips",
+                       "global_batch": world * B, "batch_per_gpu": B, "parallelism": f"dp{world}", "fov": args.fov,
+                       "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB of clip tensors per step per GPU)",
+                       "dropout": "feature/view/gaze dropout 0 (parity configuration)", "backbone": "frozen (reference: epoch <= 10)"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps, "loss": loss_host},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "loss": float(loss.item()),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(cfg, spec, sample_clips: int, steps: int, warmup: int):
+    """The reference algorithm's CPU path (oracle port: functional PyTorch restatement pinned against the reference) timed on
+    the host cores: fwd + loss + bwd + AdamW on a bounded sample of the same workload."""
+    from oracle import routeformer_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.fill_state_dict(O.state_dict_template(cfg, spec), 0)
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and not k.endswith(".pe") and
+                                          not k.startswith("video_backbone")) for k, v in sd.items()}
+    opt = torch.optim.AdamW([p for p in params.values() if p.requires_grad], lr=1e-5, weight_decay=1e-4)
+    batch = O.synthetic_batch(sample_clips, cfg, "gem", seed=5)
+    g = torch.Generator().manual_seed(6)
+    t_wp = batch["gps"][:, -1:, :] + torch.cumsum(1.83 + 0.91 * torch.randn(sample_clips, cfg.pred_len, 2, generator=g), 1)
+    t_dense = torch.randn(sample_clips, cfg.pred_len, cfg.image_embedding_size, generator=g)
+    model = O.Routeformer(params, cfg, spec)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        wp, dense = model.forward(batch, training=True)
+        loss = O.future_discounted_loss(wp, t_wp) + 0.5 * O.future_discounted_loss(dense, t_dense)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in params.values() if p.requires_grad], 2.5)
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = statistics.median(times)
+    return {"value": round(sample_clips / sec, 3), "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_clips} GEM-shaped clips per step, {steps} timed steps after {warmup} warm-up, fp32, torch {torch.__version__} CPU",
+            "sec_per_step": round(sec, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import routeformer_oracle as O
+
+    cfg, spec = O.OracleConfig(**PAPER), O.BackboneSpec(**BACKBONE)
+    sample = 8
+    res = cpu_reference(cfg, spec, sample_clips=sample, steps=max(1, min(args.steps, 3)), warmup=max(1, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": "routeformer_fwd_bwd_clips_per_sec", "value": res["value"], "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": round(1e3 * res["sec_per_step"], 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Routeformer GPS+scene video+gaze FoV training step, paper config, CPU (reference algorithm, oracle port)",
+                   "sample_clips_per_step": sample},
+        "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=64)
+    ap.add_argument("--fov", default="gaze", choices=["gaze", "frame"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

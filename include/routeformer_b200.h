@@ -259,6 +259,14 @@ int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                   const float* gnorm_sq, float max_norm, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (9) Host staging: copies only the frames the model consumes (routeformer.py:415-421: every 5th frame, never frame 0)
+ * from a PINNED host video [B, T, frame_bytes] to a compact device buffer [B, n_sel, frame_bytes], one strided async
+ * copy per selected frame time.  `src_host` is a HOST pointer, `times` a HOST int array [n_sel].
+ * ---------------------------------------------------------------------------------------------- */
+int rf_stage_frames_h2d(void* dst_dev, const void* src_host, int B, int T, const int* times, int n_sel,
+                        long long frame_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

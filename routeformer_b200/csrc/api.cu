@@ -28,3 +28,18 @@ extern "C" int rf_struct_size(int which) {
     default: return -1;
   }
 }
+
+extern "C" int rf_stage_frames_h2d(void* dst_dev, const void* src_host, int B, int T, const int* times, int n_sel, long long frame_bytes,
+                                   void* stream) {
+  using namespace rf;
+  RF_CHECK_ARG(dst_dev && src_host && times && B > 0 && T > 0 && n_sel > 0 && frame_bytes > 0, "rf_stage_frames_h2d: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int j = 0; j < n_sel; ++j) {
+    RF_CHECK_ARG(times[j] >= 0 && times[j] < T, "rf_stage_frames_h2d: frame time %d outside [0,%d)", times[j], T);
+    RF_CUDA_OK(cudaMemcpy2DAsync(static_cast<char*>(dst_dev) + static_cast<long long>(j) * frame_bytes, static_cast<size_t>(n_sel) * frame_bytes,
+                                 static_cast<const char*>(src_host) + static_cast<long long>(times[j]) * frame_bytes,
+                                 static_cast<size_t>(T) * frame_bytes, static_cast<size_t>(frame_bytes), static_cast<size_t>(B),
+                                 cudaMemcpyHostToDevice, s));
+  }
+  return RF_OK;
+}

@@ -350,3 +350,18 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
                                     float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), _ptr(gnorm_sq),
                                     float(max_norm), _stream()), "rf_adamw_step")
     _count()
+
+
+def stage_frames_h2d(host_video: torch.Tensor, times, device) -> torch.Tensor:
+    """Pinned host video [B,T,3,H,W] -> device [B,len(times),3,H,W] holding only the frames at `times` (async on the current stream)."""
+    if host_video.is_cuda or not host_video.is_pinned() or not host_video.is_contiguous():
+        raise ValueError("stage_frames_h2d needs a contiguous pinned host tensor")
+    B, T = host_video.shape[:2]
+    times = [int(t) for t in times]
+    dst = torch.empty((B, len(times)) + tuple(host_video.shape[2:]), device=device, dtype=host_video.dtype)
+    frame_bytes = host_video[0, 0].numel() * host_video.element_size()
+    arr = (C.c_int * len(times))(*times)
+    with torch.cuda.device(device):
+        check(_lib.load().rf_stage_frames_h2d(dst.data_ptr(), host_video.data_ptr(), B, T, arr, len(times), frame_bytes, _stream()),
+              "rf_stage_frames_h2d")
+    return dst

@@ -32,6 +32,15 @@ def frame_indices(T: int, rel: int) -> torch.Tensor:
     return torch.flip(torch.arange(T - 1, 0, -rel).long(), dims=[0])
 
 
+class StagedBatch(dict):
+    """Device-resident batch produced by `Routeformer.stage_batch`: the video tensors hold ONLY the frames the model
+    consumes ([B, F, 3, H, W], F = 8 of 40 at the GEM configuration); `video_len[key]` keeps the original length T."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.video_len = {}
+
+
 class Routeformer(nn.Module):
     current_epoch = 0  # LightningModule attribute read by callers / backbones
 
@@ -80,6 +89,34 @@ class Routeformer(nn.Module):
         return next(self.parameters()).device
 
     # ------------------------------------------------------------------------------------------
+    # host staging
+    # ------------------------------------------------------------------------------------------
+    def stage_batch(self, host_batch: dict, device=None) -> StagedBatch:
+        """Pinned host batch (reference layout: videos [B,T,3,H,W]) -> device batch, moving only the consumed frames.
+
+        A GEM-shaped clip is 41.2 MB of which 8.24 MB (24 frames) are read by the model (routeformer.py:415-421); the
+        copies are asynchronous on the current stream."""
+        c = self.configs
+        device = device or self.device
+        out = StagedBatch()
+        for key, value in host_batch.items():
+            if key.endswith("_video") and self.with_video:
+                rel = c.output_fps // (c.gaze_fps if key == "front_video" else c.video_fps)
+                T = value.shape[1]
+                src = value if value.is_pinned() else value.contiguous().pin_memory()
+                out[key] = ops.stage_frames_h2d(src, frame_indices(T, rel).tolist(), device)
+                out.video_len[key] = T
+            else:
+                out[key] = value.to(device, non_blocking=True)
+        return out
+
+    @staticmethod
+    def _video_len(batch, key) -> int:
+        if isinstance(batch, StagedBatch) and key in batch.video_len:
+            return batch.video_len[key]
+        return batch[key].shape[1]
+
+    # ------------------------------------------------------------------------------------------
     # CPU-RNG plan: every torch.rand / torch.randint of one preprocess+forward, in reference order
     # ------------------------------------------------------------------------------------------
     def _plan_visual(self, batch, training: bool) -> dict:
@@ -114,12 +151,12 @@ class Routeformer(nn.Module):
                 frame_sets["right"] = [draw(S, S) for _ in range(n_layers)]
             if not plan["drop_left"]:
                 frame_sets["left"] = [draw(S, S) for _ in range(n_layers)]
-            T_vid = left.shape[1]
+            T_vid = self._video_len(batch, "left_video")
             n_streams += 2
         if self.with_gaze:
             if self.gaze_dropout > 0.0 and training:  # routeformer.py:300-301
                 plan["drop_gaze"] = bool(torch.rand(1) < self.gaze_dropout)
-            T_vid = batch["front_video"].shape[1]
+            T_vid = self._video_len(batch, "front_video")
             n_streams += 1
             if not plan["drop_gaze"]:
                 frame_sets["front"] = [draw(S, S) for _ in range(n_layers)]
@@ -185,18 +222,21 @@ class Routeformer(nn.Module):
         views, n_per_view = [], None
         for name in order:
             if name == "front":
-                video, rel = batch["front_video"], c.output_fps // c.gaze_fps
+                key, rel = "front_video", c.output_fps // c.gaze_fps
             else:
-                video = batch["left_video"] if name == "left" else batch.get("right_video", batch["left_video"])
+                key = "left_video" if (name == "left" or "right_video" not in batch) else "right_video"
                 rel = c.output_fps // c.video_fps
             assert rel > 0, "Video FPS must be a divisor of the output FPS"
-            B, T = video.shape[:2]
-            t_idx = frame_indices(T, rel)
+            video = batch[key]
+            B = video.shape[0]
+            T = self._video_len(batch, key)
+            times = frame_indices(T, rel)  # frame times in the original clip
+            t_idx = torch.arange(len(times)) if video.shape[1] != T else times  # staged batches are already compact
             centers = None
             if name == "front" and isinstance(vb, PatchEmbedBackbone) and vb.configs.fov == "gaze":
                 gaze = batch["gaze"].to(torch.float32)
-                g = ops.median_downsample(gaze, T) if gaze.shape[1] > T else gaze
-                centers = g[:, t_idx.to(g.device)].reshape(-1, 2).clamp(0.0, 1.0)
+                g = ops.median_downsample(gaze.contiguous(), T) if gaze.shape[1] > T else gaze
+                centers = g[:, times.to(g.device)].reshape(-1, 2).clamp(0.0, 1.0)
             views.append({"name": name, "video": video, "t_idx": t_idx, "centers": centers, "B": B, "T": T})
             n = B * len(t_idx)
             n_per_view = n if n_per_view is None else n_per_view
@@ -234,7 +274,7 @@ class Routeformer(nn.Module):
         rel_v, rel_g = c.output_fps // c.video_fps, c.output_fps // c.gaze_fps
         feats = self._encode_frames(batch, plan, dev_tables, training)
         streams, srcs, embs = [], [], []
-        B = (batch["left_video"] if self.with_scene else batch["front_video"]).shape[0]
+        B = batch["gps"].shape[0]
 
         def frames_stream(name, rel):
             idx = frame_indices(T, rel)

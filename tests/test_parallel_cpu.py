@@ -1,0 +1,100 @@
+"""CPU (gloo, world_size 2): host-side logic of the data-parallel path -- batch sharding, bucketed flat all-reduce,
+and the arena bookkeeping the trainer relies on.  (The CUDA optimiser / model step is covered by the -m gpu tests.)"""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from routeformer_b200.parallel import allreduce_flat, bucket_bounds, shard_batch
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        w = torch.randn(5000, 3)
+        data = {"x": torch.randn(8, 5000), "y": torch.randn(8, 3)}
+        local = shard_batch(data, rank, world)
+        # stand-in for the model: per-rank gradient of a sum-reduced loss over the local shard, written into a flat arena
+        wl = w.clone().requires_grad_()
+        (((local["x"] @ wl) - local["y"]) ** 2).sum().backward()
+        flat = wl.grad.reshape(-1).clone()
+        for h in allreduce_flat(flat, n_buckets=3):
+            h.wait()
+        if rank == 0:
+            wf = w.clone().requires_grad_()
+            (((data["x"] @ wf) - data["y"]) ** 2).sum().backward()
+            out.put(float((flat - wf.grad.reshape(-1)).abs().max() / wf.grad.abs().max()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_gradients_allreduce_to_full_batch_gradient():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get(timeout=10) < 1e-5
+
+
+def test_bucket_bounds_cover_in_reverse_order():
+    for n, k in [(10, 4), (100000, 4), (4097, 3), (1, 2)]:
+        b = bucket_bounds(n, k, align=16)
+        assert b[0][1] == n and b[-1][0] == 0
+        assert sorted(b) == b[::-1]
+        assert all(lo < hi for lo, hi in b)
+        cover = sorted(b)
+        assert all(cover[i][1] == cover[i + 1][0] for i in range(len(cover) - 1))
+    assert bucket_bounds(0, 4) == []
+
+
+def test_shard_batch():
+    batch = {"gps": torch.arange(16).view(8, 2), "left_video": torch.zeros(8, 3, 2)}
+    s1 = shard_batch(batch, 1, 4)
+    assert s1["gps"].tolist() == [[4, 5], [6, 7]] and s1["left_video"].shape == (2, 3, 2)
+    try:
+        shard_batch(batch, 0, 3)
+        assert False
+    except ValueError:
+        pass
+
+
+def test_arena_round_trip_and_grad_reattach():
+    """Arena keeps state_dict round-trips, fuses q/k/v storage and re-attaches gradient views after zero_grad(set_to_none)."""
+    from oracle import routeformer_oracle as O
+    from routeformer_b200.arena import Arena
+    from routeformer_b200.functional import _fused
+    from tests.helpers import build_product, case_from_golden, load_golden
+
+    gold = load_golden("full_small_eval")
+    cfg, spec, sd, _ = case_from_golden(gold)
+    model = build_product(cfg, spec)
+    model.load_state_dict(sd)
+    arena = Arena.ensure(model)
+    assert arena.valid() and arena.n_trainable <= arena.size
+    assert all(torch.equal(v, sd[k]) for k, v in model.state_dict().items())
+    att = model.video_encoder.encoder.attn_layers[0].attention
+    w = _fused(att.query_projection.weight, att.key_projection.weight, att.value_projection.weight)
+    assert w is not None and w.shape == (3 * 128, 128) and torch.equal(w[128:256], att.key_projection.weight)
+    frozen = [n for n, p in model.named_parameters() if not p.requires_grad]
+    assert frozen == ["video_backbone.proj.weight", "video_backbone.proj.bias"]
+    model.zero_grad(set_to_none=True)
+    assert Arena.ensure(model) is arena
+    g = att.out_projection.weight.grad
+    assert g is not None and g.data_ptr() == arena.grad.data_ptr() + 4 * arena.offsets[id(att.out_projection.weight)]
+    model.load_state_dict(O.fill_state_dict(sd, 99))  # in-place copy keeps the arena
+    assert arena.valid()
