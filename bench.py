@@ -64,10 +64,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.index, self.samples, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -75,10 +75,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(2)
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
@@ -157,6 +157,12 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * B * args.steps / (ms / 1e3)
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "value": round(value, 2), "ms_per_step": round(ms / args.steps, 3), "gpu_launches": int(launches)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the public API: pinned host batch -> stage -> step -> loss.item() ----
     pinned = {k: v.contiguous().pin_memory() for k, v in host_batch.items()}
@@ -329,9 +335,12 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=64)
     ap.add_argument("--fov", default="gaze", choices=["gaze", "frame"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up + --steps steps, no e2e / roofline / CPU legs")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
+    if args.warmup < 3 and args.impl == "ours" and not args.profile:
         args.warmup = 3
+    if args.profile:
+        args.warmup = 1
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -100,6 +100,9 @@ typedef struct {
   int round_f16;                             /* 1: round the result through fp16 (backbone plugin returns input dtype) */
 } RfGemmParams;
 int rf_gemm_tf32(const RfGemmParams* p, void* stream);
+/* Profiling hook: installs (or clears with NULL) a device buffer of >= 8 u64; CTA (0,0,0) of every later GEMM launch records
+ * %globaltimer (ns) at: start, after setup, first operands landed, last MMA issued, accumulator ready, epilogue done, exit. */
+int rf_debug_gemm_stamps(unsigned long long* device_buffer);
 
 /* ------------------------------------------------------------------------------------------------
  * (3) Circular Conv1d(k=3) assembly.  The conv is computed as ONE GEMM Z = X [W_0;W_1;W_2]^T

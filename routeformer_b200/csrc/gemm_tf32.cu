@@ -54,6 +54,7 @@ struct Args {
   int kb_total, kb_per_split;
   int group_in, group_out, row_offset;
   int round_f16;
+  int tma_store;  // 1: epilogue stages 128x32 chunks in (swizzled) smem and writes them with TMA bulk stores
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -92,6 +93,20 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -152,12 +167,22 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Optional in-kernel timeline (profiling hook): when rf_debug_gemm_stamps() has installed a buffer, CTA (0,0,0) records
+// %globaltimer at its phase boundaries.  One extra global load per CTA otherwise.
+__device__ unsigned long long* g_stamps = nullptr;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const Args a) {
   using T = Tile<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -173,10 +198,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int kb_begin = blockIdx.z * a.kb_per_split;
   const int kb_end = min(a.kb_total, kb_begin + a.kb_per_split);
   const int nkb = kb_end - kb_begin;
+  unsigned long long* stamps = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? g_stamps : nullptr;
+  if (stamps && threadIdx.x == 0) stamps[0] = gtime();
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
+    if (a.tma_store) prefetch_tensormap(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -189,6 +217,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (stamps && threadIdx.x == 0) stamps[1] = gtime();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -225,6 +254,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (stamps && i == 0) stamps[2] = gtime();
         const uint32_t a_base = smem_u32(smem + s * T::STAGE_BYTES);
         const uint32_t b_base = a_base + A_BYTES;
 #pragma unroll
@@ -238,6 +268,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
       }
       umma_commit(tmem_full_bar);    // accumulator complete
+      if (stamps) stamps[3] = gtime();
     }
     __syncwarp();
   }
@@ -245,6 +276,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // ---------------- epilogue: thread t <-> accumulator row t ---------------------------------
   mbar_wait(tmem_full_bar, 0);
   tc_fence_after();
+  if (stamps && threadIdx.x == 64) stamps[4] = gtime();
   const int m = m0 + warp * 32 + lane;
   const bool row_ok = m < a.M;
   long long out_row = m;
@@ -256,52 +288,149 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const float* aux_row = a.dact ? a.dact_aux + static_cast<long long>(m) * a.ld_aux : nullptr;
   const bool vec_ok = ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0) && !a.accumulate;
 
-#pragma unroll 1
-  for (int c = 0; c < BLOCK_N; c += 32) {
-    const int nb = n0 + c;
-    if (nb >= a.N) break;  // warp-uniform
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(c), r);
-    tmem_wait_ld();
-    if (!row_ok) continue;
-    const int ncols = min(32, a.N - nb);
-    float v[32];
+  // Epilogue math on one 32-column chunk of this thread's row.  Every option is tested ONCE per chunk (not per element) and
+  // the operand rows are fetched as 8 independent 16 B loads, so the chunk is a short straight-line block per option.
+  const bool al16 = ((reinterpret_cast<uintptr_t>(a.bias) | reinterpret_cast<uintptr_t>(a.rowadd) | reinterpret_cast<uintptr_t>(a.residual) |
+                      reinterpret_cast<uintptr_t>(a.dact_aux)) & 15) == 0 &&
+                    ((a.ld_rowadd | a.ld_res | a.ld_aux) & 3) == 0;
+  auto add_row = [&](float (&x)[32], const float* src, int ncols, bool vec, bool ro) {
+    if (vec) {
+      float4 t[8];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = __uint_as_float(r[j]);
-      if (j < ncols) {
-        const int n = nb + j;
-        if (a.bias) x += __ldg(a.bias + n);
-        if (rowadd_row) x += __ldg(rowadd_row + n);
-        if (res_row) x += res_row[n];
-        if (pre_row) pre_row[n] = x;
-        x = apply_act(x, a.act);
-        if (a.dact) {
-          const float t = aux_row[n];
-          x *= (a.dact == RF_ACT_RELU) ? (t > 0.0f ? 1.0f : 0.0f) : gelu_erf_grad(t);
-        }
-        if (a.round_f16) x = __half2float(__float2half_rn(x));
-      }
-      v[j] = x;
-    }
-    if (a.accumulate) {
+      for (int q = 0; q < 8; ++q) t[q] = ro ? __ldg(reinterpret_cast<const float4*>(src) + q) : reinterpret_cast<const float4*>(src)[q];
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) atomicAdd(c_row + nb + j, v[j]);
-    } else if (vec_ok && ncols == 32) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(c_row + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int q = 0; q < 8; ++q) { x[4 * q] += t[q].x; x[4 * q + 1] += t[q].y; x[4 * q + 2] += t[q].z; x[4 * q + 3] += t[q].w; }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < ncols) c_row[nb + j] = v[j];
+        if (j < ncols) x[j] += src[j];
+    }
+  };
+  auto finish_chunk = [&](float (&x)[32], float (&pre)[32], int nb, int ncols) {
+    const bool vec = al16 && ncols == 32;
+    if (row_ok) {
+      if (a.bias) add_row(x, a.bias + nb, ncols, vec, true);
+      if (rowadd_row) add_row(x, rowadd_row + nb, ncols, vec, true);
+      if (res_row) add_row(x, res_row + nb, ncols, vec, false);
+    }
+    if (a.preact) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pre[j] = x[j];
+    }
+    if (a.act == RF_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+    } else if (a.act == RF_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+    }
+    if (a.dact && row_ok) {
+      float t[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = 0.0f;
+      add_row(t, aux_row + nb, ncols, vec, false);
+      if (a.dact == RF_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = t[j] > 0.0f ? x[j] : 0.0f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] *= gelu_erf_grad(t[j]);
+      }
+    }
+    if (a.round_f16) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = __half2float(__float2half_rn(x[j]));
+    }
+  };
+
+  if (a.tma_store) {
+    // ---- staged path: 128x32 fp32 chunks -> 128B-swizzled smem (the idle pipeline stages) -> TMA bulk store --------
+    // The output (and pre-activation) tiles leave the SM as full 128 B lines written by the TMA engine instead of
+    // 32 rows x 16 B per store instruction; TMA also clips rows >= M / cols >= N.
+    constexpr int NPAIR = (STAGES * T::STAGE_BYTES) / 32768;  // (out, preact) buffer pairs of 16 KiB each
+    const int row_in_tile = warp * 32 + lane;
+    int ci = 0;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32, ++ci) {
+      const int nb = n0 + c;
+      if (nb >= a.N) break;  // CTA-uniform
+      uint8_t* obuf = smem + (ci % NPAIR) * 32768;
+      uint8_t* pbuf = obuf + 16384;
+      if (ci >= NPAIR) {  // the buffer pair is being re-used: its previous bulk store must have finished reading smem
+        if (threadIdx.x == 0) bulk_wait_group_read<NPAIR - 1>();
+        __syncthreads();
+      }
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(c), r);
+      tmem_wait_ld();
+      float v[32], pre[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      finish_chunk(v, pre, nb, min(32, a.N - nb));
+      float* orow = reinterpret_cast<float*>(obuf + row_in_tile * 128);
+      float* prow = reinterpret_cast<float*>(pbuf + row_in_tile * 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int slot = (j ^ (row_in_tile & 7)) << 2;  // SWIZZLE_128B: 16 B chunk index XOR (row mod 8)
+        *reinterpret_cast<float4*>(orow + slot) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      if (a.preact) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int slot = (j ^ (row_in_tile & 7)) << 2;
+          *reinterpret_cast<float4*>(prow + slot) = make_float4(pre[4 * j], pre[4 * j + 1], pre[4 * j + 2], pre[4 * j + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (a.group_in > 0) tma_store_3d(&tmC, obuf, nb, 0, m0 / a.group_in);
+        else tma_store_2d(&tmC, obuf, nb, m0);
+        if (a.preact) tma_store_2d(&tmP, pbuf, nb, m0);
+        bulk_commit_group();
+      }
+    }
+    if (threadIdx.x == 0) bulk_wait_group_read<0>();
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      const int nb = n0 + c;
+      if (nb >= a.N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(c), r);
+      tmem_wait_ld();
+      if (!row_ok) continue;
+      const int ncols = min(32, a.N - nb);
+      float v[32], pre[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      finish_chunk(v, pre, nb, ncols);
+      if (pre_row) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) pre_row[nb + j] = pre[j];
+      }
+      if (a.accumulate) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) atomicAdd(c_row + nb + j, v[j]);
+      } else if (vec_ok && ncols == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(c_row + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) c_row[nb + j] = v[j];
+      }
     }
   }
 
+  if (stamps && threadIdx.x == 64) stamps[5] = gtime();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, BLOCK_N);
+  if (stamps && threadIdx.x == 64) stamps[6] = gtime();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -328,24 +457,27 @@ static bool tf32_round_in_tma() {
   return v == 1;
 }
 
-// 2-D fp32 tensor map: dim0 = `inner` contiguous elements, dim1 = `outer` rows of pitch ld; box = 32 x box_rows.
-static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_rows, bool mn_major) {
+// fp32 tensor map of rank 2 or 3: dim0 = `inner` contiguous elements (box 32 = 128 B), dim1 = rows of pitch ld (box box_rows),
+// optional dim2 = groups of pitch ld2 (box box_groups).  `round_tf32`: TFLOAT32 type (operands are rounded RN on load).
+static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_rows, bool mn_major,
+                    bool round_tf32 = true, long long groups = 0, long long ld2 = 0, int box_groups = 0) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return RF_ERR_CUDA;
   }
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, tf32_round_in_tma() ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  const int rank = groups > 0 ? 3 : 2;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer), static_cast<cuuint64_t>(groups)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(ld2) * 4};
+  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_groups)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, (round_tf32 && tf32_round_in_tma()) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
                   const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%lld outer=%lld ld=%lld box_rows=%d", static_cast<int>(r),
-              static_cast<const void*>(base), inner, outer, ld, box_rows);
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%lld outer=%lld ld=%lld box_rows=%d groups=%lld", static_cast<int>(r),
+              static_cast<const void*>(base), inner, outer, ld, box_rows, groups);
     return RF_ERR_CUDA;
   }
   return RF_OK;
@@ -362,19 +494,42 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
   if (!p->b_mn_major) rc = make_map(&tmB, p->B, p->K, p->N, p->ldb, BLOCK_N, false);
   else rc = make_map(&tmB, p->B, p->N, p->K, p->ldb, 32, true);
   if (rc != RF_OK) return rc;
+  CUtensorMap tmC, tmP;
+  memset(&tmC, 0, sizeof(tmC));
+  memset(&tmP, 0, sizeof(tmP));
+  if (args.tma_store) {
+    if (p->out_group_in > 0) {
+      const long long n_groups = ceil_div(p->M, p->out_group_in);
+      rc = make_map(&tmC, p->C, p->N, p->out_group_out, p->ldc, p->out_group_in, false, false, n_groups,
+                    static_cast<long long>(p->out_group_out) * p->ldc, BLOCK_M / p->out_group_in);
+    } else {
+      rc = make_map(&tmC, p->C, p->N, p->M, p->ldc, BLOCK_M, false, false);
+    }
+    if (rc != RF_OK) return rc;
+    if (p->preact) {
+      rc = make_map(&tmP, p->preact, p->N, p->M, p->ld_pre, BLOCK_M, false, false);
+      if (rc != RF_OK) return rc;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     RF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
     attr_set = true;
   }
   dim3 grid(ceil_div(p->M, BLOCK_M), ceil_div(p->N, BLOCK_N), splits);
-  gemm_tf32_kernel<BLOCK_N><<<grid, NUM_THREADS, T::SMEM_BYTES, stream>>>(tmA, tmB, args);
+  gemm_tf32_kernel<BLOCK_N><<<grid, NUM_THREADS, T::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmP, args);
   RF_LAUNCH_OK();
   return RF_OK;
 }
 
 }  // namespace gemm
 }  // namespace rf
+
+extern "C" int rf_debug_gemm_stamps(unsigned long long* device_buffer) {
+  using namespace rf;
+  RF_CUDA_OK(cudaMemcpyToSymbol(gemm::g_stamps, &device_buffer, sizeof(device_buffer)));
+  return RF_OK;
+}
 
 extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   using namespace rf;
@@ -413,6 +568,16 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   a.kb_total = kb_total; a.kb_per_split = kb_per_split;
   a.group_in = p->out_group_in; a.group_out = p->out_group_out; a.row_offset = p->out_row_offset;
   a.round_f16 = p->round_f16;
+  static int tma_store_enabled = -1;
+  if (tma_store_enabled < 0) {
+    const char* e = getenv("RF_GEMM_TMA_STORE");
+    tma_store_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool c_ok = (p->ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(p->C) & 15) == 0;
+  const bool group_ok = p->out_group_in == 0 ||
+                        (gemm::BLOCK_M % p->out_group_in == 0 && p->out_row_offset == 0 && p->out_group_out >= p->out_group_in);
+  const bool pre_ok = !p->preact || ((p->ld_pre % 4) == 0 && (reinterpret_cast<uintptr_t>(p->preact) & 15) == 0 && p->out_group_in == 0);
+  a.tma_store = (tma_store_enabled && !p->accumulate && c_ok && group_ok && pre_ok) ? 1 : 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return n64 ? gemm::launch<64>(p, a, splits, s) : gemm::launch<128>(p, a, splits, s);
 }
