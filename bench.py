@@ -112,7 +112,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))  # a stuck collective aborts quickly
     B = args.batch_per_gpu
     cfg, spec, host_batch, host_targets = build_case(B, seed=100 + rank, fov=args.fov)
     torch.manual_seed(0)
@@ -189,7 +190,8 @@ def run_ours(args):
     # ---- roofline of the dominant kernel family (tcgen05 GEMM): one instrumented step, CUDA events per launch ----
     roofline = cpu_baseline = None
     kernels = {}
-    if rank == 0:
+    # every rank runs the instrumented step (it contains the gradient all-reduce); only rank 0 reports
+    if True:
         peaks, peak_src = measured_peaks()
         rec = []
         orig_gemm, orig_crop, orig_af, orig_ab = ops.gemm, ops.fov_crop, ops.attention_fwd, ops.attention_bwd
@@ -204,10 +206,14 @@ def run_ours(args):
                 return r
             return wrapper
 
+        shapes = {}
+
         def gemm_work(A, Bm, out, **k):
             Kd = A.shape[0] if k.get("a_mn") else A.shape[1]
             Md = A.shape[1] if k.get("a_mn") else A.shape[0]
             Nd = Bm.shape[1] if k.get("b_mn") else Bm.shape[0]
+            key = (Md, Nd, Kd, bool(k.get("a_mn")), bool(k.get("b_mn")), bool(k.get("accumulate")))
+            shapes.setdefault(key, []).append(len(rec))
             return 2.0 * Md * Nd * Kd
 
         def crop_work(frames, centers, windows, S, mean, std, **k):
@@ -246,8 +252,20 @@ def run_ours(args):
             kernels["fov_crop"].update({"achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4)})
         for k in kernels.values():
             k.pop("work", None)
-        if world == 1 and not args.no_cpu_baseline:
+        if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+            with open(os.path.join(ROOT, "gpurun_out", "gemm_shapes.txt"), "w") as f:
+                table = []
+                for key, idxs in shapes.items():
+                    ms_list = [rec[i][1].elapsed_time(rec[i][2]) for i in idxs]
+                    table.append((sum(ms_list), len(idxs), key))
+                for tot, cnt, (Md, Nd, Kd, amn, bmn, accf) in sorted(table, reverse=True):
+                    fl = 2.0 * Md * Nd * Kd
+                    by = 4.0 * (Md * Kd + Nd * Kd + Md * Nd)
+                    f.write(f"{tot:8.3f} ms {cnt:3d} x {1e3 * tot / cnt:8.1f} us  M={Md:6d} N={Nd:5d} K={Kd:6d} a_mn={int(amn)} b_mn={int(bmn)} acc={int(accf)}"
+                            f"  {fl / (tot / cnt) / 1e9:7.1f} TFLOP/s {by / (tot / cnt) / 1e6:7.0f} GB/s\n")
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
             cpu_baseline = cpu_reference(cfg, spec, sample_clips=8, steps=2, warmup=1)
+    barrier()
 
     if rank == 0:
         line = {
