@@ -124,9 +124,12 @@ def run_ours(args):
         wp, dense = out
         return lossf(wp, tgt[0]) + 0.5 * lossf(dense, tgt[1])
 
-    trainer = DataParallelTrainer(model, loss_fn, lr=1e-5, weight_decay=1e-4, max_grad_norm=2.5)
+    trainer = DataParallelTrainer(model, loss_fn, lr=1e-5, weight_decay=1e-4, max_grad_norm=2.5, use_cuda_graph=not args.no_graph)
     trainer.broadcast_parameters()
-    batch = {k: v.to(dev) for k, v in host_batch.items()}
+    # inputs: pinned host batch in the reference layout; the device batch holds the frames the model consumes (8 of 40 per view)
+    pinned = {k: v.contiguous().pin_memory() for k, v in host_batch.items()}
+    pinned_t = tuple(t.contiguous().pin_memory() for t in host_targets)
+    batch = model.stage_batch(pinned, dev)
     targets = tuple(t.to(dev) for t in host_targets)
     in_bytes = sum(v.numel() * v.element_size() for v in batch.values())
 
@@ -151,7 +154,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = (ops.launch_count - launches0) // max(args.steps, 1)
+    launches = (ops.launch_count - launches0) // max(args.steps, 1) + trainer.graph_launches
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -166,20 +169,21 @@ def run_ours(args):
         return
 
     # ---- end to end through the public API: pinned host batch -> stage -> step -> loss.item() ----
-    pinned = {k: v.contiguous().pin_memory() for k, v in host_batch.items()}
-    pinned_t = tuple(t.contiguous().pin_memory() for t in host_targets)
     e2e_steps = max(2, min(args.steps, 5))
-    staged = model.stage_batch(pinned, dev)
-    h2d = sum(v.numel() * v.element_size() for v in staged.values()) + sum(t.numel() * t.element_size() for t in pinned_t)
+    h2d = in_bytes + sum(t.numel() * t.element_size() for t in pinned_t)
+
+    def e2e_step():
+        model.stage_batch(pinned, dev, out=batch)          # H2D: only the consumed frames + gps + gaze
+        for dst, src in zip(targets, pinned_t):
+            dst.copy_(src, non_blocking=True)
+        return trainer.step(batch, targets).item()           # D2H: the loss
+
     for _ in range(2):
-        trainer.step(model.stage_batch(pinned, dev), tuple(t.to(dev, non_blocking=True) for t in pinned_t)).item()
+        e2e_step()
     barrier()
-    t0 = time.perf_counter()
     e0.record()
     for _ in range(e2e_steps):
-        st = model.stage_batch(pinned, dev)
-        tg = tuple(t.to(dev, non_blocking=True) for t in pinned_t)
-        loss_host = trainer.step(st, tg).item()
+        loss_host = e2e_step()
     e1.record()
     barrier()
     ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -229,7 +233,9 @@ def run_ours(args):
         ops.attention_bwd = timed(orig_ab, "attention", lambda *a, **k: 0.0)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        graph_mode, trainer.use_cuda_graph = trainer.use_cuda_graph, False  # per-launch events need the eager path
         trainer.step(batch, targets)
+        trainer.use_cuda_graph = graph_mode
         ev1.record()
         torch.cuda.synchronize()
         ops.gemm, ops.fov_crop, ops.attention_fwd, ops.attention_bwd = orig_gemm, orig_crop, orig_af, orig_ab
@@ -275,7 +281,8 @@ def run_ours(args):
             "config": {"workload": "Routeformer GPS+scene video+gaze FoV training step (fwd+loss+bwd+allreduce+clip+AdamW), "
                                    "paper config, random-init patch backbone 256^2/p32/C1024, GEM-shaped clips",
                        "global_batch": world * B, "batch_per_gpu": B, "parallelism": f"dp{world}", "fov": args.fov,
-                       "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB of clip tensors per step per GPU)",
+                       "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB of consumed frames + gps + gaze per step per GPU)",
+                       "cuda_graph": bool(trainer.use_cuda_graph),
                        "dropout": "feature/view/gaze dropout 0 (parity configuration)", "backbone": "frozen (reference: epoch <= 10)"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
@@ -353,6 +360,7 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=64)
     ap.add_argument("--fov", default="gaze", choices=["gaze", "frame"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one captured CUDA graph")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up + --steps steps, no e2e / roofline / CPU legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.profile:

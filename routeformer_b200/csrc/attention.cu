@@ -377,9 +377,17 @@ static int validate(const RfAttnParams* p, const char* who, bool forward) {
   return RF_OK;
 }
 
+// Opt-in to > 48 KiB of dynamic shared memory once per kernel (not per launch: keeps launches capturable in CUDA graphs).
 template <typename K>
 static int configure(K kernel, size_t smem) {
-  if (smem > 48 * 1024) RF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  static const void* configured[16] = {nullptr};
+  static int n_configured = 0;
+  if (smem <= 48 * 1024) return RF_OK;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < n_configured; ++i)
+    if (configured[i] == key) return RF_OK;
+  RF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  if (n_configured < 16) configured[n_configured++] = key;
   return RF_OK;
 }
 

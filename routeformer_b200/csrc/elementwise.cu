@@ -70,17 +70,30 @@ __global__ void conv3_assemble_bwd_kernel(const RfConv3AssembleBwdParams a, int 
   }
 }
 
-// dst[n] += sum_m w(m) * src[m][n];  w(m) = 1 or (m % period) (time-feature weight gradient)
+// dst[n] += sum_m w(m) * src[m][n];  w(m) = 1 or (m % period) (time-feature weight gradient).
+// 32 columns x 8 row-lanes per CTA; every thread keeps 4 independent loads in flight; one atomic per column per CTA.
 __global__ void colsum_kernel(const float* __restrict__ src, long long ld, int M, int N, float* __restrict__ dst,
                               int weight_period) {
   __shared__ float part[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
   if (col < N) {
-    for (int m = blockIdx.y * 8 + threadIdx.y; m < M; m += gridDim.y * 8) {
-      const float v = src[static_cast<long long>(m) * ld + col];
-      acc += weight_period > 0 ? v * static_cast<float>(m % weight_period) : v;
+    const int stride = gridDim.y * 8;
+    int m = blockIdx.y * 8 + threadIdx.y;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (weight_period > 0) {
+      for (; m < M; m += stride) a0 += src[static_cast<long long>(m) * ld + col] * static_cast<float>(m % weight_period);
+    } else {
+      for (; m + 3 * stride < M; m += 4 * stride) {
+        const float v0 = src[static_cast<long long>(m) * ld + col];
+        const float v1 = src[static_cast<long long>(m + stride) * ld + col];
+        const float v2 = src[static_cast<long long>(m + 2 * stride) * ld + col];
+        const float v3 = src[static_cast<long long>(m + 3 * stride) * ld + col];
+        a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+      }
+      for (; m < M; m += stride) a0 += src[static_cast<long long>(m) * ld + col];
     }
+    acc = (a0 + a1) + (a2 + a3);
   }
   part[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
@@ -93,8 +106,8 @@ __global__ void colsum_kernel(const float* __restrict__ src, long long ld, int M
 }
 static void launch_colsum(const float* src, long long ld, int M, int N, float* dst, int weight_period, cudaStream_t s) {
   dim3 block(32, 8);
-  int gy = ceil_div(M, 8 * 32);
-  gy = gy < 1 ? 1 : (gy > 256 ? 256 : gy);
+  int gy = ceil_div(M, 8 * 8);  // ~8 rows per thread
+  gy = gy < 1 ? 1 : (gy > 1024 ? 1024 : gy);
   dim3 grid(ceil_div(N, 32), gy);
   colsum_kernel<<<grid, block, 0, s>>>(src, ld, M, N, dst, weight_period);
 }

@@ -64,7 +64,10 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma;  dgamma += sum dy*xhat;  dbeta += sum dy.
-// Column partials are accumulated per CTA in shared memory, then one atomic per column per CTA.
+// A lane owns the same columns (lane, lane+32, ...) for every row its warp processes, so the dgamma/dbeta partials live in
+// registers across rows (CPL = columns per lane, template) and leave the CTA as one shared-memory reduction + one global
+// atomic per column.
+template <int CPL>
 __global__ void __launch_bounds__(WARPS * 32)
 layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -76,26 +79,46 @@ layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* 
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  float gm[CPL], ag[CPL], ab[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int d = lane + 32 * c;
+    gm[c] = d < D ? gamma[d] : 0.f;
+    ag[c] = 0.f;
+    ab[c] = 0.f;
+  }
   for (long long row = static_cast<long long>(blockIdx.x) * WARPS + warp; row < M; row += static_cast<long long>(gridDim.x) * WARPS) {
     const float* xr = x + row * ldx;
     const float* gr = dy + row * lddy;
     float* dr = dx + row * lddx;
     const float mu = mean[row], rs = rstd[row];
+    float go[CPL], xh[CPL];
     float s1 = 0.f, s2 = 0.f;
-    for (int d = lane; d < D; d += 32) {
-      const float g = gr[d] * gamma[d];
-      const float xh = (xr[d] - mu) * rs;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int d = lane + 32 * c;
+      go[c] = d < D ? gr[d] : 0.f;
+      xh[c] = d < D ? (xr[d] - mu) * rs : 0.f;
+      const float g = go[c] * gm[c];
       s1 += g;
-      s2 += g * xh;
+      s2 += g * xh[c];
     }
     s1 = warp_sum(s1) / D;
     s2 = warp_sum(s2) / D;
-    for (int d = lane; d < D; d += 32) {
-      const float go = gr[d];
-      const float xh = (xr[d] - mu) * rs;
-      dr[d] = rs * (go * gamma[d] - s1 - xh * s2);
-      atomicAdd(sg + d, go * xh);
-      atomicAdd(sb + d, go);
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int d = lane + 32 * c;
+      if (d < D) dr[d] = rs * (go[c] * gm[c] - s1 - xh[c] * s2);
+      ag[c] += go[c] * xh[c];
+      ab[c] += go[c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int d = lane + 32 * c;
+    if (d < D) {
+      atomicAdd(sg + d, ag[c]);
+      atomicAdd(sb + d, ab[c]);
     }
   }
   __syncthreads();
@@ -264,11 +287,16 @@ extern "C" int rf_layernorm_fwd(const float* x, long long ldx, const float* gamm
 
 extern "C" int rf_layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* gamma, const float* mean,
                                 const float* rstd, float* dx, long long lddx, float* dgamma, float* dbeta, int M, int D, void* stream) {
-  RF_CHECK_ARG(dy && x && gamma && mean && rstd && dx && M > 0 && D > 0 && D <= 4096, "rf_layernorm_bwd: bad arguments");
+  RF_CHECK_ARG(dy && x && gamma && mean && rstd && dx && M > 0 && D > 0 && D <= 1024, "rf_layernorm_bwd: bad arguments (D <= 1024)");
   int grid = ceil_div(M, WARPS * 4);  // >= 4 rows per warp so the per-CTA column atomics amortise
   grid = grid < 1 ? 1 : (grid > 148 * 4 ? 148 * 4 : grid);
-  layernorm_bwd_kernel<<<grid, WARPS * 32, 2 * D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(dy, lddy, x, ldx, gamma, mean, rstd,
-                                                                                                      dx, lddx, dgamma, dbeta, M, D);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t sm = 2 * D * sizeof(float);
+  if (D <= 64) layernorm_bwd_kernel<2><<<grid, WARPS * 32, sm, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D);
+  else if (D <= 128) layernorm_bwd_kernel<4><<<grid, WARPS * 32, sm, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D);
+  else if (D <= 256) layernorm_bwd_kernel<8><<<grid, WARPS * 32, sm, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D);
+  else if (D <= 1024) layernorm_bwd_kernel<32><<<grid, WARPS * 32, sm, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D);
+  else { set_error("rf_layernorm_bwd: D=%d > 1024 not supported", D); return RF_ERR_UNSUPPORTED; }
   RF_LAUNCH_OK();
   return RF_OK;
 }

@@ -352,13 +352,16 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
     _count()
 
 
-def stage_frames_h2d(host_video: torch.Tensor, times, device) -> torch.Tensor:
+def stage_frames_h2d(host_video: torch.Tensor, times, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Pinned host video [B,T,3,H,W] -> device [B,len(times),3,H,W] holding only the frames at `times` (async on the current stream)."""
     if host_video.is_cuda or not host_video.is_pinned() or not host_video.is_contiguous():
         raise ValueError("stage_frames_h2d needs a contiguous pinned host tensor")
     B, T = host_video.shape[:2]
     times = [int(t) for t in times]
-    dst = torch.empty((B, len(times)) + tuple(host_video.shape[2:]), device=device, dtype=host_video.dtype)
+    shape = (B, len(times)) + tuple(host_video.shape[2:])
+    dst = out if out is not None else torch.empty(shape, device=device, dtype=host_video.dtype)
+    if tuple(dst.shape) != shape or dst.dtype != host_video.dtype or not dst.is_contiguous():
+        raise ValueError("stage_frames_h2d: `out` does not match the staged shape")
     frame_bytes = host_video[0, 0].numel() * host_video.element_size()
     arr = (C.c_int * len(times))(*times)
     with torch.cuda.device(device):

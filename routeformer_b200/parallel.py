@@ -51,8 +51,13 @@ def allreduce_flat(flat: torch.Tensor, group=None, n_buckets: int = 4) -> List:
 
 
 class DataParallelTrainer:
+    """`use_cuda_graph=True` captures zero-grad + forward + loss + backward (~950 kernel launches) into ONE CUDA graph after
+    two eager warm-up steps and replays it every step: the launch-bound tail of small kernels no longer waits on the host.
+    Requirements: static shapes, dropouts 0 (no data-dependent control flow); the CPU random draws of every step are still
+    made on the host in reference order and reach the graph through a persistent pinned buffer."""
+
     def __init__(self, model, loss_fn: Callable, lr: float = 1e-5, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 max_grad_norm: float = 2.5, group=None, n_buckets: int = 4):
+                 max_grad_norm: float = 2.5, group=None, n_buckets: int = 4, use_cuda_graph: bool = False):
         self.model = model
         self.loss_fn = loss_fn
         self.group = group
@@ -66,6 +71,56 @@ class DataParallelTrainer:
         self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
         self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
         self.step_count = 0
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self.static_batch = None
+        self.static_targets = None
+        self._static_loss = None
+        self._replayed = None
+        self.graph_launches = 0
+
+    # -- forward + backward ----------------------------------------------------------------------
+    def _fwd_bwd(self, batch, targets) -> torch.Tensor:
+        self.arena.zero_grad()
+        out = self.model(batch)
+        loss = self.loss_fn(out, targets)
+        loss.backward()
+        return loss
+
+    def _capture(self, batch, targets) -> None:
+        m = self.model
+        if m.training and (m.view_dropout > 0 or m.gaze_dropout > 0 or m.feature_dropout > 0 or m.motion_noise > 0):
+            raise ValueError("CUDA-graph capture needs a static step: view/gaze/feature dropout and motion noise must be 0")
+        self.static_batch, self.static_targets = batch, targets  # the first batch's tensors become the static input buffers
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._fwd_bwd(batch, targets)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        before = ops.launch_count
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self._fwd_bwd(batch, targets)
+        self.graph_launches = ops.launch_count - before  # kernels of this library inside the captured step
+
+    def _replay(self, batch, targets) -> torch.Tensor:
+        if batch is not self.static_batch:
+            for k, v in batch.items():
+                if v.data_ptr() != self.static_batch[k].data_ptr():
+                    self.static_batch[k].copy_(v, non_blocking=True)
+        if targets is not self.static_targets:
+            for dst, src in zip(self.static_targets, targets):
+                if src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+        if self._replayed is not None:
+            self._replayed.synchronize()  # the previous replay has consumed the pinned index buffer
+        self.model.prepare_draws(self.static_batch, refill_only=True)  # host only: this step's CPU random draws
+        self._graph.replay()
+        self._replayed = torch.cuda.Event()
+        self._replayed.record()
+        return self._static_loss
 
     def broadcast_parameters(self, src: int = 0) -> None:
         if self.world > 1:
@@ -76,10 +131,12 @@ class DataParallelTrainer:
         arena = Arena.ensure(self.model)
         if arena is not self.arena:
             raise RuntimeError("the model's parameter storage changed after the trainer was built")
-        arena.zero_grad()
-        out = self.model(batch)
-        loss = self.loss_fn(out, targets)
-        loss.backward()
+        if not self.use_cuda_graph:
+            loss = self._fwd_bwd(batch, targets)
+        else:
+            if self._graph is None:
+                self._capture(batch, targets)
+            loss = self._replay(batch, targets)
         for w in allreduce_flat(arena.grad, self.group, self.n_buckets):
             w.wait()
         self.step_count += 1

@@ -83,6 +83,8 @@ class Routeformer(nn.Module):
         # test hook: when set to a list, every ProbSparse call appends {"where", "top", "measure"} (the oracle replays them)
         self.record_tops: Optional[list] = None
         self.last_draw_log: List[tuple] = []
+        self._idx_slots = {}
+        self._pending_plan = None
 
     @property
     def device(self):
@@ -91,24 +93,34 @@ class Routeformer(nn.Module):
     # ------------------------------------------------------------------------------------------
     # host staging
     # ------------------------------------------------------------------------------------------
-    def stage_batch(self, host_batch: dict, device=None) -> StagedBatch:
+    def stage_batch(self, host_batch: dict, device=None, out: Optional[StagedBatch] = None) -> StagedBatch:
         """Pinned host batch (reference layout: videos [B,T,3,H,W]) -> device batch, moving only the consumed frames.
 
         A GEM-shaped clip is 41.2 MB of which 8.24 MB (24 frames) are read by the model (routeformer.py:415-421); the
         copies are asynchronous on the current stream."""
         c = self.configs
         device = device or self.device
-        out = StagedBatch()
+        reuse = out is not None  # write into the tensors of an existing staged batch (static buffers of a CUDA graph)
+        out = out if reuse else StagedBatch()
         for key, value in host_batch.items():
             if key.endswith("_video") and self.with_video:
                 rel = c.output_fps // (c.gaze_fps if key == "front_video" else c.video_fps)
                 T = value.shape[1]
                 src = value if value.is_pinned() else value.contiguous().pin_memory()
-                out[key] = ops.stage_frames_h2d(src, frame_indices(T, rel).tolist(), device)
+                out[key] = ops.stage_frames_h2d(src, frame_indices(T, rel).tolist(), device, out=out[key] if reuse else None)
                 out.video_len[key] = T
+            elif reuse:
+                out[key].copy_(value, non_blocking=True)
             else:
                 out[key] = value.to(device, non_blocking=True)
         return out
+
+    def _device_index(self, idx: torch.Tensor, device) -> torch.Tensor:
+        """Cached device copy of a small constant index tensor (no H2D copy inside a captured step)."""
+        key = ("index", tuple(idx.tolist()), str(device))
+        if key not in self._idx_slots:
+            self._idx_slots[key] = idx.to(device)
+        return self._idx_slots[key]
 
     @staticmethod
     def _video_len(batch, key) -> int:
@@ -192,19 +204,56 @@ class Routeformer(nn.Module):
             draw(L, T + P)
         return draws, log
 
-    @staticmethod
-    def _upload(tables: List[torch.Tensor], device) -> List[torch.Tensor]:
-        """One pinned staging buffer, one H2D copy, device views [1, L_Q, U] int32."""
+    def _upload(self, tables: List[torch.Tensor], device, slot: str, refill_only: bool = False) -> List[torch.Tensor]:
+        """Index tables -> device views [1, L_Q, U] int32 through a PERSISTENT pinned staging buffer and ONE H2D copy.
+
+        The staging / device buffers are kept per slot (same addresses every step) so that the copy can be captured in a
+        CUDA graph; `refill_only` rewrites the pinned buffer on the host without issuing the copy (graph replay does it)."""
         if not tables:
             return []
-        flat = torch.cat([t.reshape(-1) for t in tables]).to(torch.int32)
-        if device.type == "cuda":
-            flat = flat.pin_memory().to(device, non_blocking=True)
+        n = sum(t.numel() for t in tables)
+        key = (slot, n, str(device))
+        if key not in self._idx_slots:
+            host = torch.empty(n, dtype=torch.int32)
+            if device.type == "cuda":
+                host = host.pin_memory()
+            self._idx_slots[key] = (host, torch.empty(n, dtype=torch.int32, device=device))
+        host, dev = self._idx_slots[key]
+        off = 0
+        for t in tables:
+            host[off:off + t.numel()].copy_(t.reshape(-1))
+            off += t.numel()
+        if refill_only:
+            return []
+        dev.copy_(host, non_blocking=True)
         out, off = [], 0
         for t in tables:
-            out.append(flat[off:off + t.numel()].view(1, *t.shape))
+            out.append(dev[off:off + t.numel()].view(1, *t.shape))
             off += t.numel()
         return out
+
+    def prepare_draws(self, batch, training: bool = None, refill_only: bool = False, backbone: bool = True):
+        """Makes every CPU random draw of one (non-autoregressive) forward, in reference order, and stages the index tables.
+
+        Called implicitly by `preprocess_batch` / `_forward`; called explicitly with `refill_only=True` before replaying a
+        captured CUDA graph of the step (the graph contains the H2D copy, the host only has to refresh the pinned buffer)."""
+        if training is None:
+            training = self.training
+        dev = batch["gps"].device
+        plan = {"visual": None, "backbone": None}
+        log: List[tuple] = []
+        if self.with_video:
+            pv = self._plan_visual(batch, training)
+            pv["tables"] = self._upload(pv["draws"], dev, "visual", refill_only)
+            plan["visual"] = pv
+            log += pv["log"]
+        if backbone and isinstance(self.gps_backbone, Informer) and not (not self.training and self.configs.autoregressive):
+            draws, blog = self._plan_backbone(batch["gps"].shape[1], self.gps_backbone.pred_len)
+            plan["backbone"] = (blog, self._upload(draws, dev, "backbone", refill_only))
+            log += blog
+        self.last_draw_log = log
+        self._pending_plan = None if refill_only else plan
+        return plan
 
     def _source(self, keys_tables, groups=0):
         return PlannedIndexSource([(k, t, groups) for k, t in keys_tables])
@@ -236,7 +285,7 @@ class Routeformer(nn.Module):
             if name == "front" and isinstance(vb, PatchEmbedBackbone) and vb.configs.fov == "gaze":
                 gaze = batch["gaze"].to(torch.float32)
                 g = ops.median_downsample(gaze.contiguous(), T) if gaze.shape[1] > T else gaze
-                centers = g[:, times.to(g.device)].reshape(-1, 2).clamp(0.0, 1.0)
+                centers = g[:, self._device_index(times, g.device)].reshape(-1, 2).clamp(0.0, 1.0)
             views.append({"name": name, "video": video, "t_idx": t_idx, "centers": centers, "B": B, "T": T})
             n = B * len(t_idx)
             n_per_view = n if n_per_view is None else n_per_view
@@ -248,7 +297,7 @@ class Routeformer(nn.Module):
         else:  # foreign VideoBackboneModule plugin: generic (slower) path of routeformer.py:472-487
             feats = []
             for v in views:
-                frames = v["video"][:, v["t_idx"].to(v["video"].device)].flatten(0, 1)
+                frames = v["video"][:, self._device_index(v["t_idx"], v["video"].device)].flatten(0, 1)
                 f = vb(frames).to(torch.float32)
                 f = f.permute(0, 2, 3, 1).reshape(f.shape[0], -1, f.shape[1])
                 feats.append(torch.cat([f, -torch.ones_like(f)[:, :1, :]], dim=1))
@@ -340,13 +389,13 @@ class Routeformer(nn.Module):
         x8, _ = Fn.MotionFeatures.apply(gps.contiguous(), None, 0, 8, False, c.normalize_motion, c.motion_mean, c.motion_std, True, False)
         motion = x8[:, :, :2]
         visual: object = []
+        # stand-alone calls (e.g. the target pass of full_comparison.py:482) draw only what the reference's preprocess_batch
+        # draws; `forward` has already planned the GPS-backbone draws that follow
+        plan = self._pending_plan if self._pending_plan is not None else self.prepare_draws(batch, training, backbone=False)
+        self._pending_plan = None
+        self._backbone_plan = plan["backbone"]
         if self.with_video:
-            plan = self._plan_visual(batch, training)
-            tables = self._upload(plan["draws"], gps.device)
-            self.last_draw_log = list(plan["log"])
-            visual = self._visual_features(batch, training, plan, tables)
-        else:
-            self.last_draw_log = []
+            visual = self._visual_features(batch, training, plan["visual"], plan["visual"]["tables"])
         return motion, visual
 
     def _forward(self, motion_dynamics, visual_features):
@@ -362,9 +411,13 @@ class Routeformer(nn.Module):
         x, origin = Fn.MotionFeatures.apply(motion_dynamics.contiguous(), visual_features if has_vis else None, E, ld, c.rotate_motion,
                                             False, 0.0, 1.0, bool(c._only_motion) or not has_vis, True)
         if isinstance(gb, Informer):
-            draws, log = self._plan_backbone(T, gb.pred_len)
-            tables = self._upload(draws, x.device)
-            self.last_draw_log += log
+            if getattr(self, "_backbone_plan", None) is not None:
+                log, tables = self._backbone_plan
+                self._backbone_plan = None
+            else:  # autoregressive windows / direct _forward calls: draw on the spot (same stream order as the reference)
+                draws, log = self._plan_backbone(T, gb.pred_len)
+                tables = self._upload(draws, x.device, f"backbone_p{gb.pred_len}")
+                self.last_draw_log += log
             out = gb.run(x, PlannedIndexSource([(k, t, 0) for k, t in zip(log, tables)]), self.record_tops)
         else:  # foreign GPS backbone plugin (routeformer.py:241)
             out = gb(x[:, :, :enc_in])
@@ -391,6 +444,8 @@ class Routeformer(nn.Module):
 
     def forward(self, batch, target_batch=None):
         c = self.configs
+        if self._pending_plan is None:
+            self.prepare_draws(batch)
         motion, visual = self.preprocess_batch(batch)
         last_gps = batch["gps"][:, -1:, :]
         if not (not self.training and c.autoregressive):
