@@ -103,6 +103,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -384,7 +389,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       fence_proxy_async_smem();
       __syncthreads();
       if (threadIdx.x == 0) {
-        if (a.group_in > 0) tma_store_3d(&tmC, obuf, nb, 0, m0 / a.group_in);
+        if (a.accumulate) tma_reduce_add_2d(&tmC, obuf, nb, m0);  // split-K wgrad: fp32 add performed by the TMA / L2, 128 B lines
+        else if (a.group_in > 0) tma_store_3d(&tmC, obuf, nb, 0, m0 / a.group_in);
         else tma_store_2d(&tmC, obuf, nb, m0);
         if (a.preact) tma_store_2d(&tmP, pbuf, nb, m0);
         bulk_commit_group();
@@ -577,7 +583,8 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   const bool group_ok = p->out_group_in == 0 ||
                         (gemm::BLOCK_M % p->out_group_in == 0 && p->out_row_offset == 0 && p->out_group_out >= p->out_group_in);
   const bool pre_ok = !p->preact || ((p->ld_pre % 4) == 0 && (reinterpret_cast<uintptr_t>(p->preact) & 15) == 0 && p->out_group_in == 0);
-  a.tma_store = (tma_store_enabled && !p->accumulate && c_ok && group_ok && pre_ok) ? 1 : 0;
+  const bool acc_ok = !p->accumulate || (p->out_group_in == 0 && !p->preact);
+  a.tma_store = (tma_store_enabled && c_ok && group_ok && pre_ok && acc_ok) ? 1 : 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return n64 ? gemm::launch<64>(p, a, splits, s) : gemm::launch<128>(p, a, splits, s);
 }
