@@ -78,7 +78,7 @@ __device__ __forceinline__ Smem carve(float* base, int Lq, int Lk, int u, int dh
   sm.s = sm.v + Lk * pitch;
   sm.m = sm.s + round4(u * Lk);
   sm.acc = sm.m + round4(Lq);
-  sm.top = reinterpret_cast<int*>(sm.acc + round4(dh));
+  sm.top = reinterpret_cast<int*>(sm.acc + round4(dh) + THREADS * 4);
   sm.sel = sm.top + round4(u);
   sm.end = reinterpret_cast<float*>(sm.sel + round4(Lq));
   return sm;
@@ -89,22 +89,30 @@ __device__ __forceinline__ long long out_offset(const RfAttnParams& p, int b, in
                                         : ((static_cast<long long>(b) * p.H + h) * p.Lq + l) * p.dh;
 }
 
-// acc[0:dh] = sum over rows l in [0,L) with keep(l) of src[l][0:dh]; all threads participate (smem atomics, 2 barriers).
+// acc[0:dh] = sum over rows l in [0,L) with keep(l) of src[l][0:dh].  All threads participate: thread (g, c) sums rows
+// g, g+groups, ... of 4 channels into scratch[g][4c..4c+3]; then one thread per channel adds the groups in a FIXED order, so
+// the result is deterministic (no atomics: a 1-ulp difference here could flip a top-u selection in a later layer).
+// scratch = acc + round4(dh), THREADS*4 floats.
 template <int DH, typename Keep>
 __device__ __forceinline__ void column_sum(const Dims<DH> d, const float* src, int L, float* acc, Keep keep) {
   const int dh = d.dh(), dh4 = d.dh4(), pitch = d.pitch();
-  for (int i = threadIdx.x; i < dh; i += THREADS) acc[i] = 0.f;
-  __syncthreads();
+  float* scratch = acc + round4(dh);
   const int groups = dh4 <= THREADS ? THREADS / dh4 : 1;
-  for (int c = threadIdx.x % dh4 + (threadIdx.x / dh4 >= groups ? dh4 : 0); c < dh4; c += dh4) {  // threads beyond groups*dh4 idle
-    const int g = threadIdx.x / dh4;
+  const int g = threadIdx.x / dh4, c = threadIdx.x - g * dh4;
+  if (g < groups) {
     float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int l = g; l < L; l += groups)
       if (keep(l)) {
         const float4 vv = *reinterpret_cast<const float4*>(src + l * pitch + 4 * c);
         part.x += vv.x; part.y += vv.y; part.z += vv.z; part.w += vv.w;
       }
-    atomicAdd(acc + 4 * c, part.x); atomicAdd(acc + 4 * c + 1, part.y); atomicAdd(acc + 4 * c + 2, part.z); atomicAdd(acc + 4 * c + 3, part.w);
+    *reinterpret_cast<float4*>(scratch + (g * dh4 + c) * 4) = part;
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < dh; ch += THREADS) {
+    float sum = 0.f;
+    for (int gg = 0; gg < groups; ++gg) sum += scratch[gg * dh + ch];
+    acc[ch] = sum;
   }
   __syncthreads();
 }
@@ -164,6 +172,7 @@ __device__ void select_and_softmax(const RfAttnParams& p, const Dims<DH> d, cons
     float mx = -INFINITY;
 #pragma unroll
     for (int t = 0; t < MAX_KEYS_PER_LANE; ++t) {
+      if (32 * t >= Lk) break;  // warp-uniform: no work (and no issue slots) for key slots beyond Lk
       const int j = lane + 32 * t;
       float s = -INFINITY;
       if (j < Lk && !(p.mode == RF_ATTN_PROB_MASKED && j > qi)) s = dot4(d, qrow, sm.k + j * pitch) * scale;
@@ -174,6 +183,7 @@ __device__ void select_and_softmax(const RfAttnParams& p, const Dims<DH> d, cons
     float sum = 0.f;
 #pragma unroll
     for (int t = 0; t < MAX_KEYS_PER_LANE; ++t) {
+      if (32 * t >= Lk) break;  // warp-uniform: no work (and no issue slots) for key slots beyond Lk
       const float e = (lane + 32 * t < Lk) ? expf(sc[t] - mx) : 0.f;
       sc[t] = e;
       sum += e;
@@ -181,6 +191,7 @@ __device__ void select_and_softmax(const RfAttnParams& p, const Dims<DH> d, cons
     const float inv = 1.f / warp_sum(sum);
 #pragma unroll
     for (int t = 0; t < MAX_KEYS_PER_LANE; ++t) {
+      if (32 * t >= Lk) break;  // warp-uniform: no work (and no issue slots) for key slots beyond Lk
       const int j = lane + 32 * t;
       if (j < Lk) sm.s[r * Lk + j] = sc[t] * inv;
     }
@@ -275,6 +286,7 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
     float acc = 0.f;
 #pragma unroll
     for (int t = 0; t < MAX_KEYS_PER_LANE; ++t) {
+      if (32 * t >= Lk) break;  // warp-uniform: no work (and no issue slots) for key slots beyond Lk
       const int j = lane + 32 * t;
       float v = 0.f;
       if (j < Lk) {
@@ -286,6 +298,7 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
     acc = warp_sum(acc);
 #pragma unroll
     for (int t = 0; t < MAX_KEYS_PER_LANE; ++t) {
+      if (32 * t >= Lk) break;  // warp-uniform: no work (and no issue slots) for key slots beyond Lk
       const int j = lane + 32 * t;
       if (j < Lk) s_ds[r * Lk + j] = sm.s[r * Lk + j] * (dp[t] - acc) * scale;
     }
@@ -349,7 +362,7 @@ static size_t fwd_smem(const RfAttnParams* p) {
   const int pitch = p->dh + 4;
   const int u = p->mode == RF_ATTN_FULL ? p->Lq : p->u;
   return sizeof(float) * (static_cast<size_t>(p->Lq) * pitch + 2 * static_cast<size_t>(p->Lk) * pitch + round4(u * p->Lk) + round4(p->Lq) +
-                          round4(p->dh) + round4(u) + round4(p->Lq));
+                          round4(p->dh) + THREADS * 4 + round4(u) + round4(p->Lq));
 }
 static size_t bwd_smem(const RfAttnParams* p) {
   const int pitch = p->dh + 4;
@@ -365,6 +378,7 @@ static int validate(const RfAttnParams* p, const char* who, bool forward) {
                "%s: head dim and strides must be multiples of 4 (16 B vector access), dh=%d", who, p->dh);
   RF_CHECK_ARG(((reinterpret_cast<uintptr_t>(p->q) | reinterpret_cast<uintptr_t>(p->k) | reinterpret_cast<uintptr_t>(p->v)) & 15) == 0,
                "%s: q/k/v must be 16-byte aligned", who);
+  RF_CHECK_ARG(p->dh <= 4 * THREADS, "%s: head dim %d > %d", who, p->dh, 4 * THREADS);
   RF_CHECK_ARG(p->Lk <= 32 * MAX_KEYS_PER_LANE, "%s: at most %d keys per problem", who, 32 * MAX_KEYS_PER_LANE);
   RF_CHECK_ARG(p->mode >= 0 && p->mode <= 2, "%s: bad mode %d", who, p->mode);
   if (p->mode != RF_ATTN_FULL) {

@@ -68,13 +68,26 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) {  // exact-erf GELU (F.gelu default)
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. at fp32 rounding level for GELU): branch-free, one reciprocal and
+// one exponential, ~3x fewer instructions than erff() in the GEMM epilogues where it runs once per output element.
+// e = exp(-x^2) is passed in so that the GELU derivative can share it with its Gaussian term.
+__device__ __forceinline__ float erf_as(float x, float e) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  return copysignf(fmaf(-p * t, e, 1.0f), x);
 }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+__device__ __forceinline__ float gelu_erf(float x) {  // exact-erf GELU (F.gelu default): 0.5 x (1 + erf(x / sqrt 2))
+  const float z = x * 0.70710678118654752440f;
+  return 0.5f * x * (1.0f + erf_as(z, __expf(-z * z)));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {  // Phi(x) + x phi(x)
+  const float z = x * 0.70710678118654752440f;
+  const float e = __expf(-z * z);  // exp(-x^2/2)
+  return 0.5f * (1.0f + erf_as(z, e)) + x * 0.39894228040143267794f * e;
 }
 
 }  // namespace rf

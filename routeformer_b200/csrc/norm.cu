@@ -131,8 +131,9 @@ layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* 
 // ---------------------------------------------------------------------------------------------
 // Distil tail
 // ---------------------------------------------------------------------------------------------
-// per-channel sum and sum of squares over R rows -> sum1[D], sum2[D] (pre-zeroed)
-__global__ void column_moments_kernel(const float* __restrict__ z, int R, int D, float* __restrict__ sum1, float* __restrict__ sum2) {
+// per-channel sum and sum of squares over R rows, deterministic: CTA row `by` writes its partials to part[by][d] (sums) and
+// part[gy + by][d] (squares); bn_finalize adds them in a fixed order (no atomics: batch statistics feed the forward pass).
+__global__ void column_moments_kernel(const float* __restrict__ z, int R, int D, float* __restrict__ part) {
   __shared__ float p1[8][33], p2[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f, b = 0.f;
@@ -149,18 +150,23 @@ __global__ void column_moments_kernel(const float* __restrict__ z, int R, int D,
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int y = 0; y < 8; ++y) { s1 += p1[y][threadIdx.x]; s2 += p2[y][threadIdx.x]; }
-    atomicAdd(sum1 + col, s1);
-    atomicAdd(sum2 + col, s2);
+    part[static_cast<long long>(blockIdx.y) * D + col] = s1;
+    part[static_cast<long long>(gridDim.y + blockIdx.y) * D + col] = s2;
   }
 }
 
-// turns (sum, sumsq) in mean/rstd buffers into (mean, rstd) and updates the running statistics
-__global__ void bn_finalize_kernel(float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, int R, int D, float momentum, float eps) {
+// (mean, rstd) from the partial moments + running-statistics update (momentum, unbiased variance)
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int gy, float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, int R, int D, float momentum, float eps) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
-  const float m = mean[d] / R;
-  float var = rstd[d] / R - m * m;
+  float s1 = 0.f, s2 = 0.f;
+  for (int y = 0; y < gy; ++y) {
+    s1 += part[static_cast<long long>(y) * D + d];
+    s2 += part[static_cast<long long>(gy + y) * D + d];
+  }
+  const float m = s1 / R;
+  float var = s2 / R - m * m;
   var = fmaxf(var, 0.f);
   mean[d] = m;
   rstd[d] = rsqrtf(var + eps);
@@ -309,13 +315,17 @@ extern "C" int rf_distil_fwd(const RfDistilParams* p, void* stream) {
   const int R = p->B * p->Lz, D = p->D;
   const int Lp = (p->Lz - 1) / 2 + 1;
   if (p->training) {
-    RF_CUDA_OK(cudaMemsetAsync(p->mean, 0, D * sizeof(float), s));
-    RF_CUDA_OK(cudaMemsetAsync(p->rstd, 0, D * sizeof(float), s));
+    // the pooled-output buffer doubles as scratch for the partial moments (it is overwritten by the apply kernel afterwards)
     int gy = ceil_div(R, 8 * 16);
-    gy = gy < 1 ? 1 : (gy > 64 ? 64 : gy);
-    column_moments_kernel<<<dim3(ceil_div(D, 32), gy), dim3(32, 8), 0, s>>>(p->z, R, D, p->mean, p->rstd);
+    const int cap = (p->B * Lp) / 2;
+    gy = gy > 64 ? 64 : gy;
+    gy = gy > cap ? cap : gy;
+    gy = gy < 1 ? 1 : gy;
+    RF_CHECK_ARG(static_cast<long long>(p->B) * Lp >= 2, "rf_distil_fwd: needs at least 2 pooled rows");
+    column_moments_kernel<<<dim3(ceil_div(D, 32), gy), dim3(32, 8), 0, s>>>(p->z, R, D, p->out);
     RF_LAUNCH_OK();
-    bn_finalize_kernel<<<ceil_div(D, 128), 128, 0, s>>>(p->mean, p->rstd, p->running_mean, p->running_var, R, D, p->momentum, p->eps);
+    bn_finalize_kernel<<<ceil_div(D, 128), 128, 0, s>>>(p->out, gy, p->mean, p->rstd, p->running_mean, p->running_var, R, D, p->momentum,
+                                                       p->eps);
     RF_LAUNCH_OK();
   } else {
     bn_eval_stats_kernel<<<ceil_div(D, 128), 128, 0, s>>>(p->mean, p->rstd, p->running_mean, p->running_var, D, p->eps);
