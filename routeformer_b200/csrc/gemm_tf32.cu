@@ -181,6 +181,112 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 
+// Epilogue math of one accumulator row (thread <-> row), applied to one 32-column chunk at a time.  Every option is tested
+// ONCE per chunk (not per element) and operand rows are fetched as 8 independent 16 B loads.
+struct RowEpilogue {
+  bool row_ok, al16;
+  const float* rowadd_row;
+  const float* res_row;
+  const float* aux_row;
+  float* pre_row;
+  float* c_row;
+
+  __device__ __forceinline__ void init(const Args& a, int m) {
+    row_ok = m < a.M;
+    long long out_row = m;
+    if (a.group_in > 0) out_row = static_cast<long long>(m / a.group_in) * a.group_out + (m % a.group_in) + a.row_offset;
+    c_row = a.C + out_row * a.ldc;
+    rowadd_row = a.rowadd ? a.rowadd + static_cast<long long>(m % a.rowadd_period) * a.ld_rowadd : nullptr;
+    res_row = a.residual ? a.residual + static_cast<long long>(m) * a.ld_res : nullptr;
+    pre_row = a.preact ? a.preact + static_cast<long long>(m) * a.ld_pre : nullptr;
+    aux_row = a.dact ? a.dact_aux + static_cast<long long>(m) * a.ld_aux : nullptr;
+    al16 = ((reinterpret_cast<uintptr_t>(a.bias) | reinterpret_cast<uintptr_t>(a.rowadd) | reinterpret_cast<uintptr_t>(a.residual) |
+             reinterpret_cast<uintptr_t>(a.dact_aux)) & 15) == 0 &&
+           ((a.ld_rowadd | a.ld_res | a.ld_aux) & 3) == 0;
+  }
+  static __device__ __forceinline__ void add_row(float (&x)[32], const float* src, int ncols, bool vec, bool ro) {
+    if (vec) {
+      float4 t[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t[q] = ro ? __ldg(reinterpret_cast<const float4*>(src) + q) : reinterpret_cast<const float4*>(src)[q];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { x[4 * q] += t[q].x; x[4 * q + 1] += t[q].y; x[4 * q + 2] += t[q].z; x[4 * q + 3] += t[q].w; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) x[j] += src[j];
+    }
+  }
+  __device__ __forceinline__ void apply(const Args& a, float (&x)[32], float (&pre)[32], int nb, int ncols) const {
+    const bool vec = al16 && ncols == 32;
+    if (row_ok) {
+      if (a.bias) add_row(x, a.bias + nb, ncols, vec, true);
+      if (rowadd_row) add_row(x, rowadd_row + nb, ncols, vec, true);
+      if (res_row) add_row(x, res_row + nb, ncols, vec, false);
+    }
+    if (a.preact) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pre[j] = x[j];
+    }
+    if (a.act == RF_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+    } else if (a.act == RF_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+    }
+    if (a.dact && row_ok) {
+      float t[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = 0.0f;
+      add_row(t, aux_row + nb, ncols, vec, false);
+      if (a.dact == RF_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = t[j] > 0.0f ? x[j] : 0.0f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] *= gelu_erf_grad(t[j]);
+      }
+    }
+    if (a.round_f16) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = __half2float(__float2half_rn(x[j]));
+    }
+  }
+  // direct (non-TMA) store of one chunk
+  __device__ __forceinline__ void store_direct(const Args& a, const float (&v)[32], const float (&pre)[32], int nb, int ncols) const {
+    if (!row_ok) return;
+    if (pre_row) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) pre_row[nb + j] = pre[j];
+    }
+    const bool vec_ok = ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0) && !a.accumulate;
+    if (a.accumulate) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) atomicAdd(c_row + nb + j, v[j]);
+    } else if (vec_ok && ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(c_row + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) c_row[nb + j] = v[j];
+    }
+  }
+  // 128B-swizzled staging of one chunk row for the TMA store (16 B chunk index XOR (row mod 8))
+  static __device__ __forceinline__ void stage_row(uint8_t* buf, int row_in_tile, const float (&v)[32]) {
+    float* row = reinterpret_cast<float*>(buf + row_in_tile * 128);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int slot = (j ^ (row_in_tile & 7)) << 2;
+      *reinterpret_cast<float4*>(row + slot) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
@@ -198,8 +304,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BLOCK_M;
-  const int n0 = blockIdx.y * BLOCK_N;
+  // N-tiles vary fastest in launch order: the CTAs that share one 128-row A panel are resident together, so the panel is read
+  // from HBM once and served from L2 to its siblings (with M fastest a 51 MB activation matrix was re-read ~2.5x, ncu r1 v5)
+  const int n0 = blockIdx.x * BLOCK_N;
+  const int m0 = blockIdx.y * BLOCK_M;
   const int kb_begin = blockIdx.z * a.kb_per_split;
   const int kb_end = min(a.kb_total, kb_begin + a.kb_per_split);
   const int nkb = kb_end - kb_begin;
@@ -440,6 +548,214 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
+// persistent, warp-specialised variant (default)
+// ---------------------------------------------------------------------------------------------
+// One CTA per SM loops over output tiles (N-tiles fastest).  Roles: warp 0 = TMA producer running ahead across tile
+// boundaries over a 4-stage ring; warp 1 = MMA issuer ping-ponging between two TMEM accumulators; warps 2-5 = epilogue
+// (TMEM -> registers -> math -> swizzled smem -> TMA store / reduce-add).  The epilogue of tile j overlaps the operand loads
+// and MMAs of tiles j+1, j+2: for the K=128 layers of the frame encoder (4 k-blocks per tile) the loads never drain.
+constexpr int P_STAGES = 4;
+constexpr int P_THREADS = 192;
+constexpr int EPI_PAIR_BYTES = 32768;  // one (out, preact) staging pair of 2 x 16 KiB
+
+template <int BLOCK_N>
+struct PTile {
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int RING_BYTES = P_STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = RING_BYTES + 2 * EPI_PAIR_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const Args a,
+                            const int tiles_n, const int tiles_m, const int splits) {
+  using T = PTile<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* epi = smem + T::RING_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi + 2 * EPI_PAIR_BYTES);
+  uint64_t* empty_bar = full_bar + P_STAGES;
+  uint64_t* tfull_bar = empty_bar + P_STAGES;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained by the 4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total = tiles_n * tiles_m * splits;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    if (a.tma_store) prefetch_tensormap(&tmC);
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, T::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int t, int& m0, int& n0, int& kb_begin, int& nkb) {
+    const int nt = t % tiles_n;
+    const int r = t / tiles_n;
+    const int mt = r % tiles_m;
+    const int z = r / tiles_m;
+    m0 = mt * BLOCK_M;
+    n0 = nt * BLOCK_N;
+    kb_begin = z * a.kb_per_split;
+    nkb = min(a.kb_total, kb_begin + a.kb_per_split) - kb_begin;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int m0, n0, kb_begin, nkb;
+        decode(t, m0, n0, kb_begin, nkb);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % P_STAGES;
+          const uint32_t ph = (it / P_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], T::STAGE_BYTES);
+          uint8_t* sa = smem + s * T::STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          const int k0 = (kb_begin + i) * BLOCK_K;
+          if (!a.a_mn) {
+            tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BLOCK_M / 32; ++g) tma_load_2d(sa + g * GROUP_BYTES, &tmA, &full_bar[s], m0 + 32 * g, k0);
+          }
+          if (!a.b_mn) {
+            tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BLOCK_N / 32; ++g) tma_load_2d(sb + g * GROUP_BYTES, &tmB, &full_bar[s], n0 + 32 * g, k0);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a.a_mn) << 15) |
+                             (static_cast<uint32_t>(a.b_mn) << 16) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
+                             (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+      int it = 0, j = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+        int m0, n0, kb_begin, nkb;
+        decode(t, m0, n0, kb_begin, nkb);
+        const int ab = j & 1;
+        const uint32_t aph = (j >> 1) & 1;
+        mbar_wait(&tempty_bar[ab], aph ^ 1);  // epilogue has drained this accumulator (passes at once for its first use)
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(ab * BLOCK_N);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % P_STAGES;
+          const uint32_t ph = (it / P_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * T::STAGE_BYTES);
+          const uint32_t b_base = a_base + A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            const uint64_t adesc = a.a_mn ? make_smem_desc(a_base + kk * 1024, GROUP_BYTES, 512, 1)
+                                          : make_smem_desc(a_base + kk * UMMA_K * 4, 16, 1024, 2);
+            const uint64_t bdesc = a.b_mn ? make_smem_desc(b_base + kk * 1024, GROUP_BYTES, 512, 1)
+                                          : make_smem_desc(b_base + kk * UMMA_K * 4, 16, 1024, 2);
+            umma_tf32(tmem_d, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[ab]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4 -------------------------------------------
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const bool elected = threadIdx.x == 64;  // first epilogue thread issues the bulk stores
+    int j = 0, cc = 0;                       // tile counter, running chunk counter (staging pair = cc & 1)
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+      int m0, n0, kb_begin, nkb;
+      decode(t, m0, n0, kb_begin, nkb);
+      const int ab = j & 1;
+      const uint32_t aph = (j >> 1) & 1;
+      RowEpilogue re;
+      re.init(a, m0 + row_in_tile);
+      mbar_wait(&tfull_bar[ab], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(ab * BLOCK_N);
+      int n_chunks = 0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) n_chunks += (n0 + c < a.N) ? 1 : 0;
+#pragma unroll 1
+      for (int ci = 0; ci < n_chunks; ++ci) {
+        const int c = ci * 32;
+        const int nb = n0 + c;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c), r);
+        tmem_wait_ld();
+        if (ci == n_chunks - 1) {  // accumulator fully read by this warp: hand it back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+        }
+        float v[32], pre[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+        const int ncols = min(32, a.N - nb);
+        re.apply(a, v, pre, nb, ncols);
+        if (a.tma_store) {
+          uint8_t* obuf = epi + (cc & 1) * EPI_PAIR_BYTES;
+          uint8_t* pbuf = obuf + 16384;
+          if (cc >= 2) {  // staging pair re-used: its previous bulk store must have finished reading shared memory
+            if (elected) bulk_wait_group_read<1>();
+            epi_bar_sync();
+          }
+          RowEpilogue::stage_row(obuf, row_in_tile, v);
+          if (a.preact) RowEpilogue::stage_row(pbuf, row_in_tile, pre);
+          fence_proxy_async_smem();
+          epi_bar_sync();
+          if (elected) {
+            if (a.accumulate) tma_reduce_add_2d(&tmC, obuf, nb, m0);
+            else if (a.group_in > 0) tma_store_3d(&tmC, obuf, nb, 0, m0 / a.group_in);
+            else tma_store_2d(&tmC, obuf, nb, m0);
+            if (a.preact) tma_store_2d(&tmP, pbuf, nb, m0);
+            bulk_commit_group();
+          }
+          ++cc;
+        } else {
+          re.store_direct(a, v, pre, nb, ncols);
+        }
+      }
+    }
+    if (a.tma_store && elected) bulk_wait_group_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, T::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -517,12 +833,36 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
       if (rc != RF_OK) return rc;
     }
   }
+  static int persistent = -1;
+  if (persistent < 0) {
+    const char* e = getenv("RF_GEMM_PERSISTENT");
+    persistent = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int tiles_n = ceil_div(p->N, BLOCK_N), tiles_m = ceil_div(p->M, BLOCK_M);
+  // Short reductions (<= 12 k-blocks per tile: the K=128/256/384 layers) are epilogue/latency-bound -> persistent kernel whose
+  // loads run ahead across tiles.  Long reductions are L2-bandwidth-bound -> two co-resident tile-wise CTAs per SM keep more
+  // bytes in flight (2 x 3 stages) and measured 25-35 % faster there (profiles/r1_microbench_gemm_*).
+  if (persistent && args.kb_per_split <= 12) {
+    using PT = PTile<BLOCK_N>;
+    static bool attr_p = false;
+    if (!attr_p) {
+      RF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persistent_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT::SMEM_BYTES));
+      attr_p = true;
+    }
+    const long long total = static_cast<long long>(tiles_n) * tiles_m * splits;
+    RF_CHECK_ARG(total <= 2147483647LL, "rf_gemm_tf32: too many tiles");
+    const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
+    gemm_tf32_persistent_kernel<BLOCK_N><<<grid, P_THREADS, PT::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmP, args, tiles_n, tiles_m, splits);
+    RF_LAUNCH_OK();
+    return RF_OK;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     RF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(ceil_div(p->M, BLOCK_M), ceil_div(p->N, BLOCK_N), splits);
+  dim3 grid(tiles_n, tiles_m, splits);
+  RF_CHECK_ARG(grid.y <= 65535, "rf_gemm_tf32: M=%d exceeds 65535 row tiles", p->M);
   gemm_tf32_kernel<BLOCK_N><<<grid, NUM_THREADS, T::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmP, args);
   RF_LAUNCH_OK();
   return RF_OK;
