@@ -41,6 +41,9 @@ extern "C" {
 #define RF_ACT_NONE 0
 #define RF_ACT_RELU 1
 #define RF_ACT_GELU 2 /* exact erf GELU */
+#define RF_ACT_GELU_SAVE_GRAD 3 /* forward only: out = gelu(x) and the `preact` buffer receives gelu'(x) instead of x (the
+                                  derivative shares erf / exp with the activation, so the backward pass need not recompute it) */
+#define RF_DACT_SAVED 3         /* backward only (`dact`): result *= dact_aux (a derivative saved by RF_ACT_GELU_SAVE_GRAD) */
 
 int rf_abi_version(void);
 const char* rf_last_error(void);

@@ -101,6 +101,7 @@ __device__ __forceinline__ void column_sum(const Dims<DH> d, const float* src, i
   const int g = threadIdx.x / dh4, c = threadIdx.x - g * dh4;
   if (g < groups) {
     float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int l = g; l < L; l += groups)
       if (keep(l)) {
         const float4 vv = *reinterpret_cast<const float4*>(src + l * pitch + 4 * c);
@@ -128,12 +129,21 @@ __device__ void select_and_softmax(const RfAttnParams& p, const Dims<DH> d, cons
   } else if (compute_selection && !p.forced_top) {
     const int group = p.idx_group > 0 ? b / p.idx_group : 0;
     const int* idx = p.idx + static_cast<long long>(group) * Lq * p.U;
+    // the [Lq, U] table is copied once, coalesced, into the (still unused) probability buffer: u*Lk >= ... is not guaranteed,
+    // so it is only staged when it fits; otherwise it is read through L1
+    int* sidx = reinterpret_cast<int*>(sm.s);
+    const bool staged = Lq * p.U <= round4(u * Lk);
+    if (staged) {
+      for (int i = threadIdx.x; i < Lq * p.U; i += THREADS) sidx[i] = __ldg(idx + i);
+      __syncthreads();
+    }
     for (int i = threadIdx.x; i < Lq; i += THREADS) {
       const float* qi = sm.q + i * pitch;
-      const int* row = idx + i * p.U;
+      const int* row = (staged ? sidx : idx) + i * p.U;
       float mx = -INFINITY, sum = 0.f;
+#pragma unroll 4
       for (int j = 0; j < p.U; ++j) {
-        const float s = dot4(d, qi, sm.k + __ldg(row + j) * pitch);
+        const float s = dot4(d, qi, sm.k + row[j] * pitch);
         mx = fmaxf(mx, s);
         sum += s;
       }
@@ -146,6 +156,7 @@ __device__ void select_and_softmax(const RfAttnParams& p, const Dims<DH> d, cons
     for (int i = threadIdx.x; i < Lq; i += THREADS) {
       const float mi = sm.m[i];
       int rank = 0;
+#pragma unroll 8
       for (int j = 0; j < Lq; ++j) {
         const float mj = sm.m[j];
         rank += (mj > mi) || (mj == mi && j < i);
@@ -222,6 +233,7 @@ __global__ void __launch_bounds__(THREADS) attention_fwd_kernel(const RfAttnPara
     const float* prow = sm.s + r * Lk;
     const float* vcol = sm.v + 4 * c;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int j = 0; j < Lk; ++j) {
       const float w = prow[j];
       const float4 vv = *reinterpret_cast<const float4*>(vcol + j * pitch);
@@ -315,6 +327,7 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r >= 0) {
       const float* row = s_ds + r * Lk;
+#pragma unroll 4
       for (int j = 0; j < Lk; ++j) {
         const float w = row[j];
         const float4 kk = *reinterpret_cast<const float4*>(sm.k + j * pitch + 4 * c);
@@ -330,6 +343,7 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
   for (int i = threadIdx.x; i < Lk * dh4; i += THREADS) {
     const int j = i / dh4, c = i - j * dh4;
     float4 ak = make_float4(0.f, 0.f, 0.f, 0.f), av = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int r = 0; r < u; ++r) {
       const int qi = sm.top[r];
       const float ws = s_ds[r * Lk + j], wp = sm.s[r * Lk + j];

@@ -73,7 +73,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // e = exp(-x^2) is passed in so that the GELU derivative can share it with its Gaussian term.
 __device__ __forceinline__ float erf_as(float x, float e) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));  // MUFU.RCP, 1 ulp
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
@@ -83,6 +83,14 @@ __device__ __forceinline__ float erf_as(float x, float e) {
 __device__ __forceinline__ float gelu_erf(float x) {  // exact-erf GELU (F.gelu default): 0.5 x (1 + erf(x / sqrt 2))
   const float z = x * 0.70710678118654752440f;
   return 0.5f * x * (1.0f + erf_as(z, __expf(-z * z)));
+}
+// gelu(x) and gelu'(x) together: erf and exp are shared
+__device__ __forceinline__ float gelu_erf_with_grad(float x, float& grad) {
+  const float z = x * 0.70710678118654752440f;
+  const float e = __expf(-z * z);
+  const float cdf = 0.5f * (1.0f + erf_as(z, e));
+  grad = cdf + x * 0.39894228040143267794f * e;
+  return x * cdf;
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {  // Phi(x) + x phi(x)
   const float z = x * 0.70710678118654752440f;

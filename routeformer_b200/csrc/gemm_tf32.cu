@@ -224,7 +224,7 @@ struct RowEpilogue {
       if (rowadd_row) add_row(x, rowadd_row + nb, ncols, vec, true);
       if (res_row) add_row(x, res_row + nb, ncols, vec, false);
     }
-    if (a.preact) {
+    if (a.preact && a.act != RF_ACT_GELU_SAVE_GRAD) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) pre[j] = x[j];
     }
@@ -234,6 +234,9 @@ struct RowEpilogue {
     } else if (a.act == RF_ACT_GELU) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+    } else if (a.act == RF_ACT_GELU_SAVE_GRAD) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = gelu_erf_with_grad(x[j], pre[j]);
     }
     if (a.dact && row_ok) {
       float t[32];
@@ -243,6 +246,9 @@ struct RowEpilogue {
       if (a.dact == RF_ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = t[j] > 0.0f ? x[j] : 0.0f;
+      } else if (a.dact == RF_DACT_SAVED) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] *= t[j];
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] *= gelu_erf_grad(t[j]);
@@ -394,67 +400,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const bool row_ok = m < a.M;
   long long out_row = m;
   if (a.group_in > 0) out_row = static_cast<long long>(m / a.group_in) * a.group_out + (m % a.group_in) + a.row_offset;
-  float* c_row = a.C + out_row * a.ldc;
-  const float* rowadd_row = a.rowadd ? a.rowadd + static_cast<long long>(m % a.rowadd_period) * a.ld_rowadd : nullptr;
-  const float* res_row = a.residual ? a.residual + static_cast<long long>(m) * a.ld_res : nullptr;
-  float* pre_row = a.preact ? a.preact + static_cast<long long>(m) * a.ld_pre : nullptr;
-  const float* aux_row = a.dact ? a.dact_aux + static_cast<long long>(m) * a.ld_aux : nullptr;
-  const bool vec_ok = ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0) && !a.accumulate;
-
-  // Epilogue math on one 32-column chunk of this thread's row.  Every option is tested ONCE per chunk (not per element) and
-  // the operand rows are fetched as 8 independent 16 B loads, so the chunk is a short straight-line block per option.
-  const bool al16 = ((reinterpret_cast<uintptr_t>(a.bias) | reinterpret_cast<uintptr_t>(a.rowadd) | reinterpret_cast<uintptr_t>(a.residual) |
-                      reinterpret_cast<uintptr_t>(a.dact_aux)) & 15) == 0 &&
-                    ((a.ld_rowadd | a.ld_res | a.ld_aux) & 3) == 0;
-  auto add_row = [&](float (&x)[32], const float* src, int ncols, bool vec, bool ro) {
-    if (vec) {
-      float4 t[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) t[q] = ro ? __ldg(reinterpret_cast<const float4*>(src) + q) : reinterpret_cast<const float4*>(src)[q];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) { x[4 * q] += t[q].x; x[4 * q + 1] += t[q].y; x[4 * q + 2] += t[q].z; x[4 * q + 3] += t[q].w; }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) x[j] += src[j];
-    }
-  };
-  auto finish_chunk = [&](float (&x)[32], float (&pre)[32], int nb, int ncols) {
-    const bool vec = al16 && ncols == 32;
-    if (row_ok) {
-      if (a.bias) add_row(x, a.bias + nb, ncols, vec, true);
-      if (rowadd_row) add_row(x, rowadd_row + nb, ncols, vec, true);
-      if (res_row) add_row(x, res_row + nb, ncols, vec, false);
-    }
-    if (a.preact) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) pre[j] = x[j];
-    }
-    if (a.act == RF_ACT_RELU) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
-    } else if (a.act == RF_ACT_GELU) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
-    }
-    if (a.dact && row_ok) {
-      float t[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) t[j] = 0.0f;
-      add_row(t, aux_row + nb, ncols, vec, false);
-      if (a.dact == RF_ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = t[j] > 0.0f ? x[j] : 0.0f;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] *= gelu_erf_grad(t[j]);
-      }
-    }
-    if (a.round_f16) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = __half2float(__float2half_rn(x[j]));
-    }
-  };
+  RowEpilogue re;
+  re.init(a, m);
 
   if (a.tma_store) {
     // ---- staged path: 128x32 fp32 chunks -> 128B-swizzled smem (the idle pipeline stages) -> TMA bulk store --------
@@ -479,7 +426,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float v[32], pre[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      finish_chunk(v, pre, nb, min(32, a.N - nb));
+      re.apply(a, v, pre, nb, min(32, a.N - nb));
       float* orow = reinterpret_cast<float*>(obuf + row_in_tile * 128);
       float* prow = reinterpret_cast<float*>(pbuf + row_in_tile * 128);
 #pragma unroll
@@ -518,25 +465,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float v[32], pre[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      finish_chunk(v, pre, nb, ncols);
-      if (pre_row) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols) pre_row[nb + j] = pre[j];
-      }
-      if (a.accumulate) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols) atomicAdd(c_row + nb + j, v[j]);
-      } else if (vec_ok && ncols == 32) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(c_row + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols) c_row[nb + j] = v[j];
-      }
+      re.apply(a, v, pre, nb, ncols);
+      re.store_direct(a, v, pre, nb, ncols);
     }
   }
 
@@ -551,26 +481,27 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // persistent, warp-specialised variant (default)
 // ---------------------------------------------------------------------------------------------
 // One CTA per SM loops over output tiles (N-tiles fastest).  Roles: warp 0 = TMA producer running ahead across tile
-// boundaries over a 4-stage ring; warp 1 = MMA issuer ping-ponging between two TMEM accumulators; warps 2-5 = epilogue
+// boundaries over a 3-stage ring; warp 1 = MMA issuer ping-ponging between two TMEM accumulators; warps 2-9 = epilogue
 // (TMEM -> registers -> math -> swizzled smem -> TMA store / reduce-add).  The epilogue of tile j overlaps the operand loads
 // and MMAs of tiles j+1, j+2: for the K=128 layers of the frame encoder (4 k-blocks per tile) the loads never drain.
-constexpr int P_STAGES = 4;
-constexpr int P_THREADS = 192;
-constexpr int EPI_PAIR_BYTES = 32768;  // one (out, preact) staging pair of 2 x 16 KiB
+constexpr int P_STAGES = 3;
+constexpr int P_EPI_WARPS = 8;         // two warps per TMEM lane quarter: each takes one half of the tile's columns
+constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;
+constexpr int EPI_PAIR_BYTES = 32768;  // one (out, preact) staging pair of 2 x 16 KiB; 2 pairs per column half
 
 template <int BLOCK_N>
 struct PTile {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = P_STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = RING_BYTES + 2 * EPI_PAIR_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = RING_BYTES + 4 * EPI_PAIR_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int half) { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); }
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(P_THREADS, 1)
@@ -581,10 +512,10 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* epi = smem + T::RING_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi + 2 * EPI_PAIR_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi + 4 * EPI_PAIR_BYTES);
   uint64_t* empty_bar = full_bar + P_STAGES;
   uint64_t* tfull_bar = empty_bar + P_STAGES;   // [2] accumulator ready
-  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained by the 4 epilogue warps
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained by the 8 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -601,7 +532,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);
+      mbar_init(&tempty_bar[b], P_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -688,11 +619,16 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4 -------------------------------------------
+    // ---------------- epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 -------------------
+    // The K=128 layers are epilogue-bound (bias / GELU / derivative / two outputs per element), so 8 warps share one tile:
+    // both halves drain the accumulator concurrently, each with its own staging buffers, named barrier and bulk-store issuer.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
-    const bool elected = threadIdx.x == 64;  // first epilogue thread issues the bulk stores
-    int j = 0, cc = 0;                       // tile counter, running chunk counter (staging pair = cc & 1)
+    const bool elected = threadIdx.x == 64 + half * 128;  // first thread of each half issues that half's bulk stores
+    uint8_t* epi_half = epi + half * 2 * EPI_PAIR_BYTES;
+    constexpr int HALF_N = BLOCK_N / 2;
+    int j = 0, cc = 0;  // tile counter, running chunk counter of this half (staging pair = cc & 1)
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
       int m0, n0, kb_begin, nkb;
       decode(t, m0, n0, kb_begin, nkb);
@@ -702,18 +638,24 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       re.init(a, m0 + row_in_tile);
       mbar_wait(&tfull_bar[ab], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(ab * BLOCK_N);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(ab * BLOCK_N + half * HALF_N);
+      const int nh = n0 + half * HALF_N;
       int n_chunks = 0;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) n_chunks += (n0 + c < a.N) ? 1 : 0;
+      for (int c = 0; c < HALF_N; c += 32) n_chunks += (nh + c < a.N) ? 1 : 0;
+      if (n_chunks == 0) {  // this half lies entirely beyond N: nothing to read, release the accumulator right away
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+      }
 #pragma unroll 1
       for (int ci = 0; ci < n_chunks; ++ci) {
         const int c = ci * 32;
-        const int nb = n0 + c;
+        const int nb = nh + c;
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c), r);
         tmem_wait_ld();
-        if (ci == n_chunks - 1) {  // accumulator fully read by this warp: hand it back to the MMA issuer
+        if (ci == n_chunks - 1) {  // accumulator columns of this warp fully read: hand them back to the MMA issuer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[ab]);
@@ -724,16 +666,16 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         const int ncols = min(32, a.N - nb);
         re.apply(a, v, pre, nb, ncols);
         if (a.tma_store) {
-          uint8_t* obuf = epi + (cc & 1) * EPI_PAIR_BYTES;
+          uint8_t* obuf = epi_half + (cc & 1) * EPI_PAIR_BYTES;
           uint8_t* pbuf = obuf + 16384;
           if (cc >= 2) {  // staging pair re-used: its previous bulk store must have finished reading shared memory
             if (elected) bulk_wait_group_read<1>();
-            epi_bar_sync();
+            epi_bar_sync(half);
           }
           RowEpilogue::stage_row(obuf, row_in_tile, v);
           if (a.preact) RowEpilogue::stage_row(pbuf, row_in_tile, pre);
           fence_proxy_async_smem();
-          epi_bar_sync();
+          epi_bar_sync(half);
           if (elected) {
             if (a.accumulate) tma_reduce_add_2d(&tmC, obuf, nb, m0);
             else if (a.group_in > 0) tma_store_3d(&tmC, obuf, nb, 0, m0 / a.group_in);
@@ -890,6 +832,7 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
                "rf_gemm_tf32: leading dimension smaller than the row length");
   RF_CHECK_ARG(!p->rowadd || p->rowadd_period > 0, "rf_gemm_tf32: rowadd needs rowadd_period > 0");
   RF_CHECK_ARG(!p->dact || p->dact_aux, "rf_gemm_tf32: dact needs dact_aux");
+  RF_CHECK_ARG(p->act != RF_ACT_GELU_SAVE_GRAD || p->preact, "rf_gemm_tf32: RF_ACT_GELU_SAVE_GRAD needs the preact buffer");
   const int kb_total = ceil_div(p->K, gemm::BLOCK_K);
   const bool plain = !p->bias && !p->rowadd && !p->residual && p->act == RF_ACT_NONE && !p->preact && !p->dact && !p->round_f16;
   int splits = p->split_k;

@@ -217,8 +217,9 @@ class FFNBlock(Function):
         dff = w1.shape[0]
         w1m, w2m = w1.view(dff, D), w2.view(D, dff)
         h = torch.empty(M, dff, device=x.device, dtype=torch.float32)
+        # GELU: the forward epilogue stores gelu'(pre) (it shares erf/exp with gelu), the backward only multiplies by it
         pre = torch.empty(M, dff, device=x.device, dtype=torch.float32) if act == ops.ACT_GELU else None
-        ops.gemm(x, w1m, h, bias=b1, act=act, preact=pre)
+        ops.gemm(x, w1m, h, bias=b1, act=ops.ACT_GELU_SAVE_GRAD if act == ops.ACT_GELU else act, preact=pre)
         y = torch.empty(M, D, device=x.device, dtype=torch.float32)
         ops.gemm(h, w2m, y, bias=b2, residual=x)
         ctx.act = act
@@ -240,8 +241,10 @@ class FFNBlock(Function):
         if g is not None:
             ops.colsum_accumulate(dy, g)
         dpre = torch.empty(M, dff, device=x.device, dtype=torch.float32)
-        aux = pre if ctx.act == ops.ACT_GELU else h  # relu'(pre) = [h > 0]
-        ops.gemm(dy, w2.view(D, dff), dpre, b_mn=True, dact=ctx.act, dact_aux=aux)
+        if ctx.act == ops.ACT_GELU:
+            ops.gemm(dy, w2.view(D, dff), dpre, b_mn=True, dact=ops.DACT_SAVED, dact_aux=pre)
+        else:
+            ops.gemm(dy, w2.view(D, dff), dpre, b_mn=True, dact=ctx.act, dact_aux=h)  # relu'(pre) = [h > 0]
         g = grad_buffer(w1)
         if g is not None:
             ops.gemm(dpre, x, g.view(dff, D), a_mn=True, b_mn=True, accumulate=True)

@@ -15,6 +15,8 @@ from ._lib import check
 
 F32, F16, BF16, U8 = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+ACT_GELU_SAVE_GRAD = 3  # forward: out = gelu(x), `preact` receives gelu'(x)
+DACT_SAVED = 3          # backward: multiply by the saved derivative in `dact_aux`
 ATTN_PROB, ATTN_PROB_MASKED, ATTN_FULL = 0, 1, 2
 LAYOUT_BLHD, LAYOUT_BHLD = 0, 1
 ACT_CODES = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU}

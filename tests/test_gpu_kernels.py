@@ -99,6 +99,20 @@ def test_gemm_dact_and_accumulate(ops):
         out = torch.empty(M, K, device=DEV)
         ops.gemm(dY.to(DEV), W.to(DEV), out, b_mn=True, dact=code, dact_aux=pre.to(DEV))
         assert rel_err(out.cpu(), (dY.double() @ W.double()).float() * grad) < 2e-3
+    # the FFN pairing: forward stores gelu'(pre) beside gelu(pre), backward multiplies by the saved derivative
+    Xs, W1 = torch.randn(M, N, generator=gen), torch.randn(K, N, generator=gen) / math.sqrt(N)
+    b1 = torch.randn(K, generator=gen)
+    pre_ref = ((Xs.double() @ W1.double().t()) + b1).float().requires_grad_()
+    F.gelu(pre_ref).sum().backward()
+    h, saved = torch.empty(M, K, device=DEV), torch.empty(M, K, device=DEV)
+    ops.gemm(Xs.to(DEV), W1.to(DEV), h, bias=b1.to(DEV), act=ops.ACT_GELU_SAVE_GRAD, preact=saved)
+    assert rel_err(h.cpu(), F.gelu(pre_ref.detach())) < 2e-3
+    assert rel_err(saved.cpu(), pre_ref.grad) < 2e-3
+    out = torch.empty(M, K, device=DEV)
+    ops.gemm(dY.to(DEV), W.to(DEV), out, b_mn=True, dact=ops.DACT_SAVED, dact_aux=saved)
+    assert rel_err(out.cpu(), (dY.double() @ W.double()).float() * pre_ref.grad) < 2e-3
+    with pytest.raises(RuntimeError):
+        ops.gemm(Xs.to(DEV), W1.to(DEV), h, act=ops.ACT_GELU_SAVE_GRAD)
 
 
 # ------------------------------------------------------------------------------------------------ FoV crop
