@@ -217,12 +217,33 @@ struct RowEpilogue {
         if (j < ncols) x[j] += src[j];
     }
   }
+  // The per-row side operand (activation-derivative input if any, else the residual) does not depend on the accumulator:
+  // the persistent kernel issues its loads BEFORE waiting for the MMAs of the tile, hiding the global-memory round trip.
+  __device__ __forceinline__ bool side_prefetch(const Args& a, int nb, int ncols, float4 (&s)[8]) const {
+    const float* row = a.dact ? aux_row : res_row;
+    if (!row || !row_ok || !(al16 && ncols == 32)) return false;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] = reinterpret_cast<const float4*>(row + nb)[q];
+    return true;
+  }
   __device__ __forceinline__ void apply(const Args& a, float (&x)[32], float (&pre)[32], int nb, int ncols) const {
+    float4 none[8];
+    apply(a, x, pre, nb, ncols, false, none);
+  }
+  __device__ __forceinline__ void apply(const Args& a, float (&x)[32], float (&pre)[32], int nb, int ncols, bool have_side,
+                                        const float4 (&side)[8]) const {
     const bool vec = al16 && ncols == 32;
+    const bool side_is_res = have_side && !a.dact;
+    const bool side_is_aux = have_side && a.dact;
     if (row_ok) {
       if (a.bias) add_row(x, a.bias + nb, ncols, vec, true);
       if (rowadd_row) add_row(x, rowadd_row + nb, ncols, vec, true);
-      if (res_row) add_row(x, res_row + nb, ncols, vec, false);
+      if (side_is_res) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { x[4 * q] += side[q].x; x[4 * q + 1] += side[q].y; x[4 * q + 2] += side[q].z; x[4 * q + 3] += side[q].w; }
+      } else if (res_row) {
+        add_row(x, res_row + nb, ncols, vec, false);
+      }
     }
     if (a.preact && a.act != RF_ACT_GELU_SAVE_GRAD) {
 #pragma unroll
@@ -240,9 +261,14 @@ struct RowEpilogue {
     }
     if (a.dact && row_ok) {
       float t[32];
+      if (side_is_aux) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) t[j] = 0.0f;
-      add_row(t, aux_row + nb, ncols, vec, false);
+        for (int q = 0; q < 8; ++q) { t[4 * q] = side[q].x; t[4 * q + 1] = side[q].y; t[4 * q + 2] = side[q].z; t[4 * q + 3] = side[q].w; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] = 0.0f;
+        add_row(t, aux_row + nb, ncols, vec, false);
+      }
       if (a.dact == RF_ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = t[j] > 0.0f ? x[j] : 0.0f;
@@ -504,7 +530,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void epi_bar_sync(int half) { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(P_THREADS, 1)
+__global__ void __launch_bounds__(P_THREADS, 1)  // registers are granted per 4 warps: 320 threads count as 384 -> 168 per thread
 gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const Args a,
                             const int tiles_n, const int tiles_m, const int splits) {
@@ -636,13 +662,15 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const uint32_t aph = (j >> 1) & 1;
       RowEpilogue re;
       re.init(a, m0 + row_in_tile);
+      const int nh = n0 + half * HALF_N;
+      int n_chunks = 0;
+#pragma unroll
+      for (int c = 0; c < HALF_N; c += 32) n_chunks += (nh + c < a.N) ? 1 : 0;
+      float4 side[8];  // side operand of the NEXT chunk to process, loaded ahead of its use
+      bool have_side = n_chunks > 0 && re.side_prefetch(a, nh, min(32, a.N - nh), side);
       mbar_wait(&tfull_bar[ab], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(ab * BLOCK_N + half * HALF_N);
-      const int nh = n0 + half * HALF_N;
-      int n_chunks = 0;
-#pragma unroll 1
-      for (int c = 0; c < HALF_N; c += 32) n_chunks += (nh + c < a.N) ? 1 : 0;
       if (n_chunks == 0) {  // this half lies entirely beyond N: nothing to read, release the accumulator right away
         tc_fence_before();
         __syncwarp();
@@ -664,7 +692,8 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 #pragma unroll
         for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
         const int ncols = min(32, a.N - nb);
-        re.apply(a, v, pre, nb, ncols);
+        re.apply(a, v, pre, nb, ncols, have_side, side);
+        have_side = ci + 1 < n_chunks && re.side_prefetch(a, nb + 32, min(32, a.N - (nb + 32)), side);
         if (a.tma_store) {
           uint8_t* obuf = epi_half + (cc & 1) * EPI_PAIR_BYTES;
           uint8_t* pbuf = obuf + 16384;

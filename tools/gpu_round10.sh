@@ -2,5 +2,5 @@
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "gemm or conv3" --timeout 120 -p no:cacheprovider 2>&1 | tail -4
 timeout 600 python -m pytest tests/test_gpu_model.py -q -m gpu --timeout 300 -p no:cacheprovider 2>&1 | tail -4
-PYTHONPATH=. timeout 200 python tools/gemm_epi_bench.py 2>&1 | tee gpurun_out/gemm_epi_v2.log
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v10.log 2>&1; grep "^{" gpurun_out/bench_v10.log | cut -c1-220; tail -2 gpurun_out/bench_v10.log | cut -c1-300
+PYTHONPATH=. timeout 200 python tools/gemm_epi_bench.py 2>&1 | tee gpurun_out/gemm_epi_v3.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v11.log 2>&1; grep "^{" gpurun_out/bench_v11.log | cut -c1-220; tail -2 gpurun_out/bench_v11.log | cut -c1-300
