@@ -37,6 +37,11 @@ CASES = {
                          SMALL_SPEC, "tiny", 2, 5, 7, "eval"),
     "no_gaze_small": ({**SMALL, "with_gaze": False}, SMALL_SPEC, "tiny", 2, 8, 9, "eval"),
     "no_scene_small": ({**SMALL, "with_scene": False}, SMALL_SPEC, "tiny", 2, 8, 10, "eval"),
+    # routeformer.py:164-197: 30 predictions in windows of 8 (4 windows, the last one truncated) and of 15 with rotation.
+    # GPS-only autoregression is not a case: the reference slices its empty visual-feature LIST there and raises TypeError (:187)
+    "autoregressive_small": ({**SMALL, "autoregressive": True, "autoregressive_step_size": 8}, SMALL_SPEC, "tiny", 2, 13, 14, "eval"),
+    "autoregressive_dreyeve_small": ({**SMALL, "rotate_motion": True, "autoregressive": True, "autoregressive_step_size": 15},
+                                     SMALL_SPEC, "tiny", 3, 15, 16, "eval"),
     "sparse_small": ({**SMALL, "dense_prediction": False, "decoder_mode": "vanilla"}, SMALL_SPEC, "tiny", 2, 11, 12, "eval"),
 }
 

@@ -137,6 +137,7 @@ def build_reference_model(cfg, spec=None):
         cross_modal_decoder_heads=cfg.cross_modal_decoder_heads,
         cross_modal_decoder_layers=cfg.cross_modal_decoder_layers,
         view_dropout=cfg.view_dropout, gaze_dropout=cfg.gaze_dropout, feature_dropout=0.0,
+        autoregressive=cfg.autoregressive, autoregressive_step_size=cfg.autoregressive_step_size,
         output_fps=cfg.output_fps, video_backbone_config=ref.VideoBackboneConfig() if cfg.with_video else None,
     )
     backbone = make_ref_backbone_class(spec) if cfg.with_video else None

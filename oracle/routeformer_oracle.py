@@ -66,6 +66,8 @@ class OracleConfig:
     only_motion: bool = False
     view_dropout: float = 0.0
     gaze_dropout: float = 0.0
+    autoregressive: bool = False  # models/config.py:36-38 (eval only)
+    autoregressive_step_size: int = 1
     # Perceive* hard defaults (cross_modal_transformer.py:378-379,443)
     perceive_factor: int = 5
     perceive_d_model: int = 128
@@ -591,12 +593,32 @@ class Routeformer:
         return mv, wp, dense
 
     def forward(self, batch: dict, training: bool = False, draw=None):
-        """routeformer.py:124-202 (non-autoregressive branch)."""
+        """routeformer.py:124-202, both branches."""
         draw = draw or CpuRandint()
+        cfg = self.cfg
         motion, visual = self.preprocess(batch, training, draw)
-        out = self.backbone_forward(motion, visual, training, draw)
-        _, wp, dense = self.postprocess(batch["gps"][:, -1:, :], out)
-        return (wp, dense) if self.cfg.dense_prediction else wp
+        last_gps = batch["gps"][:, -1:, :]
+        if training or not cfg.autoregressive:
+            out = self.backbone_forward(motion, visual, training, draw)
+            _, wp, dense = self.postprocess(last_gps, out)
+        else:
+            # routeformer.py:164-197: windows of `step` predictions; the window slides over the model's own motion vectors
+            # and predicted visual features, the anchor moves to the last predicted position.
+            if not cfg.with_video:  # the reference slices its empty visual-feature list here (:187)
+                raise TypeError("list indices must be integers or slices, not tuple")
+            step, done, wps, denses = cfg.autoregressive_step_size, 0, [], []
+            while done < cfg.pred_len:
+                out = self.backbone_forward(motion, visual, training, draw, pred_len=step)
+                mv, wp_s, dense_s = self.postprocess(last_gps, out)
+                wps.append(wp_s)
+                denses.append(dense_s)
+                motion = torch.cat([motion[:, step:], mv], dim=1)
+                last_gps = wp_s[:, -1:, :]
+                visual = torch.cat([visual[:, step:], dense_s], dim=1)  # needs dense_prediction, as in the reference
+                done += step
+            wp = torch.cat(wps, dim=1)[:, : cfg.pred_len]
+            dense = torch.cat(denses, dim=1)[:, : cfg.pred_len] if cfg.with_video else None
+        return (wp, dense) if cfg.dense_prediction else wp
 
 
 # --------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "librouteformer_b200.so")
+LIB_PATH = os.environ.get("RF_LIB_PATH") or os.path.join(HERE, "_lib", "librouteformer_b200.so")  # RF_LIB_PATH: A/B-test a prebuilt library
 
 c_fp = C.c_void_p  # device pointers travel as plain addresses
 c_ll = C.c_longlong
@@ -142,7 +142,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing:
+    if build_if_missing and not os.environ.get("RF_LIB_PATH"):
         try:
             from . import build as _build
 

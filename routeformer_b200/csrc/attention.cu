@@ -13,6 +13,8 @@
 //     rows are padded to dh+4 floats (16 B aligned, conflict-free for 128-bit shared loads);
 //   * no integer division by run-time values in inner loops: work is walked as (warp -> row, lane -> column);
 //   * scores + softmax of one selected query stay in the registers of one warp (shuffle reductions), P is written once.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rf {
@@ -51,23 +53,72 @@ __device__ __forceinline__ void load_tile(const Dims<DH> d, float* dst, const fl
   }
 }
 
+// Packed fp32 arithmetic (Blackwell FFMA2: two IEEE fp32 FMAs per issue slot).  Each half is an ordinary fma.rn, so results are
+// bit-identical to the scalar formulation with the same accumulation order; these kernels are issue-bound, halving the FMA
+// instruction count is a direct win.
+#ifndef RF_ATTN_FFMA2
+#define RF_ATTN_FFMA2 1
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi);
+__device__ __forceinline__ float2 unpack2(f32x2 v);
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+#if RF_ATTN_FFMA2
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+#else
+  const float2 x = unpack2(a), y = unpack2(b), z = unpack2(c);
+  return pack2(fmaf(x.x, y.x, z.x), fmaf(x.y, y.y, z.y));
+#endif
+}
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+// acc(4 channels as two pairs) += w * x(4 channels); the scalar w is a broadcast operand of FFMA2
+struct Acc4 {
+  f32x2 lo, hi;
+  __device__ __forceinline__ Acc4() : lo(0ull), hi(0ull) {}
+  __device__ __forceinline__ void fma(float w, const float* x4) {
+    const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(x4);
+    const f32x2 ww = pack2(w, w);
+    lo = ffma2(ww, x.x, lo);
+    hi = ffma2(ww, x.y, hi);
+  }
+  __device__ __forceinline__ float4 get() const {
+    const float2 a = unpack2(lo), b = unpack2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+
+// a . b over dh channels: lanes (0,1) of one packed accumulator take channels (4c, 4c+1) then (4c+2, 4c+3)
 template <int DH>
 __device__ __forceinline__ float dot4(const Dims<DH> d, const float* a, const float* b) {
-  float acc0 = 0.f, acc1 = 0.f;
+  f32x2 acc = 0ull;
   if (DH != 0) {
 #pragma unroll
     for (int c = 0; c < (DH ? DH / 4 : 1); ++c) {
-      const float4 x = reinterpret_cast<const float4*>(a)[c], y = reinterpret_cast<const float4*>(b)[c];
-      acc0 = fmaf(x.x, y.x, acc0); acc1 = fmaf(x.y, y.y, acc1); acc0 = fmaf(x.z, y.z, acc0); acc1 = fmaf(x.w, y.w, acc1);
+      const ulonglong2 x = reinterpret_cast<const ulonglong2*>(a)[c], y = reinterpret_cast<const ulonglong2*>(b)[c];
+      acc = ffma2(x.x, y.x, acc);
+      acc = ffma2(x.y, y.y, acc);
     }
   } else {
     const int dh4 = d.dh4();
     for (int c = 0; c < dh4; ++c) {
-      const float4 x = reinterpret_cast<const float4*>(a)[c], y = reinterpret_cast<const float4*>(b)[c];
-      acc0 = fmaf(x.x, y.x, acc0); acc1 = fmaf(x.y, y.y, acc1); acc0 = fmaf(x.z, y.z, acc0); acc1 = fmaf(x.w, y.w, acc1);
+      const ulonglong2 x = reinterpret_cast<const ulonglong2*>(a)[c], y = reinterpret_cast<const ulonglong2*>(b)[c];
+      acc = ffma2(x.x, y.x, acc);
+      acc = ffma2(x.y, y.y, acc);
     }
   }
-  return acc0 + acc1;
+  const float2 r = unpack2(acc);
+  return r.x + r.y;
 }
 
 __device__ __forceinline__ Smem carve(float* base, int Lq, int Lk, int u, int dh, int pitch) {
@@ -195,7 +246,7 @@ __device__ void select_and_softmax(const RfAttnParams& p, const Dims<DH> d, cons
 #pragma unroll
     for (int t = 0; t < MAX_KEYS_PER_LANE; ++t) {
       if (32 * t >= Lk) break;  // warp-uniform: no work (and no issue slots) for key slots beyond Lk
-      const float e = (lane + 32 * t < Lk) ? expf(sc[t] - mx) : 0.f;
+      const float e = (lane + 32 * t < Lk) ? __expf(sc[t] - mx) : 0.f;  // ex2.approx: 2 ulp, same call in fwd and bwd
       sc[t] = e;
       sum += e;
     }
@@ -232,14 +283,10 @@ __global__ void __launch_bounds__(THREADS) attention_fwd_kernel(const RfAttnPara
     const int r = i / dh4, c = i - r * dh4;
     const float* prow = sm.s + r * Lk;
     const float* vcol = sm.v + 4 * c;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    Acc4 acc;
 #pragma unroll 4
-    for (int j = 0; j < Lk; ++j) {
-      const float w = prow[j];
-      const float4 vv = *reinterpret_cast<const float4*>(vcol + j * pitch);
-      acc.x = fmaf(w, vv.x, acc.x); acc.y = fmaf(w, vv.y, acc.y); acc.z = fmaf(w, vv.z, acc.z); acc.w = fmaf(w, vv.w, acc.w);
-    }
-    *reinterpret_cast<float4*>(p.out + out_offset(p, b, h, sm.top[r]) + 4 * c) = acc;
+    for (int j = 0; j < Lk; ++j) acc.fma(prow[j], vcol + j * pitch);
+    *reinterpret_cast<float4*>(p.out + out_offset(p, b, h, sm.top[r]) + 4 * c) = acc.get();
   }
   // unselected queries: mean(V) (unmasked) or cumsum(V) (masked)
   if (p.mode == RF_ATTN_PROB) {
@@ -324,17 +371,13 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
   for (int i = threadIdx.x; i < Lq * dh4; i += THREADS) {
     const int l = i / dh4, c = i - l * dh4;
     const int r = sm.sel[l];
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    Acc4 acc;
     if (r >= 0) {
       const float* row = s_ds + r * Lk;
 #pragma unroll 4
-      for (int j = 0; j < Lk; ++j) {
-        const float w = row[j];
-        const float4 kk = *reinterpret_cast<const float4*>(sm.k + j * pitch + 4 * c);
-        acc.x = fmaf(w, kk.x, acc.x); acc.y = fmaf(w, kk.y, acc.y); acc.z = fmaf(w, kk.z, acc.z); acc.w = fmaf(w, kk.w, acc.w);
-      }
+      for (int j = 0; j < Lk; ++j) acc.fma(row[j], sm.k + j * pitch + 4 * c);
     }
-    *reinterpret_cast<float4*>(dq + static_cast<long long>(l) * p.q_ls + 4 * c) = acc;
+    *reinterpret_cast<float4*>(dq + static_cast<long long>(l) * p.q_ls + 4 * c) = acc.get();
   }
   // dK and dV: one thread per (key j, 4 channels), loop over the selected rows
   float* dk = bp.dk + b * p.k_bs + h * dh;
@@ -342,16 +385,14 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
   const float inv_lk = 1.f / Lk;
   for (int i = threadIdx.x; i < Lk * dh4; i += THREADS) {
     const int j = i / dh4, c = i - j * dh4;
-    float4 ak = make_float4(0.f, 0.f, 0.f, 0.f), av = make_float4(0.f, 0.f, 0.f, 0.f);
+    Acc4 acck, accv;
 #pragma unroll 4
     for (int r = 0; r < u; ++r) {
       const int qi = sm.top[r];
-      const float ws = s_ds[r * Lk + j], wp = sm.s[r * Lk + j];
-      const float4 qq = *reinterpret_cast<const float4*>(sm.q + qi * pitch + 4 * c);
-      const float4 oo = *reinterpret_cast<const float4*>(s_do + qi * pitch + 4 * c);
-      ak.x = fmaf(ws, qq.x, ak.x); ak.y = fmaf(ws, qq.y, ak.y); ak.z = fmaf(ws, qq.z, ak.z); ak.w = fmaf(ws, qq.w, ak.w);
-      av.x = fmaf(wp, oo.x, av.x); av.y = fmaf(wp, oo.y, av.y); av.z = fmaf(wp, oo.z, av.z); av.w = fmaf(wp, oo.w, av.w);
+      acck.fma(s_ds[r * Lk + j], sm.q + qi * pitch + 4 * c);
+      accv.fma(sm.s[r * Lk + j], s_do + qi * pitch + 4 * c);
     }
+    float4 ak = acck.get(), av = accv.get();
     if (p.mode == RF_ATTN_PROB) {
       const float4 f4 = *reinterpret_cast<const float4*>(sm.acc + 4 * c);
       av.x += f4.x * inv_lk; av.y += f4.y * inv_lk; av.z += f4.z * inv_lk; av.w += f4.w * inv_lk;
@@ -370,6 +411,379 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small-problem ProbSparse path: mode PROB, head dim 8 / 16, Lk <= 96, Lq*Lk scores fit in shared memory.
+//
+// The generic kernels above are bound by shared-memory bandwidth, not arithmetic (ncu: LSU shared wavefronts ~77 % busy, FMA
+// pipe < 20 %): every dot product re-reads a key row (4 x LDS.128 per lane).  For the frame encoder (1536 sequences x 8 heads,
+// L = 65, dh = 16: 2/3 of all attention time) the operands are re-organised around registers instead:
+//   * lane j of a "key-slot" warp keeps key row j (and, in the backward pass, value row j) in REGISTERS; the query rows arrive
+//     as warp-wide broadcast loads (1 wavefront each), so one raw score costs 0.16 wavefronts instead of ~0.6;
+//   * the full raw score matrix S = Q K^T [Lq][Lk] is produced ONCE: the sparsity measure gathers its sampled entries from it
+//     and the selected rows are soft-maxed in place, so the selected queries need no second round of dot products;
+//   * dK / dV accumulate in registers of the lane that owns key j and leave through one 64 B row store each.
+// Arithmetic order of every reduction is fixed (deterministic) and identical between forward and the backward recompute.
+// ---------------------------------------------------------------------------------------------
+template <int DH>
+__device__ __forceinline__ void load_row_regs(float (&r)[DH], const float* src, bool ok) {
+#pragma unroll
+  for (int c = 0; c < DH / 4; ++c) {
+    const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(src) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    r[4 * c] = t.x; r[4 * c + 1] = t.y; r[4 * c + 2] = t.z; r[4 * c + 3] = t.w;
+  }
+}
+// register row . shared (broadcast) row, same two-accumulator order as dot4
+template <int DH>
+__device__ __forceinline__ float dot_reg(const float (&r)[DH], const float* row) {
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < DH / 4; ++c) {
+    const float4 x = reinterpret_cast<const float4*>(row)[c];
+    a0 = fmaf(x.x, r[4 * c], a0); a1 = fmaf(x.y, r[4 * c + 1], a1); a0 = fmaf(x.z, r[4 * c + 2], a0); a1 = fmaf(x.w, r[4 * c + 3], a1);
+  }
+  return a0 + a1;
+}
+template <int DH>
+__device__ __forceinline__ void axpy_reg(float (&acc)[DH], float w, const float* row) {
+#pragma unroll
+  for (int c = 0; c < DH / 4; ++c) {
+    const float4 x = reinterpret_cast<const float4*>(row)[c];
+    acc[4 * c] = fmaf(w, x.x, acc[4 * c]); acc[4 * c + 1] = fmaf(w, x.y, acc[4 * c + 1]);
+    acc[4 * c + 2] = fmaf(w, x.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(w, x.w, acc[4 * c + 3]);
+  }
+}
+template <int DH>
+__device__ __forceinline__ void stage_rows(float* dst, const float* src, long long ls, int L) {  // [L][DH] dense in shared memory
+  constexpr int DH4 = DH / 4;
+  for (int i = threadIdx.x; i < L * DH4; i += THREADS) {
+    const int l = i / DH4, c = i - l * DH4;
+    reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(l) * ls) + c);
+  }
+}
+// One warp: acc[0:DH] = sum over rows l < L with keep(l) of src[l][0:DH] (dense [L][DH]).  Lane (g, c) sums rows g, g+G, ...
+// of channel group c, then the G partial sums are combined by a butterfly (a + b == b + a: all lanes agree, fixed order).
+template <int DH, typename Keep>
+__device__ __forceinline__ void warp_column_sum(const float* src, int L, float* acc, Keep keep) {
+  constexpr int DH4 = DH / 4, G = 32 / DH4;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / DH4, c = lane - g * DH4;
+  float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = g; l < L; l += G)
+    if (keep(l)) {
+      const float4 v = reinterpret_cast<const float4*>(src)[l * DH4 + c];
+      part.x += v.x; part.y += v.y; part.z += v.z; part.w += v.w;
+    }
+#pragma unroll
+  for (int off = DH4; off < 32; off <<= 1) {
+    part.x += __shfl_xor_sync(0xffffffffu, part.x, off); part.y += __shfl_xor_sync(0xffffffffu, part.y, off);
+    part.z += __shfl_xor_sync(0xffffffffu, part.z, off); part.w += __shfl_xor_sync(0xffffffffu, part.w, off);
+  }
+  if (lane < DH4) reinterpret_cast<float4*>(acc)[lane] = part;
+}
+
+struct SmallPlan {  // how the (key slot, row chunk) pairs of the score phase are dealt to the warps
+  int nslots, nchunks;
+  __device__ __forceinline__ SmallPlan(int Lk) {
+    nslots = (Lk + 31) >> 5;
+    nchunks = nslots >= NWARPS ? 1 : NWARPS / nslots;
+  }
+};
+
+template <int DH>
+__global__ void __launch_bounds__(THREADS) attention_small_fwd_kernel(const RfAttnParams p) {
+  extern __shared__ __align__(16) float smem_f[];
+  constexpr int DH4 = DH / 4;
+  const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
+  const int Lq = p.Lq, Lk = p.Lk, u = p.u, U = p.U;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_q = smem_f;                     // [Lq][DH]
+  float* s_v = s_q + Lq * DH;              // [Lk][DH]
+  float* s_s = s_v + Lk * DH;              // [Lq][Lk] raw scores; rows of the selected queries become probabilities in place
+  float* s_m = s_s + round4(Lq * Lk);      // [Lq]
+  float* s_acc = s_m + round4(Lq);         // [DH]
+  int* s_top = reinterpret_cast<int*>(s_acc + DH);
+  int* s_sel = s_top + round4(u);
+  unsigned char* s_idx = reinterpret_cast<unsigned char*>(s_sel + round4(Lq));  // [Lq][U] sampled key ids (Lk <= 96 < 256)
+  const float* gq = p.q + b * p.q_bs + h * DH;
+  const float* gk = p.k + b * p.k_bs + h * DH;
+  const float* gv = p.v + b * p.v_bs + h * DH;
+  const long long bh = static_cast<long long>(b) * p.H + h;
+  const bool select = p.forced_top == nullptr;
+
+  stage_rows<DH>(s_q, gq, p.q_ls, Lq);
+  stage_rows<DH>(s_v, gv, p.v_ls, Lk);
+  if (select) {
+    const int group = p.idx_group > 0 ? b / p.idx_group : 0;
+    const int* idx = p.idx + static_cast<long long>(group) * Lq * U;
+    for (int i = threadIdx.x; i < Lq * U; i += THREADS) s_idx[i] = static_cast<unsigned char>(__ldg(idx + i));
+  }
+  __syncthreads();
+
+  // raw scores S[i][j] = q_i . k_j: key rows in registers, query rows broadcast
+  const SmallPlan plan(Lk);
+  const int chunk_rows = (Lq + plan.nchunks - 1) / plan.nchunks;
+  for (int pi = warp; pi < plan.nslots * plan.nchunks; pi += NWARPS) {
+    const int slot = pi % plan.nslots, chunk = pi / plan.nslots;
+    const int j = slot * 32 + lane;
+    float kr[DH];
+    load_row_regs<DH>(kr, gk + static_cast<long long>(j) * p.k_ls, j < Lk);
+    const int i1 = min(Lq, (chunk + 1) * chunk_rows);
+#pragma unroll 2
+    for (int i = chunk * chunk_rows; i < i1; ++i) {
+      const float sc = dot_reg<DH>(kr, s_q + i * DH);
+      if (j < Lk) s_s[i * Lk + j] = sc;
+    }
+  }
+  if (warp == NWARPS - 1) warp_column_sum<DH>(s_v, Lk, s_acc, [](int) { return true; });  // mean(V) numerator
+  __syncthreads();
+
+  if (select) {
+    // sparsity measure from the sampled entries of S (routeformer cross_modal_transformer.py:95-103)
+    for (int i = threadIdx.x; i < Lq; i += THREADS) {
+      const float* row = s_s + i * Lk;
+      const unsigned char* irow = s_idx + i * U;
+      float mx = -INFINITY, sum = 0.f;
+#pragma unroll 5
+      for (int jj = 0; jj < U; ++jj) {
+        const float sc = row[irow[jj]];
+        mx = fmaxf(mx, sc);
+        sum += sc;
+      }
+      const float mval = mx - sum / Lk;
+      s_m[i] = mval;
+      if (p.measure) p.measure[bh * Lq + i] = mval;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Lq; i += THREADS) {  // rank-based top-u, ties -> lower index first
+      const float mi = s_m[i];
+      int rank = 0;
+#pragma unroll 8
+      for (int j = 0; j < Lq; ++j) {
+        const float mj = s_m[j];
+        rank += (mj > mi) || (mj == mi && j < i);
+      }
+      if (rank < u) { s_top[rank] = i; s_sel[i] = rank; }
+      else s_sel[i] = -1;
+    }
+  } else {
+    for (int i = threadIdx.x; i < Lq; i += THREADS) s_sel[i] = -1;
+    __syncthreads();
+    const int* top_in = p.forced_top + bh * u;
+    for (int r = threadIdx.x; r < u; r += THREADS) {
+      const int i = top_in[r];
+      s_top[r] = i;
+      s_sel[i] = r;
+    }
+  }
+  __syncthreads();
+  if (p.top)
+    for (int r = threadIdx.x; r < u; r += THREADS) p.top[bh * u + r] = s_top[r];
+
+  // selected rows: probabilities in place (one warp per row, registers + shuffles)
+  const float scale = rsqrtf(static_cast<float>(DH));
+  for (int r = warp; r < u; r += NWARPS) {
+    float* row = s_s + s_top[r] * Lk;
+    float sc[3];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const int j = lane + 32 * t;
+      sc[t] = j < Lk ? row[j] * scale : -INFINITY;
+      mx = fmaxf(mx, sc[t]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      sc[t] = (lane + 32 * t < Lk) ? __expf(sc[t] - mx) : 0.f;
+      sum += sc[t];
+    }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+      if (lane + 32 * t < Lk) row[lane + 32 * t] = sc[t] * inv;
+  }
+  __syncthreads();
+
+  // context of the selected queries: P V, one thread per (row, 4 channels)
+  for (int i = threadIdx.x; i < u * DH4; i += THREADS) {
+    const int r = i / DH4, c = i - r * DH4;
+    const int qi = s_top[r];
+    const float* prow = s_s + qi * Lk;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int j = 0; j < Lk; ++j) {
+      const float w = prow[j];
+      const float4 vv = reinterpret_cast<const float4*>(s_v)[j * DH4 + c];
+      acc.x = fmaf(w, vv.x, acc.x); acc.y = fmaf(w, vv.y, acc.y); acc.z = fmaf(w, vv.z, acc.z); acc.w = fmaf(w, vv.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(p.out + out_offset(p, b, h, qi) + 4 * c) = acc;
+  }
+  // every other query: mean(V)
+  const float inv_lk = 1.f / Lk;
+  for (int i = threadIdx.x; i < Lq * DH4; i += THREADS) {
+    const int l = i / DH4, c = i - l * DH4;
+    if (s_sel[l] < 0) {
+      const float4 a4 = reinterpret_cast<const float4*>(s_acc)[c];
+      *reinterpret_cast<float4*>(p.out + out_offset(p, b, h, l) + 4 * c) = make_float4(a4.x * inv_lk, a4.y * inv_lk, a4.z * inv_lk, a4.w * inv_lk);
+    }
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(THREADS) attention_small_bwd_kernel(const RfAttnBwdParams bp) {
+  extern __shared__ __align__(16) float smem_f[];
+  constexpr int DH4 = DH / 4;
+  const RfAttnParams& p = bp.f;
+  const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
+  const int Lq = p.Lq, Lk = p.Lk, u = p.u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_q = smem_f;                      // [Lq][DH]
+  float* s_k = s_q + Lq * DH;               // [Lk][DH]
+  float* s_do = s_k + Lk * DH;              // [Lq][DH] context gradient of this head
+  float* s_p = s_do + Lq * DH;              // [u][Lk] raw scores -> probabilities
+  float* s_ds = s_p + round4(u * Lk);       // [u][Lk] dP -> dS
+  float* s_acc = s_ds + round4(u * Lk);     // [DH] sum of the unselected context gradients
+  int* s_top = reinterpret_cast<int*>(s_acc + DH);
+  int* s_sel = s_top + round4(u);
+  const float* gq = p.q + b * p.q_bs + h * DH;
+  const float* gk = p.k + b * p.k_bs + h * DH;
+  const float* gv = p.v + b * p.v_bs + h * DH;
+  const long long bh = static_cast<long long>(b) * p.H + h;
+
+  stage_rows<DH>(s_q, gq, p.q_ls, Lq);
+  stage_rows<DH>(s_k, gk, p.k_ls, Lk);
+  for (int i = threadIdx.x; i < Lq * DH4; i += THREADS) {
+    const int l = i / DH4, c = i - l * DH4;
+    reinterpret_cast<float4*>(s_do)[i] = __ldg(reinterpret_cast<const float4*>(bp.dout + out_offset(p, b, h, l)) + c);
+  }
+  for (int i = threadIdx.x; i < Lq; i += THREADS) s_sel[i] = -1;
+  __syncthreads();
+  for (int r = threadIdx.x; r < u; r += THREADS) {
+    const int i = p.top[bh * u + r];
+    s_top[r] = i;
+    s_sel[i] = r;
+  }
+  __syncthreads();
+
+  // raw scores and dP of the selected rows: key and value rows in registers, q / dO rows broadcast
+  const SmallPlan plan(Lk);
+  const int chunk_rows = (u + plan.nchunks - 1) / plan.nchunks;
+  for (int pi = warp; pi < plan.nslots * plan.nchunks; pi += NWARPS) {
+    const int slot = pi % plan.nslots, chunk = pi / plan.nslots;
+    const int j = slot * 32 + lane;
+    float kr[DH], vr[DH];
+    load_row_regs<DH>(kr, gk + static_cast<long long>(j) * p.k_ls, j < Lk);
+    load_row_regs<DH>(vr, gv + static_cast<long long>(j) * p.v_ls, j < Lk);
+    const int r1 = min(u, (chunk + 1) * chunk_rows);
+#pragma unroll 2
+    for (int r = chunk * chunk_rows; r < r1; ++r) {
+      const int qi = s_top[r];
+      const float sc = dot_reg<DH>(kr, s_q + qi * DH);
+      const float dp = dot_reg<DH>(vr, s_do + qi * DH);
+      if (j < Lk) { s_p[r * Lk + j] = sc; s_ds[r * Lk + j] = dp; }
+    }
+  }
+  if (warp == NWARPS - 1) warp_column_sum<DH>(s_do, Lq, s_acc, [&](int l) { return s_sel[l] < 0; });
+  __syncthreads();
+
+  // P = softmax(scale S), dS = P o (dP - rowsum(P o dP)) * scale, in place, one warp per row
+  const float scale = rsqrtf(static_cast<float>(DH));
+  for (int r = warp; r < u; r += NWARPS) {
+    float* prow = s_p + r * Lk;
+    float* drow = s_ds + r * Lk;
+    float sc[3], dp[3];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const int j = lane + 32 * t;
+      sc[t] = j < Lk ? prow[j] * scale : -INFINITY;
+      dp[t] = j < Lk ? drow[j] : 0.f;
+      mx = fmaxf(mx, sc[t]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      sc[t] = (lane + 32 * t < Lk) ? __expf(sc[t] - mx) : 0.f;
+      sum += sc[t];
+    }
+    const float inv = 1.f / warp_sum(sum);
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      sc[t] *= inv;
+      acc = fmaf(sc[t], dp[t], acc);
+    }
+    acc = warp_sum(acc);
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+      if (lane + 32 * t < Lk) {
+        prow[lane + 32 * t] = sc[t];
+        drow[lane + 32 * t] = sc[t] * (dp[t] - acc) * scale;
+      }
+  }
+  __syncthreads();
+
+  // dQ: selected rows get dS K, the others zero
+  float* dq = bp.dq + b * p.q_bs + h * DH;
+  for (int i = threadIdx.x; i < Lq * DH4; i += THREADS) {
+    const int l = i / DH4, c = i - l * DH4;
+    const int r = s_sel[l];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= 0) {
+      const float* row = s_ds + r * Lk;
+#pragma unroll 4
+      for (int j = 0; j < Lk; ++j) {
+        const float w = row[j];
+        const float4 kk = reinterpret_cast<const float4*>(s_k)[j * DH4 + c];
+        acc.x = fmaf(w, kk.x, acc.x); acc.y = fmaf(w, kk.y, acc.y); acc.z = fmaf(w, kk.z, acc.z); acc.w = fmaf(w, kk.w, acc.w);
+      }
+    }
+    *reinterpret_cast<float4*>(dq + static_cast<long long>(l) * p.q_ls + 4 * c) = acc;
+  }
+  // dK[j] = sum_r dS[r][j] q_top_r, dV[j] = sum_r P[r][j] dO_top_r + fill gradient: accumulators in the registers of lane j
+  float* dk = bp.dk + b * p.k_bs + h * DH;
+  float* dv = bp.dv + b * p.v_bs + h * DH;
+  const float inv_lk = 1.f / Lk;
+  for (int slot = warp; slot < plan.nslots; slot += NWARPS) {
+    const int j = slot * 32 + lane;
+    const bool ok = j < Lk;
+    float ak[DH], av[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) { ak[c] = 0.f; av[c] = 0.f; }
+#pragma unroll 2
+    for (int r = 0; r < u; ++r) {
+      const int qi = s_top[r];
+      const float ws = ok ? s_ds[r * Lk + j] : 0.f, wp = ok ? s_p[r * Lk + j] : 0.f;
+      axpy_reg<DH>(ak, ws, s_q + qi * DH);
+      axpy_reg<DH>(av, wp, s_do + qi * DH);
+    }
+    if (ok) {
+#pragma unroll
+      for (int c = 0; c < DH4; ++c) {
+        const float4 f4 = reinterpret_cast<const float4*>(s_acc)[c];
+        reinterpret_cast<float4*>(dk + static_cast<long long>(j) * p.k_ls)[c] = make_float4(ak[4 * c], ak[4 * c + 1], ak[4 * c + 2], ak[4 * c + 3]);
+        reinterpret_cast<float4*>(dv + static_cast<long long>(j) * p.v_ls)[c] =
+            make_float4(av[4 * c] + f4.x * inv_lk, av[4 * c + 1] + f4.y * inv_lk, av[4 * c + 2] + f4.z * inv_lk, av[4 * c + 3] + f4.w * inv_lk);
+      }
+    }
+  }
+}
+
+static bool small_path(const RfAttnParams* p) {
+  static const bool enabled = [] { const char* e = getenv("RF_ATTN_SMALL"); return !(e && e[0] == '0'); }();
+  return enabled && p->mode == RF_ATTN_PROB && (p->dh == 8 || p->dh == 16) && p->Lk <= 96 && p->Lq <= 255 &&
+         static_cast<long long>(p->Lq) * p->Lk * 4 <= 40 * 1024;
+}
+static size_t small_fwd_smem(const RfAttnParams* p) {
+  return sizeof(float) * (static_cast<size_t>(p->Lq + p->Lk) * p->dh + round4(p->Lq * p->Lk) + round4(p->Lq) + p->dh + round4(p->u) + round4(p->Lq)) +
+         static_cast<size_t>(round4(p->Lq * p->U));
+}
+static size_t small_bwd_smem(const RfAttnParams* p) {
+  return sizeof(float) * (static_cast<size_t>(2 * p->Lq + p->Lk) * p->dh + 2 * round4(p->u * p->Lk) + p->dh + round4(p->u) + round4(p->Lq));
 }
 
 static size_t fwd_smem(const RfAttnParams* p) {
@@ -441,9 +855,16 @@ extern "C" int rf_attention_fwd(const RfAttnParams* p, void* stream) {
   RF_CHECK_ARG(p && p->out, "rf_attention_fwd: null pointer");
   int rc = attn::validate(p, "rf_attention_fwd", true);
   if (rc != RF_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (attn::small_path(p)) {
+    const size_t smem = attn::small_fwd_smem(p);
+    if (p->dh == 8) RF_ATTN_LAUNCH(attention_small_fwd_kernel, 8, *p, p->B * p->H, smem, s)
+    else RF_ATTN_LAUNCH(attention_small_fwd_kernel, 16, *p, p->B * p->H, smem, s)
+    RF_LAUNCH_OK();
+    return RF_OK;
+  }
   const size_t smem = attn::fwd_smem(p);
   RF_CHECK_ARG(smem <= 220 * 1024, "rf_attention_fwd: problem needs %zu B of shared memory (> 220 KiB)", smem);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   RF_ATTN_DISPATCH(attention_fwd_kernel, *p, p->dh, p->B * p->H, smem, s)
   RF_LAUNCH_OK();
   return RF_OK;
@@ -454,9 +875,16 @@ extern "C" int rf_attention_bwd(const RfAttnBwdParams* p, void* stream) {
   RF_CHECK_ARG(p && p->dout && p->dq && p->dk && p->dv, "rf_attention_bwd: null pointer");
   int rc = attn::validate(&p->f, "rf_attention_bwd", false);
   if (rc != RF_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (attn::small_path(&p->f)) {
+    const size_t smem = attn::small_bwd_smem(&p->f);
+    if (p->f.dh == 8) RF_ATTN_LAUNCH(attention_small_bwd_kernel, 8, *p, p->f.B * p->f.H, smem, s)
+    else RF_ATTN_LAUNCH(attention_small_bwd_kernel, 16, *p, p->f.B * p->f.H, smem, s)
+    RF_LAUNCH_OK();
+    return RF_OK;
+  }
   const size_t smem = attn::bwd_smem(&p->f);
   RF_CHECK_ARG(smem <= 220 * 1024, "rf_attention_bwd: problem needs %zu B of shared memory (> 220 KiB)", smem);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   RF_ATTN_DISPATCH(attention_bwd_kernel, *p, p->f.dh, p->f.B * p->f.H, smem, s)
   RF_LAUNCH_OK();
   return RF_OK;

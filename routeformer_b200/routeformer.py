@@ -452,6 +452,8 @@ class Routeformer(nn.Module):
             out, origin = self._forward(motion, visual)
             _, wp, dense = self.postprocess_batch(last_gps, out, origin)
         else:  # autoregressive windows (routeformer.py:164-197)
+            if not self.with_video:  # the reference slices its empty visual-feature list at :187
+                raise TypeError("list indices must be integers or slices, not tuple")
             outputs, done = [], 0
             step = c.autoregressive_step_size
             pred_len = self.gps_backbone.pred_len
@@ -463,8 +465,7 @@ class Routeformer(nn.Module):
                     outputs.append((wp_s, dense_s))
                     motion = torch.cat([motion[:, step:], mv], dim=1)
                     last_gps = wp_s[:, -1:, :]
-                    if self.with_video:
-                        visual = torch.cat([visual[:, step:], dense_s], dim=1)
+                    visual = torch.cat([visual[:, step:], dense_s], dim=1)
                     done += step
             finally:
                 self.gps_backbone.pred_len = pred_len

@@ -48,7 +48,8 @@ def build_product(cfg, spec, fov="frame", **overrides):
               cross_modal_decoder_heads=cfg.cross_modal_decoder_heads, cross_modal_decoder_layers=cfg.cross_modal_decoder_layers,
               rotate_motion=cfg.rotate_motion, normalize_motion=cfg.normalize_motion, motion_mean=cfg.motion_mean,
               motion_std=cfg.motion_std, video_fps=cfg.video_fps, gaze_fps=cfg.gaze_fps, output_fps=cfg.output_fps,
-              view_dropout=cfg.view_dropout, gaze_dropout=cfg.gaze_dropout)
+              view_dropout=cfg.view_dropout, gaze_dropout=cfg.gaze_dropout, autoregressive=cfg.autoregressive,
+              autoregressive_step_size=cfg.autoregressive_step_size)
     kw.update(overrides)
     rc = R.RouteformerConfig(**kw)
     return R.Routeformer(rc, gps_backbone=R.Informer, video_backbone=R.PatchEmbedBackbone if spec is not None else None)

@@ -199,6 +199,11 @@ ATTN_CASES = [
     (3, 8, 70, 4, 104, 4, "prob", "bhld"),
     (2, 4, 7, 7, 16, 4, "prob", "bhld"),
     (3, 8, 40, 30, 8, 5, "full", "blhd"),
+    # register-blocked small-problem path (dh 8/16, Lk <= 96): 1 / 2 / 3 key slots, Lq != Lk, both layouts
+    (4, 8, 40, 40, 8, 5, "prob", "blhd"),
+    (3, 4, 40, 70, 16, 5, "prob", "bhld"),
+    (3, 8, 90, 33, 8, 4, "prob", "blhd"),
+    (6, 2, 20, 96, 16, 5, "prob", "blhd"),
 ]
 
 

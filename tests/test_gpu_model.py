@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 CASES = ["gps_only_paper", "full_small_eval", "dreyeve_small", "normalized_small", "no_gaze_small", "no_scene_small", "sparse_small",
-         "full_paper_eval"]
+         "full_paper_eval", "autoregressive_small", "autoregressive_dreyeve_small"]
 
 
 def view_order(cfg):

@@ -6,7 +6,7 @@ from oracle import routeformer_oracle as O
 from tests.helpers import case_from_golden, load_golden, rel_err, targets_for
 
 EVAL_CASES = ["gps_only_paper", "full_small_eval", "full_paper_eval", "dreyeve_small", "normalized_small",
-              "no_gaze_small", "no_scene_small", "sparse_small"]
+              "no_gaze_small", "no_scene_small", "sparse_small", "autoregressive_small", "autoregressive_dreyeve_small"]
 
 
 @pytest.mark.parametrize("name", EVAL_CASES)
@@ -31,6 +31,14 @@ def test_eval_forward_matches_reference(name):
     assert abs(O.ade(wp, t_wp).item() - gold["ade"]) < tol(gold["ade"])
     assert abs(O.fde(wp[-1:], t_wp[-1:]).item() - gold["fde"]) < tol(gold["fde"])
     assert abs(O.fde(wp, t_wp).item() - gold["fde_batch"]) < tol(gold["fde_batch"])
+
+
+def test_autoregressive_gps_only_raises_like_the_reference():
+    """routeformer.py:187 slices the empty visual-feature LIST of the GPS-only model: TypeError, not a result."""
+    cfg = O.OracleConfig(d_model=64, n_heads=4, e_layers=2, d_ff=128, autoregressive=True, autoregressive_step_size=10)
+    sd = O.fill_state_dict(O.state_dict_template(cfg, None), 3)
+    with pytest.raises(TypeError), torch.no_grad():
+        O.Routeformer(sd, cfg, None).forward(O.synthetic_batch(2, cfg, "tiny", seed=4), training=False)
 
 
 def test_train_step_matches_reference():
