@@ -426,34 +426,40 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
 //   * dK / dV accumulate in registers of the lane that owns key j and leave through one 64 B row store each.
 // Arithmetic order of every reduction is fixed (deterministic) and identical between forward and the backward recompute.
 // ---------------------------------------------------------------------------------------------
+// A row of DH floats held in registers as DH/2 packed pairs.
 template <int DH>
-__device__ __forceinline__ void load_row_regs(float (&r)[DH], const float* src, bool ok) {
+struct RegRow {
+  f32x2 v[DH / 2];
+  __device__ __forceinline__ void load(const float* src, bool ok) {  // global or shared, 16 B aligned
 #pragma unroll
-  for (int c = 0; c < DH / 4; ++c) {
-    const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(src) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    r[4 * c] = t.x; r[4 * c + 1] = t.y; r[4 * c + 2] = t.z; r[4 * c + 3] = t.w;
+    for (int c = 0; c < DH / 4; ++c) {
+      const ulonglong2 t = ok ? *reinterpret_cast<const ulonglong2*>(src + 4 * c) : make_ulonglong2(0ull, 0ull);
+      v[2 * c] = t.x;
+      v[2 * c + 1] = t.y;
+    }
   }
-}
-// register row . shared (broadcast) row, same two-accumulator order as dot4
-template <int DH>
-__device__ __forceinline__ float dot_reg(const float (&r)[DH], const float* row) {
-  float a0 = 0.f, a1 = 0.f;
+  __device__ __forceinline__ void zero() {
 #pragma unroll
-  for (int c = 0; c < DH / 4; ++c) {
-    const float4 x = reinterpret_cast<const float4*>(row)[c];
-    a0 = fmaf(x.x, r[4 * c], a0); a1 = fmaf(x.y, r[4 * c + 1], a1); a0 = fmaf(x.z, r[4 * c + 2], a0); a1 = fmaf(x.w, r[4 * c + 3], a1);
+    for (int c = 0; c < DH / 2; ++c) v[c] = 0ull;
   }
-  return a0 + a1;
-}
-template <int DH>
-__device__ __forceinline__ void axpy_reg(float (&acc)[DH], float w, const float* row) {
+  // this . x: pairs (4c,4c+1) then (4c+2,4c+3) into one packed accumulator, the order of dot4
+  __device__ __forceinline__ float dot(const RegRow& x) const {
+    f32x2 acc = 0ull;
 #pragma unroll
-  for (int c = 0; c < DH / 4; ++c) {
-    const float4 x = reinterpret_cast<const float4*>(row)[c];
-    acc[4 * c] = fmaf(w, x.x, acc[4 * c]); acc[4 * c + 1] = fmaf(w, x.y, acc[4 * c + 1]);
-    acc[4 * c + 2] = fmaf(w, x.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(w, x.w, acc[4 * c + 3]);
+    for (int c = 0; c < DH / 2; ++c) acc = ffma2(x.v[c], v[c], acc);
+    const float2 r = unpack2(acc);
+    return r.x + r.y;
   }
-}
+  __device__ __forceinline__ void axpy(float w, const RegRow& x) {  // this += w * x
+    const f32x2 ww = pack2(w, w);
+#pragma unroll
+    for (int c = 0; c < DH / 2; ++c) v[c] = ffma2(ww, x.v[c], v[c]);
+  }
+  __device__ __forceinline__ void store(float* dst) const {
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c) *reinterpret_cast<ulonglong2*>(dst + 4 * c) = make_ulonglong2(v[2 * c], v[2 * c + 1]);
+  }
+};
 template <int DH>
 __device__ __forceinline__ void stage_rows(float* dst, const float* src, long long ls, int L) {  // [L][DH] dense in shared memory
   constexpr int DH4 = DH / 4;
@@ -482,17 +488,34 @@ __device__ __forceinline__ void warp_column_sum(const float* src, int L, float* 
   }
   if (lane < DH4) reinterpret_cast<float4*>(acc)[lane] = part;
 }
-
-struct SmallPlan {  // how the (key slot, row chunk) pairs of the score phase are dealt to the warps
-  int nslots, nchunks;
-  __device__ __forceinline__ SmallPlan(int Lk) {
-    nslots = (Lk + 31) >> 5;
-    nchunks = nslots >= NWARPS ? 1 : NWARPS / nslots;
-  }
-};
-
+// out[rows of one 4-row tile][4c..4c+3] = sum_j W[row][j] * X[j][4c..4c+3]: the X row is loaded once per j for four output rows
+// (a shared-memory load costs one wavefront per 128 B quarter-warp whether or not lanes coincide, so operand re-use in
+// registers is the only way to cut shared-memory traffic).  wrow[k] = shared row of weights of output row k (clamped rows repeat).
 template <int DH>
-__global__ void __launch_bounds__(THREADS) attention_small_fwd_kernel(const RfAttnParams p) {
+__device__ __forceinline__ void tile4_matvec(const float* const (&wrow)[4], const float* x, int L, float4 (&out)[4]) {
+  Acc4 acc[4];
+#pragma unroll 4
+  for (int j = 0; j < L; ++j) {
+    const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(x + j * DH);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float w = wrow[k][j];
+      const f32x2 ww = pack2(w, w);
+      acc[k].lo = ffma2(ww, xv.x, acc[k].lo);
+      acc[k].hi = ffma2(ww, xv.y, acc[k].hi);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) out[k] = acc[k].get();
+}
+
+// Key ownership: lane l of every warp owns keys l, l+32, ... (NT register rows); the rows of the left operand are split over the
+// warps.  A short remainder of <= 8 keys (the 65th token of the frame encoder) would cost a whole register slot for almost no
+// work, so those "tail" keys are handled transposed (lane per row).  NT is chosen on the host: see small_nt().
+__host__ __device__ __forceinline__ int small_nt(int Lk) { return (Lk >> 5) + ((Lk & 31) > 8 ? 1 : 0); }
+
+template <int DH, int NT>
+__global__ void __launch_bounds__(THREADS, 7) attention_small_fwd_kernel(const RfAttnParams p) {
   extern __shared__ __align__(16) float smem_f[];
   constexpr int DH4 = DH / 4;
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
@@ -511,6 +534,7 @@ __global__ void __launch_bounds__(THREADS) attention_small_fwd_kernel(const RfAt
   const float* gv = p.v + b * p.v_bs + h * DH;
   const long long bh = static_cast<long long>(b) * p.H + h;
   const bool select = p.forced_top == nullptr;
+  const int tail_start = min(Lk, NT * 32), tail = Lk - tail_start;
 
   stage_rows<DH>(s_q, gq, p.q_ls, Lq);
   stage_rows<DH>(s_v, gv, p.v_ls, Lk);
@@ -519,28 +543,43 @@ __global__ void __launch_bounds__(THREADS) attention_small_fwd_kernel(const RfAt
     const int* idx = p.idx + static_cast<long long>(group) * Lq * U;
     for (int i = threadIdx.x; i < Lq * U; i += THREADS) s_idx[i] = static_cast<unsigned char>(__ldg(idx + i));
   }
+  RegRow<DH> kr[NT > 0 ? NT : 1];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) kr[t].load(gk + static_cast<long long>(lane + 32 * t) * p.k_ls, lane + 32 * t < Lk);
   __syncthreads();
 
-  // raw scores S[i][j] = q_i . k_j: key rows in registers, query rows broadcast
-  const SmallPlan plan(Lk);
-  const int chunk_rows = (Lq + plan.nchunks - 1) / plan.nchunks;
-  for (int pi = warp; pi < plan.nslots * plan.nchunks; pi += NWARPS) {
-    const int slot = pi % plan.nslots, chunk = pi / plan.nslots;
-    const int j = slot * 32 + lane;
-    float kr[DH];
-    load_row_regs<DH>(kr, gk + static_cast<long long>(j) * p.k_ls, j < Lk);
-    const int i1 = min(Lq, (chunk + 1) * chunk_rows);
+  // raw scores S[i][j] = q_i . k_j: every query row is read once per warp and meets NT register-resident keys per lane
+  if (NT > 0) {
+    const int chunk_rows = (Lq + NWARPS - 1) / NWARPS;
+    const int i0 = warp * chunk_rows, i1 = min(Lq, i0 + chunk_rows);
 #pragma unroll 2
-    for (int i = chunk * chunk_rows; i < i1; ++i) {
-      const float sc = dot_reg<DH>(kr, s_q + i * DH);
-      if (j < Lk) s_s[i * Lk + j] = sc;
+    for (int i = i0; i < i1; ++i) {
+      RegRow<DH> qr;
+      qr.load(s_q + i * DH, true);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const float sc = kr[t].dot(qr);
+        if (lane + 32 * t < Lk) s_s[i * Lk + lane + 32 * t] = sc;
+      }
+    }
+  }
+  {  // tail keys, transposed: lane per query row
+    const int qblocks = (Lq + 31) >> 5;
+    for (int it = NWARPS - 1 - warp; it < tail * qblocks; it += NWARPS) {
+      const int jt = tail_start + it / qblocks, i = (it % qblocks) * 32 + lane;
+      RegRow<DH> kt, qr;
+      kt.load(gk + static_cast<long long>(jt) * p.k_ls, true);
+      if (i < Lq) {
+        qr.load(s_q + i * DH, true);
+        s_s[i * Lk + jt] = kt.dot(qr);
+      }
     }
   }
   if (warp == NWARPS - 1) warp_column_sum<DH>(s_v, Lk, s_acc, [](int) { return true; });  // mean(V) numerator
   __syncthreads();
 
   if (select) {
-    // sparsity measure from the sampled entries of S (routeformer cross_modal_transformer.py:95-103)
+    // sparsity measure from the sampled entries of S (cross_modal_transformer.py:95-103)
     for (int i = threadIdx.x; i < Lq; i += THREADS) {
       const float* row = s_s + i * Lk;
       const unsigned char* irow = s_idx + i * U;
@@ -560,10 +599,9 @@ __global__ void __launch_bounds__(THREADS) attention_small_fwd_kernel(const RfAt
       const float mi = s_m[i];
       int rank = 0;
 #pragma unroll 8
-      for (int j = 0; j < Lq; ++j) {
-        const float mj = s_m[j];
-        rank += (mj > mi) || (mj == mi && j < i);
-      }
+      for (int j = 0; j < i; ++j) rank += s_m[j] >= mi;
+#pragma unroll 8
+      for (int j = i + 1; j < Lq; ++j) rank += s_m[j] > mi;
       if (rank < u) { s_top[rank] = i; s_sel[i] = rank; }
       else s_sel[i] = -1;
     }
@@ -607,23 +645,26 @@ __global__ void __launch_bounds__(THREADS) attention_small_fwd_kernel(const RfAt
   }
   __syncthreads();
 
-  // context of the selected queries: P V, one thread per (row, 4 channels)
-  for (int i = threadIdx.x; i < u * DH4; i += THREADS) {
-    const int r = i / DH4, c = i - r * DH4;
-    const int qi = s_top[r];
-    const float* prow = s_s + qi * Lk;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int j = 0; j < Lk; ++j) {
-      const float w = prow[j];
-      const float4 vv = reinterpret_cast<const float4*>(s_v)[j * DH4 + c];
-      acc.x = fmaf(w, vv.x, acc.x); acc.y = fmaf(w, vv.y, acc.y); acc.z = fmaf(w, vv.z, acc.z); acc.w = fmaf(w, vv.w, acc.w);
+  // context of the selected queries: P V in 4-row x 4-channel register tiles (28 threads at u = 25: the first warp);
+  // the other warps meanwhile write mean(V) to every other query
+  const int ntiles = ((u + 3) >> 2) * DH4;
+  for (int it = threadIdx.x; it < ntiles; it += THREADS) {
+    const int r0 = (it / DH4) * 4, c = it % DH4;
+    const float* wrow[4];
+    int qi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      qi[k] = s_top[min(r0 + k, u - 1)];
+      wrow[k] = s_s + qi[k] * Lk;
     }
-    *reinterpret_cast<float4*>(p.out + out_offset(p, b, h, qi) + 4 * c) = acc;
+    float4 o[4];
+    tile4_matvec<DH>(wrow, s_v + 4 * c, Lk, o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (r0 + k < u) *reinterpret_cast<float4*>(p.out + out_offset(p, b, h, qi[k]) + 4 * c) = o[k];
   }
-  // every other query: mean(V)
   const float inv_lk = 1.f / Lk;
-  for (int i = threadIdx.x; i < Lq * DH4; i += THREADS) {
+  for (int i = THREADS - 1 - threadIdx.x; i < Lq * DH4; i += THREADS) {  // reversed: the tile threads come last
     const int l = i / DH4, c = i - l * DH4;
     if (s_sel[l] < 0) {
       const float4 a4 = reinterpret_cast<const float4*>(s_acc)[c];
@@ -632,8 +673,8 @@ __global__ void __launch_bounds__(THREADS) attention_small_fwd_kernel(const RfAt
   }
 }
 
-template <int DH>
-__global__ void __launch_bounds__(THREADS) attention_small_bwd_kernel(const RfAttnBwdParams bp) {
+template <int DH, int NT>
+__global__ void __launch_bounds__(THREADS, 7) attention_small_bwd_kernel(const RfAttnBwdParams bp) {
   extern __shared__ __align__(16) float smem_f[];
   constexpr int DH4 = DH / 4;
   const RfAttnParams& p = bp.f;
@@ -652,6 +693,7 @@ __global__ void __launch_bounds__(THREADS) attention_small_bwd_kernel(const RfAt
   const float* gk = p.k + b * p.k_bs + h * DH;
   const float* gv = p.v + b * p.v_bs + h * DH;
   const long long bh = static_cast<long long>(b) * p.H + h;
+  const int tail_start = min(Lk, NT * 32), tail = Lk - tail_start;
 
   stage_rows<DH>(s_q, gq, p.q_ls, Lq);
   stage_rows<DH>(s_k, gk, p.k_ls, Lk);
@@ -660,34 +702,59 @@ __global__ void __launch_bounds__(THREADS) attention_small_bwd_kernel(const RfAt
     reinterpret_cast<float4*>(s_do)[i] = __ldg(reinterpret_cast<const float4*>(bp.dout + out_offset(p, b, h, l)) + c);
   }
   for (int i = threadIdx.x; i < Lq; i += THREADS) s_sel[i] = -1;
+  for (int r = threadIdx.x; r < u; r += THREADS) s_top[r] = p.top[bh * u + r];
   __syncthreads();
-  for (int r = threadIdx.x; r < u; r += THREADS) {
-    const int i = p.top[bh * u + r];
-    s_top[r] = i;
-    s_sel[i] = r;
-  }
-  __syncthreads();
+  for (int r = threadIdx.x; r < u; r += THREADS) s_sel[s_top[r]] = r;
 
-  // raw scores and dP of the selected rows: key and value rows in registers, q / dO rows broadcast
-  const SmallPlan plan(Lk);
-  const int chunk_rows = (u + plan.nchunks - 1) / plan.nchunks;
-  for (int pi = warp; pi < plan.nslots * plan.nchunks; pi += NWARPS) {
-    const int slot = pi % plan.nslots, chunk = pi / plan.nslots;
-    const int j = slot * 32 + lane;
-    float kr[DH], vr[DH];
-    load_row_regs<DH>(kr, gk + static_cast<long long>(j) * p.k_ls, j < Lk);
-    load_row_regs<DH>(vr, gv + static_cast<long long>(j) * p.v_ls, j < Lk);
-    const int r1 = min(u, (chunk + 1) * chunk_rows);
+  // raw scores S[r][j] = q_top_r . k_j, then dP[r][j] = dO_top_r . v_j: key / value rows in registers, selected rows split
+  // over the warps, each q / dO row read once per warp
+  if (NT > 0) {
+    const int chunk_rows = (u + NWARPS - 1) / NWARPS;
+    const int r0 = warp * chunk_rows, r1 = min(u, r0 + chunk_rows);
+    RegRow<DH> kv[NT > 0 ? NT : 1];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) kv[t].load(s_k + (lane + 32 * t) * DH, lane + 32 * t < Lk);
 #pragma unroll 2
-    for (int r = chunk * chunk_rows; r < r1; ++r) {
-      const int qi = s_top[r];
-      const float sc = dot_reg<DH>(kr, s_q + qi * DH);
-      const float dp = dot_reg<DH>(vr, s_do + qi * DH);
-      if (j < Lk) { s_p[r * Lk + j] = sc; s_ds[r * Lk + j] = dp; }
+    for (int r = r0; r < r1; ++r) {
+      RegRow<DH> x;
+      x.load(s_q + s_top[r] * DH, true);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const float sc = kv[t].dot(x);
+        if (lane + 32 * t < Lk) s_p[r * Lk + lane + 32 * t] = sc;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) kv[t].load(gv + static_cast<long long>(lane + 32 * t) * p.v_ls, lane + 32 * t < Lk);
+#pragma unroll 2
+    for (int r = r0; r < r1; ++r) {
+      RegRow<DH> x;
+      x.load(s_do + s_top[r] * DH, true);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const float dp = kv[t].dot(x);
+        if (lane + 32 * t < Lk) s_ds[r * Lk + lane + 32 * t] = dp;
+      }
     }
   }
+  {  // tail keys, transposed: lane per selected row
+    const int rblocks = (u + 31) >> 5;
+    for (int it = NWARPS - 1 - warp; it < tail * rblocks; it += NWARPS) {
+      const int jt = tail_start + it / rblocks, r = (it % rblocks) * 32 + lane;
+      RegRow<DH> kt, vt, x;
+      kt.load(s_k + jt * DH, true);
+      vt.load(gv + static_cast<long long>(jt) * p.v_ls, true);
+      if (r < u) {
+        const int qi = s_top[r];
+        x.load(s_q + qi * DH, true);
+        s_p[r * Lk + jt] = kt.dot(x);
+        x.load(s_do + qi * DH, true);
+        s_ds[r * Lk + jt] = vt.dot(x);
+      }
+    }
+  }
+  __syncthreads();  // s_sel complete as well
   if (warp == NWARPS - 1) warp_column_sum<DH>(s_do, Lq, s_acc, [&](int l) { return s_sel[l] < 0; });
-  __syncthreads();
 
   // P = softmax(scale S), dS = P o (dP - rowsum(P o dP)) * scale, in place, one warp per row
   const float scale = rsqrtf(static_cast<float>(DH));
@@ -727,48 +794,70 @@ __global__ void __launch_bounds__(THREADS) attention_small_bwd_kernel(const RfAt
   }
   __syncthreads();
 
-  // dQ: selected rows get dS K, the others zero
   float* dq = bp.dq + b * p.q_bs + h * DH;
-  for (int i = threadIdx.x; i < Lq * DH4; i += THREADS) {
-    const int l = i / DH4, c = i - l * DH4;
-    const int r = s_sel[l];
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r >= 0) {
-      const float* row = s_ds + r * Lk;
-#pragma unroll 4
-      for (int j = 0; j < Lk; ++j) {
-        const float w = row[j];
-        const float4 kk = reinterpret_cast<const float4*>(s_k)[j * DH4 + c];
-        acc.x = fmaf(w, kk.x, acc.x); acc.y = fmaf(w, kk.y, acc.y); acc.z = fmaf(w, kk.z, acc.z); acc.w = fmaf(w, kk.w, acc.w);
-      }
-    }
-    *reinterpret_cast<float4*>(dq + static_cast<long long>(l) * p.q_ls + 4 * c) = acc;
-  }
-  // dK[j] = sum_r dS[r][j] q_top_r, dV[j] = sum_r P[r][j] dO_top_r + fill gradient: accumulators in the registers of lane j
   float* dk = bp.dk + b * p.k_bs + h * DH;
   float* dv = bp.dv + b * p.v_bs + h * DH;
   const float inv_lk = 1.f / Lk;
-  for (int slot = warp; slot < plan.nslots; slot += NWARPS) {
-    const int j = slot * 32 + lane;
-    const bool ok = j < Lk;
-    float ak[DH], av[DH];
+  if (NT > 0 && warp < 2) {
+    // warp 0: dK[j] = sum_r dS[r][j] q_top_r; warp 1: dV[j] = sum_r P[r][j] dO_top_r + fill gradient.  Accumulators live in
+    // the registers of the lane that owns key j; each q / dO row is read once.
+    const float* w = warp == 0 ? s_ds : s_p;
+    const float* xs = warp == 0 ? s_q : s_do;
+    RegRow<DH> acc[NT > 0 ? NT : 1];
 #pragma unroll
-    for (int c = 0; c < DH; ++c) { ak[c] = 0.f; av[c] = 0.f; }
+    for (int t = 0; t < NT; ++t) acc[t].zero();
 #pragma unroll 2
     for (int r = 0; r < u; ++r) {
-      const int qi = s_top[r];
-      const float ws = ok ? s_ds[r * Lk + j] : 0.f, wp = ok ? s_p[r * Lk + j] : 0.f;
-      axpy_reg<DH>(ak, ws, s_q + qi * DH);
-      axpy_reg<DH>(av, wp, s_do + qi * DH);
-    }
-    if (ok) {
+      RegRow<DH> x;
+      x.load(xs + s_top[r] * DH, true);
 #pragma unroll
-      for (int c = 0; c < DH4; ++c) {
-        const float4 f4 = reinterpret_cast<const float4*>(s_acc)[c];
-        reinterpret_cast<float4*>(dk + static_cast<long long>(j) * p.k_ls)[c] = make_float4(ak[4 * c], ak[4 * c + 1], ak[4 * c + 2], ak[4 * c + 3]);
-        reinterpret_cast<float4*>(dv + static_cast<long long>(j) * p.v_ls)[c] =
-            make_float4(av[4 * c] + f4.x * inv_lk, av[4 * c + 1] + f4.y * inv_lk, av[4 * c + 2] + f4.z * inv_lk, av[4 * c + 3] + f4.w * inv_lk);
+      for (int t = 0; t < NT; ++t) acc[t].axpy(lane + 32 * t < Lk ? w[r * Lk + lane + 32 * t] : 0.f, x);
+    }
+    if (warp == 1) {
+      RegRow<DH> fill;
+      fill.load(s_acc, true);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) acc[t].axpy(inv_lk, fill);
+    }
+    float* dst = warp == 0 ? dk : dv;
+    const long long ls = warp == 0 ? p.k_ls : p.v_ls;
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+      if (lane + 32 * t < Lk) acc[t].store(dst + static_cast<long long>(lane + 32 * t) * ls);
+  } else {
+    // the other warps: dQ in 4-row x 4-channel register tiles, zero rows, and the tail keys' dK / dV
+    const int first = NT > 0 ? 64 : 0;
+    const int tid2 = threadIdx.x - first, n2 = THREADS - first;
+    const int ntiles = ((u + 3) >> 2) * DH4;
+    for (int it = tid2; it < ntiles; it += n2) {
+      const int r0 = (it / DH4) * 4, c = it % DH4;
+      const float* wrow[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wrow[k] = s_ds + min(r0 + k, u - 1) * Lk;
+      float4 o[4];
+      tile4_matvec<DH>(wrow, s_k + 4 * c, Lk, o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r0 + k < u) *reinterpret_cast<float4*>(dq + static_cast<long long>(s_top[r0 + k]) * p.q_ls + 4 * c) = o[k];
+    }
+    for (int i = n2 - 1 - tid2; i < Lq * DH4; i += n2) {  // every other row: zero (reversed: the tile threads come last)
+      const int l = i / DH4, c = i - l * DH4;
+      if (s_sel[l] < 0) *reinterpret_cast<float4*>(dq + static_cast<long long>(l) * p.q_ls + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = n2 - 1 - tid2; i < tail * DH4; i += n2) {
+      const int jt = tail_start + i / DH4, c = i % DH4;
+      Acc4 ak, av;
+#pragma unroll 5
+      for (int r = 0; r < u; ++r) {
+        const int qi = s_top[r];
+        ak.fma(s_ds[r * Lk + jt], s_q + qi * DH + 4 * c);
+        av.fma(s_p[r * Lk + jt], s_do + qi * DH + 4 * c);
       }
+      const float4 f4 = reinterpret_cast<const float4*>(s_acc)[c];
+      float4 vv = av.get();
+      vv.x += f4.x * inv_lk; vv.y += f4.y * inv_lk; vv.z += f4.z * inv_lk; vv.w += f4.w * inv_lk;
+      *reinterpret_cast<float4*>(dk + static_cast<long long>(jt) * p.k_ls + 4 * c) = ak.get();
+      *reinterpret_cast<float4*>(dv + static_cast<long long>(jt) * p.v_ls + 4 * c) = vv;
     }
   }
 }
@@ -850,6 +939,23 @@ static int configure(K kernel, size_t smem) {
     default: RF_ATTN_LAUNCH(KERNEL, 0, ARG, GRID, SMEM, STREAM) break;             \
   }
 
+#define RF_ATTN_SMALL_LAUNCH(KERNEL, DHT, NTT, ARG, GRID, SMEM, STREAM)             \
+  {                                                                                \
+    rc = attn::configure(attn::KERNEL<DHT, NTT>, SMEM);                            \
+    if (rc != RF_OK) return rc;                                                    \
+    attn::KERNEL<DHT, NTT><<<GRID, attn::THREADS, SMEM, STREAM>>>(ARG);            \
+  }
+#define RF_ATTN_SMALL_NT(KERNEL, DHT, ARG, NTVAL, GRID, SMEM, STREAM)              \
+  switch (NTVAL) {                                                                 \
+    case 0: RF_ATTN_SMALL_LAUNCH(KERNEL, DHT, 0, ARG, GRID, SMEM, STREAM) break;   \
+    case 1: RF_ATTN_SMALL_LAUNCH(KERNEL, DHT, 1, ARG, GRID, SMEM, STREAM) break;   \
+    case 2: RF_ATTN_SMALL_LAUNCH(KERNEL, DHT, 2, ARG, GRID, SMEM, STREAM) break;   \
+    default: RF_ATTN_SMALL_LAUNCH(KERNEL, DHT, 3, ARG, GRID, SMEM, STREAM) break;  \
+  }
+#define RF_ATTN_SMALL_DISPATCH(KERNEL, ARG, DHVAL, NTVAL, GRID, SMEM, STREAM)      \
+  if ((DHVAL) == 8) RF_ATTN_SMALL_NT(KERNEL, 8, ARG, NTVAL, GRID, SMEM, STREAM)    \
+  else RF_ATTN_SMALL_NT(KERNEL, 16, ARG, NTVAL, GRID, SMEM, STREAM)
+
 extern "C" int rf_attention_fwd(const RfAttnParams* p, void* stream) {
   using namespace rf;
   RF_CHECK_ARG(p && p->out, "rf_attention_fwd: null pointer");
@@ -858,8 +964,7 @@ extern "C" int rf_attention_fwd(const RfAttnParams* p, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (attn::small_path(p)) {
     const size_t smem = attn::small_fwd_smem(p);
-    if (p->dh == 8) RF_ATTN_LAUNCH(attention_small_fwd_kernel, 8, *p, p->B * p->H, smem, s)
-    else RF_ATTN_LAUNCH(attention_small_fwd_kernel, 16, *p, p->B * p->H, smem, s)
+    RF_ATTN_SMALL_DISPATCH(attention_small_fwd_kernel, *p, p->dh, attn::small_nt(p->Lk), p->B * p->H, smem, s)
     RF_LAUNCH_OK();
     return RF_OK;
   }
@@ -878,8 +983,7 @@ extern "C" int rf_attention_bwd(const RfAttnBwdParams* p, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (attn::small_path(&p->f)) {
     const size_t smem = attn::small_bwd_smem(&p->f);
-    if (p->f.dh == 8) RF_ATTN_LAUNCH(attention_small_bwd_kernel, 8, *p, p->f.B * p->f.H, smem, s)
-    else RF_ATTN_LAUNCH(attention_small_bwd_kernel, 16, *p, p->f.B * p->f.H, smem, s)
+    RF_ATTN_SMALL_DISPATCH(attention_small_bwd_kernel, *p, p->f.dh, attn::small_nt(p->f.Lk), p->f.B * p->f.H, smem, s)
     RF_LAUNCH_OK();
     return RF_OK;
   }

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "attention" --timeout 300 -p no:cacheprovider 2>&1 | tail -15
-PYTHONPATH=. timeout 300 python tools/microbench.py 2>&1 | grep -E "^attention" | tee gpurun_out/microbench_attn_v3.log
-RF_ATTN_SMALL=0 PYTHONPATH=. timeout 300 python tools/microbench.py 2>&1 | grep -E "^attention" | tee gpurun_out/microbench_attn_v3_generic.log
+PYTHONPATH=. timeout 300 python tools/microbench.py 2>&1 | grep -E "^attention" | tee gpurun_out/microbench_attn_v5.log
 timeout 600 python -m pytest tests/test_gpu_model.py -q -m gpu --timeout 300 -p no:cacheprovider 2>&1 | tail -8
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v13.log 2>&1; grep "^{" gpurun_out/bench_v13.log | cut -c1-220
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v15.log 2>&1; grep "^{" gpurun_out/bench_v15.log | cut -c1-220
