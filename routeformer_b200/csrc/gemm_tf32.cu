@@ -28,12 +28,13 @@ namespace gemm {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;  // 32 fp32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;    // K of one tcgen05.mma.kind::tf32
-constexpr int STAGES = 3;
+constexpr int STAGES_SHALLOW = 3;  // 2 CTAs per SM (large grids: bytes in flight come from CTA count)
+constexpr int STAGES_DEEP = 6;     // 1 CTA per SM (grids below one wave: the K loop of each CTA is latency-bound)
 constexpr int NUM_THREADS = 128;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KiB
 constexpr int GROUP_BYTES = 32 * BLOCK_K * 4;   // one MN-major box: 32 k-rows x 128 B
 
-template <int BLOCK_N>
+template <int BLOCK_N, int STAGES = STAGES_SHALLOW>
 struct Tile {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -322,11 +323,11 @@ struct RowEpilogue {
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, STAGES == STAGES_SHALLOW ? 2 : 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const Args a) {
-  using T = Tile<BLOCK_N>;
+  using T = Tile<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * T::STAGE_BYTES);
@@ -827,14 +828,32 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
     RF_LAUNCH_OK();
     return RF_OK;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    RF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-    attr_set = true;
-  }
   dim3 grid(tiles_n, tiles_m, splits);
   RF_CHECK_ARG(grid.y <= 65535, "rf_gemm_tf32: M=%d exceeds 65535 row tiles", p->M);
-  gemm_tf32_kernel<BLOCK_N><<<grid, NUM_THREADS, T::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmP, args);
+  static int deep = -1;
+  if (deep < 0) {
+    const char* e = getenv("RF_GEMM_DEEP");
+    deep = (e && e[0] == '0') ? 0 : 1;
+  }
+  // A grid that does not even fill one wave leaves the HBM/L2 pipes idle while every CTA walks its K loop at the pace of the
+  // TMA round trip (measured 0.38 us per k-block with 3 stages): give those CTAs the whole SM's shared memory instead.
+  if (deep && static_cast<long long>(tiles_n) * tiles_m * splits <= num_sms() && args.kb_per_split > STAGES_SHALLOW) {
+    using TD = Tile<BLOCK_N, STAGES_DEEP>;
+    static bool attr_deep = false;
+    if (!attr_deep) {
+      RF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, STAGES_DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD::SMEM_BYTES));
+      attr_deep = true;
+    }
+    gemm_tf32_kernel<BLOCK_N, STAGES_DEEP><<<grid, NUM_THREADS, TD::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmP, args);
+    RF_LAUNCH_OK();
+    return RF_OK;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    RF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, STAGES_SHALLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm_tf32_kernel<BLOCK_N, STAGES_SHALLOW><<<grid, NUM_THREADS, T::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmP, args);
   RF_LAUNCH_OK();
   return RF_OK;
 }
@@ -870,7 +889,7 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   if (splits <= 0) {
     splits = 1;
     if (p->accumulate && plain) {
-      const int want = ceil_div(2 * num_sms(), tiles);       // ~2 CTAs per SM
+      const int want = max(1, (2 * num_sms()) / tiles);       // fill, but do not overflow, one wave of 2 CTAs per SM
       splits = max(1, min(want, kb_total / 4));              // keep >= 4 k-blocks per split
     }
   }
