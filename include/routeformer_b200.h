@@ -247,6 +247,11 @@ int rf_median_downsample(const float* x, float* y, int B, int S, int C, int targ
  * result[1] = reference "FDE" = Frobenius norm of the LAST batch element's [T,2] error;
  * per_sample (optional, [B,2]) = per-clip (ADE, FDE) as computed by full_comparison.py:667-674. */
 int rf_ade_fde(const float* pred, const float* truth, int B, int T, float* result, float* per_sample, void* stream);
+/* replaces: experiments/full_comparison.py:654-679 (_eval_step): mean of S stochastic forwards, then per clip the
+ * FutureDiscountedLoss, ADE and "FDE" of the [1,T,2] slices.  preds [S,B,T,2] (sample-major), truth [B,T,2];
+ * mean_pred (optional, [B,T,2]) = stack(preds).mean(0); per_clip [B,3] = (loss, ade, fde).  kind / gamma / epsilon as below. */
+int rf_eval_samples(const float* preds, const float* truth, int S, int B, int T, float gamma, float epsilon, int kind,
+                    float* mean_pred, float* per_clip, void* stream);
 /* replaces: losses/future_discounted_mse.py:56-95 (smooth_l1 | mse | mae with gamma^t weights).
  * kind: 0 smooth_l1, 1 mse, 2 mae.  loss[0] = mean over B*T*C.  bwd writes dpred = dloss * d loss/d pred. */
 int rf_discounted_loss_fwd(const float* pred, long long ldp, const float* truth, long long ldt, int B, int T,

@@ -150,10 +150,80 @@ def generate_submodules():
     print("submodules ok")
 
 
+def generate_steps():
+    """The two callers of the path, experiments/full_comparison.py:470-532 (training_step) and :654-679 (_eval_step), evaluated
+    with the reference's own model / loss / metric objects.  The LightningModule that hosts them needs lightning, wandb and
+    the datasets, so the few lines of step logic are replayed here verbatim around the reference components."""
+    ref = R.load()
+    cfg, spec = O.OracleConfig(**SMALL), O.BackboneSpec(**SMALL_SPEC)
+    B, wseed, dseed = 3, 17, 18
+    model = R.build_reference_model(cfg, spec)
+    sd = O.fill_state_dict(model.state_dict(), wseed)
+    model.load_state_dict(sd)
+    batch = {"train": O.synthetic_batch(B, cfg, "tiny", seed=dseed), "target": O.synthetic_batch(B, cfg, "tiny", seed=dseed + 1, T=cfg.pred_len)}
+    # continue the target track from the end of the input track, as a real clip does
+    batch["target"]["gps"] = batch["target"]["gps"] + batch["train"]["gps"][:, -1:]
+    discount, eps, veps, ratio = {0: 0.97}, 1.0, 0.3, 0.5
+    traj_loss = ref.FutureDiscountedLoss(discount, eps, loss_function="smooth_l1")
+    dense_lossf = ref.FutureDiscountedLoss(discount, veps, loss_function="smooth_l1")
+    gold = {"cfg": SMALL, "spec": SMALL_SPEC, "B": B, "wseed": wseed, "dseed": dseed, "discount": discount, "epsilon": eps,
+            "visual_epsilon": veps, "dense_loss_ratio": ratio}
+    # ---- training_step (:470-532), epochs 0 (dense weight 0) and 10 (weight active)
+    model.train()
+    for epoch in (0, 10):
+        model.zero_grad()
+        torch.manual_seed(12345)
+        with DrawLog() as dl:
+            inp, target = batch["train"], batch["target"]
+            target_gps = target["gps"].to(torch.float32)
+            future_gps, future_visual_features = model(inp)
+            _, target_visual_features = model.preprocess_batch(target, training=False)
+            target_visual_features = target_visual_features[:, : future_visual_features.shape[1]]
+            trajectory_loss = traj_loss(future_gps, target_gps)
+            target_visual_features = target_visual_features.detach()
+            dense_loss = dense_lossf(future_visual_features, target_visual_features)
+            dense_loss_weight = (ratio * trajectory_loss / max(dense_loss, 1e-6)).detach()
+            if epoch < 10:
+                dense_loss_weight = 0
+            loss = trajectory_loss + dense_loss_weight * dense_loss
+        loss.backward()
+        gold[f"train_epoch{epoch}"] = {
+            "loss": loss.item(), "trajectory_loss": trajectory_loss.item(), "dense_loss": dense_loss.item(),
+            "ade": ref.ade(future_gps, target_gps).item(), "fde": ref.fde(future_gps, target_gps).item(),
+            "target_visual": target_visual_features.clone(), "draws": dl.log,
+            "grad_norm": {k: p.grad.norm().item() for k, p in model.named_parameters() if p.grad is not None},
+        }
+    # ---- _eval_step (:654-679), from the same initial state (the training passes above moved the BatchNorm running statistics)
+    model.load_state_dict(sd)
+    model.eval()
+    torch.manual_seed(12345)
+    with torch.no_grad(), DrawLog() as dl:
+        inter = []
+        for _ in range(5):
+            future_gps, _ = model(batch["train"])
+            inter.append(future_gps)
+        future_gps = torch.stack(inter).mean(dim=0)
+        losses, ades, fdes = [], [], []
+        target_gps = batch["target"]["gps"]
+        for index in range(future_gps.shape[0]):
+            fgps, tgps = future_gps[index:index + 1], target_gps[index:index + 1]
+            losses.append(traj_loss(fgps, tgps))
+            ades.append(ref.ade(fgps, tgps))
+            fdes.append(ref.fde(fgps, tgps))
+    gold["eval"] = {"mean_prediction": future_gps.clone(), "samples": torch.stack(inter), "losses": torch.stack(losses),
+                    "ades": torch.stack(ades), "fdes": torch.stack(fdes), "draws": dl.log}
+    torch.save(gold, os.path.join(OUT, "steps_small.pt"))
+    print("steps ok: train loss", gold["train_epoch0"]["loss"], gold["train_epoch10"]["loss"], "eval ade", gold["eval"]["ades"].tolist())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     names = sys.argv[1:] or list(CASES)
+    if names == ["steps"]:
+        generate_steps()
+        names = []
     for n in names:
         generate(n)
     if len(sys.argv) == 1:
         generate_submodules()
+        generate_steps()

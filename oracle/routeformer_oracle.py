@@ -647,6 +647,41 @@ def future_discounted_loss(pred: Tensor, truth: Tensor, gamma: float = 0.97, kin
 
 
 # --------------------------------------------------------------------------------------
+# the two callers of the path (experiments/full_comparison.py), for one model
+# --------------------------------------------------------------------------------------
+def training_step(model: "Routeformer", batch: dict, discount: float = 0.97, dense_loss_ratio: float = 0.5,
+                  current_epoch: int = 0, draw=None):
+    """full_comparison.py:470-532 for a dense-prediction, non-autoregressive model -> (loss, metrics)."""
+    draw = draw or CpuRandint()
+    inp, target = batch["train"], batch["target"]
+    target_gps = target["gps"].to(torch.float32)
+    future_gps, future_visual = model.forward(inp, training=True, draw=draw)
+    _, target_visual = model.preprocess(target, False, draw)               # :482, eval-mode target pass
+    target_visual = target_visual[:, : future_visual.shape[1]].detach()    # :483-485, :497
+    trajectory_loss = future_discounted_loss(future_gps, target_gps, discount)
+    dense_loss = future_discounted_loss(future_visual, target_visual, discount)
+    weight = (dense_loss_ratio * trajectory_loss / max(dense_loss, 1e-6)).detach() if current_epoch >= 10 else 0  # :502-508
+    loss = trajectory_loss + weight * dense_loss
+    return loss, {"trajectory_loss": trajectory_loss, "dense_loss": dense_loss, "ade": ade(future_gps, target_gps),
+                  "fde": fde(future_gps, target_gps), "target_visual": target_visual}
+
+
+def eval_step(model: "Routeformer", batch: dict, discount: float = 0.97, n_samples: int = 5, draw=None):
+    """full_comparison.py:654-679 (the caller seeds torch with 12345 first): mean of five stochastic forwards, per-clip metrics."""
+    draw = draw or CpuRandint()
+    target_gps = batch["target"]["gps"]
+    preds = []
+    for _ in range(n_samples):
+        out = model.forward(batch["train"], training=False, draw=draw)
+        preds.append(out[0] if isinstance(out, tuple) else out)
+    mean = torch.stack(preds).mean(dim=0)
+    losses = torch.stack([future_discounted_loss(mean[i:i + 1], target_gps[i:i + 1], discount) for i in range(mean.shape[0])])
+    ades = torch.stack([ade(mean[i:i + 1], target_gps[i:i + 1]) for i in range(mean.shape[0])])
+    fdes = torch.stack([fde(mean[i:i + 1], target_gps[i:i + 1]) for i in range(mean.shape[0])])
+    return losses, ades, fdes, mean, torch.stack(preds)
+
+
+# --------------------------------------------------------------------------------------
 # deterministic weights and synthetic batches (shared by golden generation and tests)
 # --------------------------------------------------------------------------------------
 def fill_state_dict(sd: SD, seed: int) -> SD:

@@ -6,6 +6,7 @@ everything underneath is hand-written CUDA behind the C ABI of include/routeform
 from .backbone import PatchEmbedBackbone, VideoBackboneModule  # noqa: F401
 from .config import (BaseConfig, GPSBackboneConfig, PatchBackboneConfig, RouteformerConfig,  # noqa: F401
                      VideoBackboneConfig)
+from .experiment import ParallelTrainerSteps  # noqa: F401
 from .informer import Informer  # noqa: F401
 from .layers import PerceiveDecoder, PerceiveEncoder  # noqa: F401
 from .metrics import FutureDiscountedLoss, ade, ade_fde_per_sample, fde  # noqa: F401
@@ -14,5 +15,5 @@ from .routeformer import Routeformer  # noqa: F401
 __all__ = [
     "Routeformer", "RouteformerConfig", "GPSBackboneConfig", "VideoBackboneConfig", "PatchBackboneConfig", "BaseConfig",
     "VideoBackboneModule", "PatchEmbedBackbone", "Informer", "PerceiveEncoder", "PerceiveDecoder",
-    "ade", "fde", "ade_fde_per_sample", "FutureDiscountedLoss",
+    "ade", "fde", "ade_fde_per_sample", "FutureDiscountedLoss", "ParallelTrainerSteps",
 ]

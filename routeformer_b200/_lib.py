@@ -120,6 +120,7 @@ SIGNATURES = {
     "rf_decode_waypoints_bwd": [_P, _P, _P, _L, _I, _I, _I, _I, _F, _P],
     "rf_median_downsample": [_P, _P, _I, _I, _I, _I, _P],
     "rf_ade_fde": [_P, _P, _I, _I, _P, _P, _P],
+    "rf_eval_samples": [_P, _P, _I, _I, _I, _F, _F, _I, _P, _P, _P],
     "rf_discounted_loss_fwd": [_P, _L, _P, _L, _I, _I, _I, _F, _F, _I, _P, _P],
     "rf_discounted_loss_bwd": [_P, _L, _P, _L, _I, _I, _I, _F, _F, _I, _P, _F, _P, _L, _I, _P],
     "rf_colsum_accumulate": [_P, _L, _I, _I, _P, _P],

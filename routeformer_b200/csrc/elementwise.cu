@@ -386,6 +386,34 @@ __device__ __forceinline__ float loss_grad(float e, int kind, float eps) {
   if (fabsf(e) < eps) return 0.f;
   return kind == 1 ? 2.f * e : (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f));
 }
+// one warp per clip: mean over the S stochastic forwards, then loss / ADE / FDE of that clip (full_comparison.py:654-679)
+__global__ void eval_samples_kernel(const float* __restrict__ preds, const float* __restrict__ truth, int S, int B, int T, float gamma,
+                                    float eps, int kind, float* __restrict__ mean_pred, float* __restrict__ per_clip) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const long long stride = static_cast<long long>(B) * T * 2;
+  for (int b = blockIdx.x * nwarps + warp; b < B; b += gridDim.x * nwarps) {
+    float sl = 0.f, sn = 0.f, sq = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const long long i = (static_cast<long long>(b) * T + t) * 2;
+      float px = 0.f, py = 0.f;
+      for (int s = 0; s < S; ++s) { px += preds[s * stride + i]; py += preds[s * stride + i + 1]; }  // stack(...).mean(0)
+      px /= S; py /= S;
+      if (mean_pred) { mean_pred[i] = px; mean_pred[i + 1] = py; }
+      const float ex = px - truth[i], ey = py - truth[i + 1];
+      sl += (loss_term(ex, kind, eps) + loss_term(ey, kind, eps)) * powf(gamma, static_cast<float>(t));
+      const float q = ex * ex + ey * ey;
+      sn += sqrtf(q);
+      sq += q;
+    }
+    sl = warp_sum(sl); sn = warp_sum(sn); sq = warp_sum(sq);
+    if (lane == 0) {
+      per_clip[3 * b] = sl / (2.f * T);
+      per_clip[3 * b + 1] = sn / T;
+      per_clip[3 * b + 2] = sqrtf(sq);
+    }
+  }
+}
+
 __global__ void discounted_loss_fwd_kernel(const float* __restrict__ pred, long long ldp, const float* __restrict__ truth, long long ldt,
                                            int T, int C, float gamma, float eps, int kind, float inv_count, float* __restrict__ loss,
                                            long long total) {
@@ -592,6 +620,15 @@ extern "C" int rf_median_downsample(const float* x, float* y, int B, int S, int 
 extern "C" int rf_ade_fde(const float* pred, const float* truth, int B, int T, float* result, float* per_sample, void* stream) {
   RF_CHECK_ARG(pred && truth && result && B > 0 && T > 0, "rf_ade_fde: bad arguments");
   ade_fde_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred, truth, B, T, result, per_sample);
+  RF_LAUNCH_OK();
+  return RF_OK;
+}
+
+extern "C" int rf_eval_samples(const float* preds, const float* truth, int S, int B, int T, float gamma, float epsilon, int kind,
+                               float* mean_pred, float* per_clip, void* stream) {
+  RF_CHECK_ARG(preds && truth && per_clip && S > 0 && B > 0 && T > 0 && kind >= 0 && kind <= 2, "rf_eval_samples: bad arguments");
+  eval_samples_kernel<<<min(ceil_div(B, 8), 1184), 256, 0, static_cast<cudaStream_t>(stream)>>>(preds, truth, S, B, T, gamma, epsilon, kind,
+                                                                                                   mean_pred, per_clip);
   RF_LAUNCH_OK();
   return RF_OK;
 }

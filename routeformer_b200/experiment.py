@@ -1,0 +1,82 @@
+"""The two callers of the hot path in experiments/full_comparison.py, for ONE Routeformer model.
+
+`ParallelTrainerSteps.training_step` = `ParallelTrainer.training_step` (:470-532): forward on the input window, the target pass
+`preprocess_batch(target, training=False)` for the dense supervision, the two FutureDiscountedLosses and the dense-loss
+re-weighting (`dense_loss_ratio * trajectory_loss / max(dense_loss, 1e-6)`, detached, switched on after epoch 10), plus the
+logged ADE / FDE.  `eval_step` = `_eval_step` (:654-679): `torch.manual_seed(12345)`, five stochastic forwards, their mean,
+then per-clip loss / ADE / FDE -- here ONE kernel (`rf_eval_samples`) instead of a Python loop of 3 x B tiny reductions.
+The Lightning plumbing around them (logging, PCI buckets, optimiser config) stays with the caller.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+from . import ops
+from .metrics import FutureDiscountedLoss, ade, fde
+
+
+class ParallelTrainerSteps:
+    def __init__(self, model, n_eval_samples: int = 5):
+        c = model.configs
+        self.model = model
+        self.n_eval_samples = n_eval_samples
+        # full_comparison.py:445-454
+        self.trajectory_loss = FutureDiscountedLoss(c.discount_factor, c.epsilon, loss_function="smooth_l1")
+        self.dense_loss = FutureDiscountedLoss(c.discount_factor, c.visual_epsilon, loss_function="smooth_l1")
+
+    # -- full_comparison.py:470-532 ----------------------------------------------------------------
+    def training_step(self, batch: Dict[str, Dict[str, torch.Tensor]], current_epoch: int = 0) -> Tuple[torch.Tensor, dict]:
+        model, c = self.model, self.model.configs
+        inp, target = batch["train"], batch["target"]
+        target_gps = target["gps"].to(torch.float32)
+        metrics = {}
+        if c.dense_prediction:
+            future_gps, future_visual = model(inp)
+            with torch.no_grad():
+                _, target_visual = model.preprocess_batch(target, training=False)
+            target_visual = target_visual[:, : future_visual.shape[1]]
+            step = c.autoregressive_step_size
+            if c.autoregressive:
+                future_gps, target_gps = future_gps[:, :step], target_gps[:, :step]
+            trajectory_loss = self.trajectory_loss(future_gps, target_gps)
+            if c.autoregressive:
+                trajectory_loss = trajectory_loss * (c.gps_backbone_config.pred_len / step)
+            target_visual = target_visual.detach()
+            if c.autoregressive:
+                future_visual, target_visual = future_visual[:, :step], target_visual[:, :step]
+            dense_loss = self.dense_loss(future_visual, target_visual)
+            weight = (c.dense_loss_ratio * trajectory_loss / torch.clamp(dense_loss, min=1e-6)).detach()
+            if current_epoch < 10:  # "Activate dense loss after 10 epochs"
+                weight = 0
+            metrics["train_dense_loss"] = dense_loss
+            loss = trajectory_loss + weight * dense_loss
+        else:
+            future_gps = model(inp)
+            trajectory_loss = self.trajectory_loss(future_gps, target_gps)
+            loss = trajectory_loss
+        metrics["train_loss"] = trajectory_loss
+        metrics["train_ade"] = ade(future_gps, target_gps)
+        metrics["train_fde"] = fde(future_gps, target_gps)
+        return loss, metrics
+
+    # -- full_comparison.py:654-679 ----------------------------------------------------------------
+    @torch.no_grad()
+    def eval_step(self, batch: Dict[str, Dict[str, torch.Tensor]]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Returns per-clip (losses, ades, fdes), each [B].  The model must be in eval mode, as under Lightning's validation loop."""
+        model = self.model
+        torch.manual_seed(12345)
+        inp, target_gps = batch["train"], batch["target"]["gps"]
+        preds = []
+        for _ in range(self.n_eval_samples):
+            out = model(inp)
+            preds.append(out[0] if model.configs.dense_prediction else out)
+        loss = self.trajectory_loss
+        if loss.current_epoch in loss.discount_factor_dict:
+            loss.current_discount_factor = loss.discount_factor_dict[loss.current_epoch]
+        eps = 0.0 if loss.epsilon is None else float(loss.epsilon)
+        self.last_mean_prediction, per_clip = ops.eval_samples(torch.stack(preds), target_gps, float(loss.current_discount_factor), eps,
+                                                               loss.loss_function)
+        torch.seed()
+        return per_clip[:, 0], per_clip[:, 1], per_clip[:, 2]

@@ -311,6 +311,18 @@ def ade_fde(pred: torch.Tensor, truth: torch.Tensor, per_sample: bool = False):
 LOSS_KINDS = {"smooth_l1": 0, "mse": 1, "mae": 2}
 
 
+def eval_samples(preds: torch.Tensor, truth: torch.Tensor, gamma: float, epsilon: float, kind: str = "smooth_l1"):
+    """preds [S,B,T,2] stacked stochastic forwards, truth [B,T,2] -> (mean prediction [B,T,2], per clip [B,3] = loss, ade, fde)."""
+    S, B, T, _ = preds.shape
+    preds, truth = _f32(preds, "preds").contiguous(), _f32(truth, "truth").contiguous()
+    mean = torch.empty(B, T, 2, device=preds.device, dtype=torch.float32)
+    per_clip = torch.empty(B, 3, device=preds.device, dtype=torch.float32)
+    check(_lib.load().rf_eval_samples(_ptr(preds), _ptr(truth), S, B, T, float(gamma), float(epsilon), LOSS_KINDS[kind], _ptr(mean),
+                                      _ptr(per_clip), _stream()), "rf_eval_samples")
+    _count()
+    return mean, per_clip
+
+
 def discounted_loss_fwd(pred, truth, gamma, epsilon, kind):
     B, T = pred.shape[:2]
     Cc = pred[0, 0].numel()

@@ -278,6 +278,22 @@ def test_attention_forced_selection(ops):
     assert rel_err(out.cpu(), ctx) < 1e-5
 
 
+def test_reductions_eval_samples(ops):
+    """rf_eval_samples: mean of S stochastic forwards + per-clip loss / ADE / FDE (full_comparison.py:654-679)."""
+    gen = g(77)
+    S, B, T = 5, 37, 30
+    preds = torch.randn(S, B, T, 2, generator=gen) * 3 + 50
+    truth = torch.randn(B, T, 2, generator=gen) * 3 + 50
+    mean_ref = torch.stack(list(preds)).mean(dim=0)
+    for kind, eps in (("smooth_l1", 1.0), ("mse", 0.3), ("mae", 0.3)):
+        mean, per_clip = ops.eval_samples(preds.to(DEV), truth.to(DEV), 0.97, eps, kind)
+        assert rel_err(mean.cpu(), mean_ref) < 1e-6
+        for i in range(B):
+            p, t = mean_ref[i:i + 1], truth[i:i + 1]
+            ref = torch.stack([O.future_discounted_loss(p, t, 0.97, kind, eps), O.ade(p, t), O.fde(p, t)])
+            assert torch.allclose(per_clip[i].cpu(), ref, rtol=2e-5, atol=1e-6), (kind, i)
+
+
 # ------------------------------------------------------------------------------------------------ norms
 @pytest.mark.parametrize("M,D", [(1000, 128), (77, 64), (300, 832), (33, 30)])
 def test_layernorm(ops, M, D):

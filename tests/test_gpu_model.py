@@ -224,3 +224,81 @@ def test_cuda_graph_step_matches_eager():
         run_to_run = rel_err(g2.cpu(), g0.cpu())
         assert rel_err(g1.cpu(), g0.cpu()) <= max(5 * run_to_run, 1e-5), (rel_err(g1.cpu(), g0.cpu()), run_to_run)
     assert eager[0][0] != eager[1][0]  # different draws every step
+
+
+def _steps_case():
+    gold = load_golden("steps_small")
+    cfg, spec = O.OracleConfig(**gold["cfg"]), O.BackboneSpec(**gold["spec"])
+    sd = O.fill_state_dict(O.state_dict_template(cfg, spec), gold["wseed"])
+    batch = {"train": O.synthetic_batch(gold["B"], cfg, "tiny", seed=gold["dseed"]),
+             "target": O.synthetic_batch(gold["B"], cfg, "tiny", seed=gold["dseed"] + 1, T=cfg.pred_len)}
+    batch["target"]["gps"] = batch["target"]["gps"] + batch["train"]["gps"][:, -1:]
+    model = build_product(cfg, spec, discount_factor=gold["discount"], epsilon=gold["epsilon"], visual_epsilon=gold["visual_epsilon"],
+                          dense_loss_ratio=gold["dense_loss_ratio"]).to(DEV)
+    model.load_state_dict(sd)
+    dev_batch = {k: to_device(v, DEV) for k, v in batch.items()}
+    return gold, cfg, spec, sd, batch, model, dev_batch
+
+
+@pytest.mark.parametrize("epoch", [0, 10])
+def test_training_step_caller(epoch):
+    """ParallelTrainerSteps.training_step (full_comparison.py:470-532) vs the oracle (replaying the GPU's selections) and the
+    reference's golden values: forward, eval-mode target pass, both losses, the detached dense re-weighting, ADE / FDE."""
+    import routeformer_b200 as R
+
+    gold, cfg, spec, sd, batch, model, dev_batch = _steps_case()
+    model.train()
+    model.record_tops = []
+    steps = R.ParallelTrainerSteps(model)
+    torch.manual_seed(12345)
+    loss, metrics = steps.training_step(dev_batch, current_epoch=epoch)
+    loss.backward()
+    torch.cuda.synchronize()
+    g = gold[f"train_epoch{epoch}"]
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and not k.endswith(".pe") and
+                                          not k.startswith("video_backbone")) for k, v in sd.items()}
+    orc = O.Routeformer(params, cfg, spec)
+    torch.manual_seed(12345)
+    rloss, rm = O.training_step(orc, batch, gold["discount"][0], gold["dense_loss_ratio"], epoch,
+                                ReplayDraw(tops_for_oracle(model.record_tops, ["right", "left", "front"])))
+    assert abs(loss.item() - rloss.item()) < 2e-3 * abs(rloss.item())
+    assert abs(metrics["train_loss"].item() - rm["trajectory_loss"].item()) < 2e-3 * abs(rm["trajectory_loss"].item())
+    assert abs(metrics["train_dense_loss"].item() - rm["dense_loss"].item()) < 1e-2 * abs(rm["dense_loss"].item())
+    assert abs(metrics["train_ade"].item() - rm["ade"].item()) < 2e-3 * rm["ade"].item()
+    assert abs(metrics["train_fde"].item() - rm["fde"].item()) < 2e-3 * rm["fde"].item()
+    # raw, against the reference's own numbers (no replay)
+    assert abs(loss.item() - g["loss"]) < 2e-2 * abs(g["loss"])
+    assert abs(metrics["train_ade"].item() - g["ade"]) < 1e-2 * g["ade"]
+    named = dict(model.named_parameters())
+    missing = [k for k, p in params.items() if p.requires_grad and (named[k].grad is None or not torch.isfinite(named[k].grad).all())]
+    assert not missing, missing
+
+
+def test_eval_step_caller():
+    """ParallelTrainerSteps.eval_step (full_comparison.py:654-679): RNG order over the five forwards, mean prediction, per-clip metrics."""
+    import routeformer_b200 as R
+
+    gold, cfg, spec, sd, batch, model, dev_batch = _steps_case()
+    model.eval()
+    steps = R.ParallelTrainerSteps(model)
+    logs = []
+    orig = model.prepare_draws
+
+    def spy(*a, **k):
+        plan = orig(*a, **k)
+        logs.extend(model.last_draw_log)
+        return plan
+
+    model.prepare_draws = spy
+    losses, ades, fdes = steps.eval_step(dev_batch)
+    torch.cuda.synchronize()
+    e = gold["eval"]
+    assert [(lk, (lq, u)) for lk, lq, u in logs] == [tuple(d) for d in e["draws"]]
+    assert rel_err(steps.last_mean_prediction.cpu(), e["mean_prediction"]) < 5e-3
+    assert torch.allclose(ades.cpu(), e["ades"], rtol=1e-2) and torch.allclose(fdes.cpu(), e["fdes"], rtol=1e-2)
+    assert torch.allclose(losses.cpu(), e["losses"], rtol=1e-2)
+    # the metric kernel itself, exactly, on the product's own mean prediction
+    mean = steps.last_mean_prediction.cpu()
+    t = batch["target"]["gps"]
+    ref_ade = torch.stack([O.ade(mean[i:i + 1], t[i:i + 1]) for i in range(mean.shape[0])])
+    assert torch.allclose(ades.cpu(), ref_ade, rtol=2e-5)

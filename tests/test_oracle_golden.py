@@ -106,3 +106,49 @@ def test_explicit_circular_conv_matches_aten():
         e = O.circular_conv3_explicit(x, w, b, pad)
         assert a.shape == (3, L + 2 * pad - 2, 8)
         assert torch.allclose(a, e, atol=1e-5)
+
+
+def _steps_case():
+    gold = load_golden("steps_small")
+    cfg, spec = O.OracleConfig(**gold["cfg"]), O.BackboneSpec(**gold["spec"])
+    sd = O.fill_state_dict(O.state_dict_template(cfg, spec), gold["wseed"])
+    batch = {"train": O.synthetic_batch(gold["B"], cfg, "tiny", seed=gold["dseed"]),
+             "target": O.synthetic_batch(gold["B"], cfg, "tiny", seed=gold["dseed"] + 1, T=cfg.pred_len)}
+    batch["target"]["gps"] = batch["target"]["gps"] + batch["train"]["gps"][:, -1:]
+    return gold, cfg, spec, sd, batch
+
+
+@pytest.mark.parametrize("epoch", [0, 10])
+def test_training_step_matches_reference(epoch):
+    """experiments/full_comparison.py:470-532: forward + target pass + both losses + dense re-weighting (+ gradients)."""
+    gold, cfg, spec, sd, batch = _steps_case()
+    g = gold[f"train_epoch{epoch}"]
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and not k.endswith(".pe")) for k, v in sd.items()}
+    model = O.Routeformer(params, cfg, spec)
+    torch.manual_seed(12345)
+    draw = O.CpuRandint()
+    loss, m = O.training_step(model, batch, gold["discount"][0], gold["dense_loss_ratio"], epoch, draw)
+    assert [(lk, (lq, u)) for lk, lq, u in draw.log] == [tuple(d) for d in g["draws"]]
+    for key in ("trajectory_loss", "dense_loss", "ade", "fde"):
+        assert abs(m[key].item() - g[key]) < 2e-5 * max(1.0, abs(g[key])), key
+    assert abs(loss.item() - g["loss"]) < 2e-5 * max(1.0, abs(g["loss"]))
+    assert rel_err(m["target_visual"], g["target_visual"]) < 2e-5
+    loss.backward()
+    for k, n in g["grad_norm"].items():
+        # fp32 summation order differs between the functional oracle and the reference's module autograd; the saturated
+        # smooth-L1 of this untrained model amplifies it to ~3e-3 on a few decoder projections
+        assert abs(params[k].grad.norm().item() - n) <= 1e-2 * n + 1e-6, (k, params[k].grad.norm().item(), n)
+
+
+def test_eval_step_matches_reference():
+    """experiments/full_comparison.py:654-679: five stochastic forwards under manual_seed(12345), mean, per-clip metrics."""
+    gold, cfg, spec, sd, batch = _steps_case()
+    torch.manual_seed(12345)
+    draw = O.CpuRandint()
+    with torch.no_grad():
+        losses, ades, fdes, mean, samples = O.eval_step(O.Routeformer(sd, cfg, spec), batch, gold["discount"][0], 5, draw)
+    e = gold["eval"]
+    assert [(lk, (lq, u)) for lk, lq, u in draw.log] == [tuple(d) for d in e["draws"]]
+    assert rel_err(samples, e["samples"]) < 2e-6 and rel_err(mean, e["mean_prediction"]) < 2e-6
+    assert torch.allclose(losses, e["losses"], rtol=1e-5) and torch.allclose(ades, e["ades"], rtol=1e-5)
+    assert torch.allclose(fdes, e["fdes"], rtol=1e-5)
