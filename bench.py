@@ -209,13 +209,18 @@ def run_ours(args):
         rec = []
         orig_gemm, orig_crop, orig_af, orig_ab = ops.gemm, ops.fov_crop, ops.attention_fwd, ops.attention_bwd
 
+        gemm_calls = []  # (args, kwargs, work) of every GEMM launch of the step, replayed below for clean per-launch timings
+
         def timed(fn, tag, work):
             def wrapper(*a, **k):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
                 r = fn(*a, **k)
                 e.record()
-                rec.append((tag, s, e, work(*a, **k)))
+                w = work(*a, **k)
+                rec.append((tag, s, e, w))
+                if tag == "gemm":
+                    gemm_calls.append((a, k, w))
                 return r
             return wrapper
 
@@ -257,15 +262,33 @@ def run_ours(args):
             rows = [(s.elapsed_time(e), w) for t_, s, e, w in rec if t_ == tag]
             if rows:
                 kernels[tag] = {"launches": len(rows), "ms": round(sum(r[0] for r in rows), 3), "work": sum(r[1] for r in rows)}
-        # GEMM launches, split by the roofline that bounds each one (time at peak: bytes / HBM vs flops / TF32).  Launches shorter
-        # than 20 us are listed but kept out of the roofline: an event pair around an eager launch adds ~2-4 us of its own.
+        # GEMM launches, split by the roofline that bounds each one (time at peak: bytes / HBM vs flops / TF32).  The eager step
+        # is host-bound (an event pair then also measures the ~10-20 us the host needs to issue the launch), so the launches that
+        # matter -- at least 8 us at the roofline -- are REPLAYED with their own arguments behind a queue of work that keeps the
+        # host ahead of the device; each one is timed by its own event pair on the launching stream.
         g_rows = [(s.elapsed_time(e), w) for t_, s, e, w in rec if t_ == "gemm"]
+        at_peak = lambda w: max(w["bytes"] / (hbm_peak * 1e9), w["flops"] / (tf32_peak * 1e12))
+        replay = [(a_, k_, w) for a_, k_, w in gemm_calls if at_peak(w) >= 8e-6]
+        blocker = torch.empty(256 << 20, device=dev, dtype=torch.float32)
+        timings = []
+        for _ in range(2):  # first pass warms the tensor-map / attribute caches
+            timings.clear()
+            for _ in range(4):
+                blocker.zero_()
+            for a_, k_, w in replay:
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record()
+                orig_gemm(*a_, **k_)
+                e_.record()
+                timings.append((s_, e_, w))
+            torch.cuda.synchronize()
+        del blocker
         fam = {"hbm": [0.0, 0.0, 0.0, 0], "tensor": [0.0, 0.0, 0.0, 0]}
-        for ms_l, w in g_rows:
-            if ms_l < 0.020:
-                continue
+        for s_, e_, w in timings:
+            ms_l = s_.elapsed_time(e_)
             f = fam["hbm" if w["bytes"] / (hbm_peak * 1e9) >= w["flops"] / (tf32_peak * 1e12) else "tensor"]
             f[0] += ms_l; f[1] += w["bytes"]; f[2] += w["flops"]; f[3] += 1
+        gemm_calls.clear()
         kernels["gemm"] = {"launches": len(g_rows), "ms": round(sum(r[0] for r in g_rows), 3)}
         for name, (ms_f, by, fl, n) in fam.items():
             if n:
@@ -290,7 +313,8 @@ def run_ours(args):
                     "bound": dom, "achieved": round(achieved, 1), "peak": peak, "unit": unit, "frac": round(achieved / peak, 4),
                     "traffic": traffic, "peak_source": src, "launches": n, "avg_launch_us": round(1e3 * ms_f / n, 2),
                     "algorithmic_bytes_per_launch": round(by / n), "algorithmic_flops_per_launch": round(fl / n),
-                    "timing": "CUDA events around every launch of one eager (non-graph) step on the launching stream"}
+                    "timing": "the step's own launches (same tensors and arguments), replayed back to back after the step with one CUDA "
+                              "event pair per launch on the launching stream; launches below 8 us at the roofline are left out"}
         if "fov_crop" in kernels:
             c = kernels["fov_crop"]
             gbs = c["work"] / (c["ms"] / 1e3) / 1e9
