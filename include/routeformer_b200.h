@@ -69,7 +69,7 @@ typedef struct {
   int out_size;             /* S: output is S x S */
   int patch;                /* 0: planar [n,3,S,S];  p>0: patch-major rows [(n*G+py)*G+px][(c*p+iy)*p+ix], G=S/p */
   void* out;
-  int out_dtype;            /* RF_F32 | RF_BF16 */
+  int out_dtype;            /* RF_F32 | RF_F16 | RF_BF16 */
   long long out_ld;         /* row pitch in elements when patch>0 (>= 3*p*p) */
 } RfFovCropParams;
 int rf_fov_crop(const RfFovCropParams* p, void* stream);
@@ -101,6 +101,9 @@ typedef struct {
   int split_k;                               /* 0 = auto (only >1 when accumulate=1) */
   int out_group_in, out_group_out, out_row_offset; /* if out_group_in>0: row m is stored at (m/gi)*go + m%gi + offset */
   int round_f16;                             /* 1: round the result through fp16 (backbone plugin returns input dtype) */
+  int ab_dtype;                              /* RF_F32: A, B are fp32, multiplied as TF32 (kind::tf32).  RF_F16: A, B point to fp16
+                                                (kind::f16, fp32 accumulate; the reference backbone runs under fp16 autocast,
+                                                TimmBackbone.py:106-145); K-major operands only, pitches multiples of 8 */
 } RfGemmParams;
 int rf_gemm_tf32(const RfGemmParams* p, void* stream);
 /* Profiling hook: installs (or clears with NULL) a device buffer of >= 8 u64; CTA (0,0,0) of every later GEMM launch records

@@ -89,7 +89,10 @@ class PatchEmbedBackbone(VideoBackboneModule):
         G, S, p, C = c.grid, c.image_size, c.patch, c.channels
         dev = views[0]["video"].device
         n_total = sum(v["video"].shape[0] * len(v["t_idx"]) for v in views)
-        patches = torch.empty(n_total * G * G, 3 * p * p, device=dev, dtype=torch.float32)
+        # fp16 clips: crop to fp16 patches and multiply in fp16 with fp32 accumulation, as the reference backbone does under
+        # autocast (TimmBackbone.py:106-145) -- half the patch bytes and twice the MMA rate of the TF32 path; other dtypes: TF32.
+        half = all(v["video"].dtype == torch.float16 for v in views) and not self.proj.weight.requires_grad
+        patches = torch.empty(n_total * G * G, 3 * p * p, device=dev, dtype=torch.float16 if half else torch.float32)
         row = 0
         round_f16 = True
         for v in views:
@@ -110,9 +113,20 @@ class PatchEmbedBackbone(VideoBackboneModule):
         tokens = torch.empty(n_total * (G * G + 1), C, device=dev, dtype=torch.float32)
         tokens.view(n_total, G * G + 1, C)[:, G * G, :] = -1.0
         # the plugin returns features in the input dtype (fp16 video -> fp16 features, TimmBackbone.py:141-143)
-        ops.gemm(patches, self.proj.weight.view(C, 3 * p * p), tokens, bias=self.proj.bias, out_group=(G * G, G * G + 1, 0),
-                 round_f16=round_f16)
+        ops.gemm(patches, self._weight_matrix(half), tokens, bias=self.proj.bias, out_group=(G * G, G * G + 1, 0), round_f16=round_f16)
         return tokens
+
+    def _weight_matrix(self, half: bool) -> torch.Tensor:
+        """[C, 3*p*p] view of the projection weight; for the fp16 path a cached fp16 copy, refreshed when the weight changes."""
+        w = self.proj.weight
+        mat = w.view(w.shape[0], -1)
+        if not half:
+            return mat
+        key = (w.data_ptr(), w._version)
+        cached = getattr(self, "_w16", None)
+        if cached is None or cached[0] != key:
+            self._w16 = (key, mat.detach().to(torch.float16).contiguous())
+        return self._w16[1]
 
     def forward(self, images: torch.Tensor) -> torch.Tensor:
         """Plugin API: [N,3,H,W] -> [N,C,G,G] in the input dtype, whole-frame FoV."""

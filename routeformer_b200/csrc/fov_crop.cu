@@ -33,6 +33,15 @@ __device__ __forceinline__ void store4(__nv_bfloat16* dst, const float (&v)[4]) 
   *reinterpret_cast<uint2*>(dst) = u;
 }
 
+__device__ __forceinline__ void store4(__half* dst, const float (&v)[4]) {
+  __half2 a = __floats2half2_rn(v[0], v[1]);
+  __half2 b = __floats2half2_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(dst) = u;
+}
+
 struct Args {
   const void* frames; const int* frame_ids; int n_frames, H, W;
   const float* centers; const float* windows;
@@ -66,31 +75,66 @@ __global__ void __launch_bounds__(256) fov_crop_kernel(const Args a) {
   const bool y0_ok = y0 >= 0 && y0 < a.H, y1_ok = (y0 + 1) >= 0 && (y0 + 1) < a.H;
 
   float acc[3][4];
+  // sample columns of the 4 pixels (channel independent)
+  int x0[4];
+  float wx1[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float gx = (2 * (ox0 + i) + 1) * inv_s - 1.0f;
     const float sx = ((fw * gx + (2.0f * cx - 1.0f) + 1.0f) * a.W - 1.0f) * 0.5f;
     const float fx0 = floorf(sx);
-    const int x0 = static_cast<int>(fx0);
-    const float wx1 = sx - fx0, wx0 = 1.0f - wx1;
-    const bool x0_ok = x0 >= 0 && x0 < a.W, x1_ok = (x0 + 1) >= 0 && (x0 + 1) < a.W;
+    x0[i] = static_cast<int>(fx0);
+    wx1[i] = sx - fx0;
+  }
+  const bool rows_in = y0_ok && y1_ok;
+  const bool mono = fw > 0.0f;  // then sx grows with i and the 4 pixels' taps lie in [x0[0], x0[3]+1]
+  const bool cols_in = mono && x0[0] >= 0 && x0[3] + 1 < a.W;
+  const bool cols_out = mono && (x0[3] + 1 < 0 || x0[0] >= a.W);
+  if ((!y0_ok && !y1_ok) || cols_out) {
+    // the whole 4-pixel group samples the zero padding (pad-to-square scene views: ~3/4 of all outputs): constants only
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[c][i] = (0.0f - a.mean[c]) * a.inv_std[c];
+  } else if (rows_in && cols_in) {
+    // interior: all 16 taps are inside the frame, no per-tap predicates
+    const long long r0 = static_cast<long long>(y0) * a.W;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const TS* pl = src + c * plane;
-      float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
-      if (y0_ok) {
-        const TS* row = pl + static_cast<long long>(y0) * a.W;
-        if (x0_ok) v00 = load_px<TS>(row + x0);
-        if (x1_ok) v01 = load_px<TS>(row + x0 + 1);
+      const TS* row0 = src + c * plane + r0;
+      const TS* row1 = row0 + a.W;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float v00 = load_px<TS>(row0 + x0[i]), v01 = load_px<TS>(row0 + x0[i] + 1);
+        const float v10 = load_px<TS>(row1 + x0[i]), v11 = load_px<TS>(row1 + x0[i] + 1);
+        const float wx0 = 1.0f - wx1[i];
+        const float sacc = v00 * (wx0 * wy0) + v01 * (wx1[i] * wy0) + v10 * (wx0 * wy1) + v11 * (wx1[i] * wy1);
+        acc[c][i] = (sacc - a.mean[c]) * a.inv_std[c];
       }
-      if (y1_ok) {
-        const TS* row = pl + static_cast<long long>(y0 + 1) * a.W;
-        if (x0_ok) v10 = load_px<TS>(row + x0);
-        if (x1_ok) v11 = load_px<TS>(row + x0 + 1);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float wx0 = 1.0f - wx1[i];
+      const bool x0_ok = x0[i] >= 0 && x0[i] < a.W, x1_ok = (x0[i] + 1) >= 0 && (x0[i] + 1) < a.W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const TS* pl = src + c * plane;
+        float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
+        if (y0_ok) {
+          const TS* row = pl + static_cast<long long>(y0) * a.W;
+          if (x0_ok) v00 = load_px<TS>(row + x0[i]);
+          if (x1_ok) v01 = load_px<TS>(row + x0[i] + 1);
+        }
+        if (y1_ok) {
+          const TS* row = pl + static_cast<long long>(y0 + 1) * a.W;
+          if (x0_ok) v10 = load_px<TS>(row + x0[i]);
+          if (x1_ok) v11 = load_px<TS>(row + x0[i] + 1);
+        }
+        // same association order as ATen's grid_sampler: sum of (value * area weight)
+        const float sacc = v00 * (wx0 * wy0) + v01 * (wx1[i] * wy0) + v10 * (wx0 * wy1) + v11 * (wx1[i] * wy1);
+        acc[c][i] = (sacc - a.mean[c]) * a.inv_std[c];
       }
-      // same association order as ATen's grid_sampler: sum of (value * area weight)
-      const float s = v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
-      acc[c][i] = (s - a.mean[c]) * a.inv_std[c];
     }
   }
   TD* out = reinterpret_cast<TD*>(a.out);
@@ -114,6 +158,7 @@ static int dispatch_out(const RfFovCropParams* p, const Args& a, cudaStream_t s)
   dim3 grid(ceil_div(p->out_size, ROWS_PER_CTA), p->n_frames);
   const int threads = ((quads * ROWS_PER_CTA + 31) / 32) * 32;
   if (p->out_dtype == RF_F32) fov_crop_kernel<TS, float><<<grid, threads, 0, s>>>(a);
+  else if (p->out_dtype == RF_F16) fov_crop_kernel<TS, __half><<<grid, threads, 0, s>>>(a);
   else fov_crop_kernel<TS, __nv_bfloat16><<<grid, threads, 0, s>>>(a);
   RF_LAUNCH_OK();
   return RF_OK;
@@ -131,7 +176,7 @@ extern "C" int rf_fov_crop(const RfFovCropParams* p, void* stream) {
   RF_CHECK_ARG(p->patch == 0 || (p->patch % 4 == 0 && p->out_size % p->patch == 0), "rf_fov_crop: patch=%d must divide out_size and be a multiple of 4",
                p->patch);
   RF_CHECK_ARG(p->patch == 0 || (p->out_ld >= 3ll * p->patch * p->patch && p->out_ld % 4 == 0), "rf_fov_crop: out_ld too small or not a multiple of 4");
-  RF_CHECK_ARG(p->out_dtype == RF_F32 || p->out_dtype == RF_BF16, "rf_fov_crop: out_dtype must be RF_F32 or RF_BF16");
+  RF_CHECK_ARG(p->out_dtype == RF_F32 || p->out_dtype == RF_BF16 || p->out_dtype == RF_F16, "rf_fov_crop: out_dtype must be RF_F32, RF_F16 or RF_BF16");
   RF_CHECK_ARG(p->n_frames <= 65535, "rf_fov_crop: at most 65535 frames per call");
   crop::Args a;
   a.frames = p->frames; a.frame_ids = p->frame_ids; a.n_frames = p->n_frames; a.H = p->H; a.W = p->W;

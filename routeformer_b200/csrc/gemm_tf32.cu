@@ -53,6 +53,7 @@ struct Args {
   const float* dact_aux; long long ld_aux; int dact;
   int accumulate;
   int kb_total, kb_per_split;
+  int f16;  // operands are fp16 (kind::f16, 64 elements per 128 B k-block row) instead of fp32 read as tf32
   int group_in, group_out, row_offset;
   int round_f16;
   int tma_store;  // 1: epilogue stages 128x32 chunks in (swizzled) smem and writes them with TMA bulk stores
@@ -133,6 +134,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
@@ -374,7 +383,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_arrive_expect_tx(&full_bar[s], T::STAGE_BYTES);
         uint8_t* sa = smem + s * T::STAGE_BYTES;
         uint8_t* sb = sa + A_BYTES;
-        const int k0 = (kb_begin + i) * BLOCK_K;
+        const int k0 = (kb_begin + i) * (a.f16 ? 2 * BLOCK_K : BLOCK_K);  // a 128 B row holds 32 fp32 or 64 fp16
         if (!a.a_mn) {
           tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
         } else {
@@ -392,7 +401,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) /*D fp32*/ | (2u << 7) /*A tf32*/ | (2u << 10) /*B tf32*/ |
+      // instruction descriptor: D fp32; A/B format tf32 (2) or f16 (0); major-ness; N >> 3; M >> 4
+      const uint32_t fmt = a.f16 ? 0u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) |
                              (static_cast<uint32_t>(a.a_mn) << 15) | (static_cast<uint32_t>(a.b_mn) << 16) |
                              (static_cast<uint32_t>(BLOCK_N >> 3) << 17) | (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
       for (int i = 0; i < nkb; ++i) {
@@ -409,7 +420,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                         : make_smem_desc(a_base + kk * UMMA_K * 4, 16, 1024, 2);
           const uint64_t bdesc = a.b_mn ? make_smem_desc(b_base + kk * 1024, GROUP_BYTES, 512, 1)
                                         : make_smem_desc(b_base + kk * UMMA_K * 4, 16, 1024, 2);
-          umma_tf32(tmem_base, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
+          // one MMA consumes 32 B of K per row either way: 8 tf32 or 16 fp16
+          if (a.f16) umma_f16(tmem_base, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
+          else umma_tf32(tmem_base, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
       }
@@ -754,7 +767,7 @@ static bool tf32_round_in_tma() {
 // fp32 tensor map of rank 2 or 3: dim0 = `inner` contiguous elements (box 32 = 128 B), dim1 = rows of pitch ld (box box_rows),
 // optional dim2 = groups of pitch ld2 (box box_groups).  `round_tf32`: TFLOAT32 type (operands are rounded RN on load).
 static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_rows, bool mn_major,
-                    bool round_tf32 = true, long long groups = 0, long long ld2 = 0, int box_groups = 0) {
+                    bool round_tf32 = true, long long groups = 0, long long ld2 = 0, int box_groups = 0, bool f16 = false) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -762,10 +775,13 @@ static int make_map(CUtensorMap* map, const float* base, long long inner, long l
   }
   const int rank = groups > 0 ? 3 : 2;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer), static_cast<cuuint64_t>(groups)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(ld2) * 4};
-  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_groups)};
+  const cuuint64_t esize = f16 ? 2 : 4;
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * esize, static_cast<cuuint64_t>(ld2) * esize};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / esize), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_groups)};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, (round_tf32 && tf32_round_in_tma()) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
+  const CUtensorMapDataType dtype = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                        : ((round_tf32 && tf32_round_in_tma()) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  CUresult r = fn(map, dtype, rank,
                   const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -782,10 +798,11 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
   using T = Tile<BLOCK_N>;
   CUtensorMap tmA, tmB;
   int rc;
-  if (!p->a_mn_major) rc = make_map(&tmA, p->A, p->K, p->M, p->lda, BLOCK_M, false);
+  const bool f16 = args.f16 != 0;
+  if (!p->a_mn_major) rc = make_map(&tmA, p->A, p->K, p->M, p->lda, BLOCK_M, false, true, 0, 0, 0, f16);
   else rc = make_map(&tmA, p->A, p->M, p->K, p->lda, 32, true);
   if (rc != RF_OK) return rc;
-  if (!p->b_mn_major) rc = make_map(&tmB, p->B, p->K, p->N, p->ldb, BLOCK_N, false);
+  if (!p->b_mn_major) rc = make_map(&tmB, p->B, p->K, p->N, p->ldb, BLOCK_N, false, true, 0, 0, 0, f16);
   else rc = make_map(&tmB, p->B, p->N, p->K, p->ldb, 32, true);
   if (rc != RF_OK) return rc;
   CUtensorMap tmC, tmP;
@@ -814,7 +831,7 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
   // Short reductions (<= 12 k-blocks per tile: the K=128/256/384 layers) are epilogue/latency-bound -> persistent kernel whose
   // loads run ahead across tiles.  Long reductions are L2-bandwidth-bound -> two co-resident tile-wise CTAs per SM keep more
   // bytes in flight (2 x 3 stages) and measured 25-35 % faster there (profiles/r1_microbench_gemm_*).
-  if (persistent && args.kb_per_split <= 12) {
+  if (persistent && args.kb_per_split <= 12 && !f16) {
     using PT = PTile<BLOCK_N>;
     static bool attr_p = false;
     if (!attr_p) {
@@ -872,8 +889,12 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   RF_CHECK_ARG(p != nullptr, "rf_gemm_tf32: null params");
   RF_CHECK_ARG(p->M > 0 && p->N > 0 && p->K > 0, "rf_gemm_tf32: empty problem M=%d N=%d K=%d", p->M, p->N, p->K);
   RF_CHECK_ARG(p->A && p->B && p->C, "rf_gemm_tf32: null operand");
-  RF_CHECK_ARG((p->lda % 4) == 0 && (p->ldb % 4) == 0, "rf_gemm_tf32: lda=%lld ldb=%lld must be multiples of 4 (TMA 16 B pitch)",
-               p->lda, p->ldb);
+  RF_CHECK_ARG(p->ab_dtype == RF_F32 || p->ab_dtype == RF_F16, "rf_gemm_tf32: ab_dtype must be RF_F32 or RF_F16");
+  const bool f16 = p->ab_dtype == RF_F16;
+  const int pitch_mult = f16 ? 8 : 4;
+  RF_CHECK_ARG((p->lda % pitch_mult) == 0 && (p->ldb % pitch_mult) == 0, "rf_gemm_tf32: lda=%lld ldb=%lld must be multiples of %d (TMA 16 B pitch)",
+               p->lda, p->ldb, pitch_mult);
+  RF_CHECK_ARG(!f16 || (!p->a_mn_major && !p->b_mn_major), "rf_gemm_tf32: fp16 operands must be K-major");
   RF_CHECK_ARG((reinterpret_cast<uintptr_t>(p->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->B) & 15) == 0,
                "rf_gemm_tf32: A/B must be 16-byte aligned");
   RF_CHECK_ARG(p->lda >= (p->a_mn_major ? p->M : p->K) && p->ldb >= (p->b_mn_major ? p->N : p->K) && p->ldc >= p->N,
@@ -881,7 +902,7 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   RF_CHECK_ARG(!p->rowadd || p->rowadd_period > 0, "rf_gemm_tf32: rowadd needs rowadd_period > 0");
   RF_CHECK_ARG(!p->dact || p->dact_aux, "rf_gemm_tf32: dact needs dact_aux");
   RF_CHECK_ARG(p->act != RF_ACT_GELU_SAVE_GRAD || p->preact, "rf_gemm_tf32: RF_ACT_GELU_SAVE_GRAD needs the preact buffer");
-  const int kb_total = ceil_div(p->K, gemm::BLOCK_K);
+  const int kb_total = ceil_div(p->K, f16 ? 2 * gemm::BLOCK_K : gemm::BLOCK_K);
   const bool plain = !p->bias && !p->rowadd && !p->residual && p->act == RF_ACT_NONE && !p->preact && !p->dact && !p->round_f16;
   int splits = p->split_k;
   const bool n64 = p->N <= 64;
@@ -902,7 +923,7 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   a.bias = p->bias; a.rowadd = p->rowadd; a.rowadd_period = p->rowadd_period; a.ld_rowadd = p->ld_rowadd;
   a.residual = p->residual; a.ld_res = p->ld_res; a.act = p->act; a.preact = p->preact; a.ld_pre = p->ld_pre;
   a.dact_aux = p->dact_aux; a.ld_aux = p->ld_aux; a.dact = p->dact; a.accumulate = p->accumulate;
-  a.kb_total = kb_total; a.kb_per_split = kb_per_split;
+  a.kb_total = kb_total; a.kb_per_split = kb_per_split; a.f16 = f16 ? 1 : 0;
   a.group_in = p->out_group_in; a.group_out = p->out_group_out; a.row_offset = p->out_row_offset;
   a.round_f16 = p->round_f16;
   static int tma_store_enabled = -1;

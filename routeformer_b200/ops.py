@@ -96,12 +96,19 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
          residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, preact: Optional[torch.Tensor] = None,
          dact_aux: Optional[torch.Tensor] = None, dact: int = ACT_NONE, accumulate: bool = False, split_k: int = 0,
          out_group=(0, 0, 0), round_f16: bool = False, M: Optional[int] = None) -> torch.Tensor:
-    """out[M,N] (+)= epilogue(A . B^T) on the tcgen05 TF32 kernel.  A, B, out are 2-D fp32 views.
+    """out[M,N] (+)= epilogue(A . B^T) on the tcgen05 kernel.  A, B are 2-D fp32 views (multiplied as TF32) or both fp16
+    (kind::f16, K-major only); out and the epilogue operands are fp32.
 
     a_mn=False: A is [M,K] memory; True: A is [K,M] memory (logical A^T).  Same for B with N.
     """
     lib = _lib.load()
-    _f32(A, "A"), _f32(B, "B"), _f32(out, "out")
+    f16 = A.dtype == torch.float16
+    if f16:
+        if B.dtype != torch.float16 or a_mn or b_mn:
+            raise TypeError("gemm: fp16 operands need both A and B in fp16, K-major")
+    else:
+        _f32(A, "A"), _f32(B, "B")
+    _f32(out, "out")
     if a_mn:
         K, Ma = A.shape
     else:
@@ -131,6 +138,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
     p.accumulate, p.split_k = int(accumulate), split_k
     p.out_group_in, p.out_group_out, p.out_row_offset = out_group
     p.round_f16 = int(round_f16)
+    p.ab_dtype = F16 if f16 else F32
     check(lib.rf_gemm_tf32(C.byref(p), _stream()), "rf_gemm_tf32")
     _count()
     return out

@@ -60,6 +60,33 @@ def test_gemm_epilogue_forward(ops):
         assert rel_err(out.cpu(), fn(pre_ref)) < 2e-3
 
 
+def test_gemm_fp16_operands(ops):
+    """kind::f16 path (fp16 A and B, fp32 accumulate): the patch-embedding GEMM under the reference's fp16 autocast."""
+    gen = g(4)
+    for (M, N, K) in [(300, 136, 200), (640, 1024, 3072), (130, 48, 192)]:
+        A = torch.randn(M, K, generator=gen).half()
+        B = (torch.randn(N, K, generator=gen) / math.sqrt(K)).half()
+        bias = torch.randn(N, generator=gen)
+        ref = (A.double() @ B.double().t()).float() + bias
+        out = torch.empty(M, N, device=DEV)
+        ops.gemm(A.to(DEV), B.to(DEV), out, bias=bias.to(DEV))
+        assert rel_err(out.cpu(), ref) < 1e-5  # exact products of fp16 values, fp32 accumulation
+    # row remap + fp16 rounding of the result, as encode_views uses it
+    n, K, N = 6, 192, 40
+    A = torch.randn(n * 8, K, generator=gen).half()
+    W = (torch.randn(N, K, generator=gen) / math.sqrt(K)).half()
+    buf = torch.full((n * 9, N), -1.0, device=DEV)
+    ops.gemm(A.to(DEV), W.to(DEV), buf, out_group=(8, 9, 0), round_f16=True)
+    ref = (A.float() @ W.float().t()).half().float().view(n, 8, N)
+    got = buf.cpu().view(n, 9, N)
+    assert rel_err(got[:, :8], ref) < 1e-3
+    assert torch.equal(got[:, 8], torch.full((n, N), -1.0))
+    with pytest.raises(TypeError):
+        ops.gemm(A.to(DEV), W.float().to(DEV), buf)
+    with pytest.raises(TypeError):
+        ops.gemm(A.to(DEV), W.to(DEV), buf, b_mn=True)
+
+
 def test_gemm_strided_rows_and_row_remap(ops):
     gen = g(2)
     n, K, N = 6, 96, 40
@@ -145,6 +172,9 @@ def test_fov_crop(ops, H, W, S, patch, dtype):
     bf = ops.fov_crop(frames.to(DEV), centers.to(DEV), windows.to(DEV), S, spec.mean, spec.std, patch=patch, frame_ids=ids.to(DEV),
                       out_dtype=torch.bfloat16)
     assert (bf.float().cpu() - ref).abs().max() < 3e-2
+    hf = ops.fov_crop(frames.to(DEV), centers.to(DEV), windows.to(DEV), S, spec.mean, spec.std, patch=patch, frame_ids=ids.to(DEV),
+                      out_dtype=torch.float16)
+    assert torch.equal(hf.cpu(), got.half())  # same values, rounded to fp16 (the A operand of the fp16 patch GEMM)
 
 
 # ------------------------------------------------------------------------------------------------ circular conv
