@@ -241,7 +241,8 @@ def run_ours(args):
             H, W = frames.shape[-2:]
             win = windows[0].tolist()
             src = 3 * min(H, win[1] * H + 2) * min(W, win[0] * W + 2) * frames.element_size()
-            return n * (src + 3 * S * S * 4)
+            out_t = k.get("out")
+            return n * (src + 3 * S * S * (out_t.element_size() if out_t is not None else 4))
 
         ops.gemm = timed(orig_gemm, "gemm", gemm_work)
         ops.fov_crop = timed(orig_crop, "fov_crop", crop_work)
