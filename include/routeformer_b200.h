@@ -165,6 +165,8 @@ typedef struct {
   int* top;                /* out [B,H,u] selected queries (unused for FULL) */
   float* measure;          /* optional out [B,H,Lq] (NULL to skip) */
   const int* forced_top;   /* optional in [B,H,u]: use this selection instead (test hook) */
+  float dropout_p;         /* RF_ATTN_FULL only: dropout on the softmax probabilities (cross_modal_transformer.py:63), 0 = off */
+  unsigned long long dropout_seed, dropout_offset; /* mask = rf_dropout's for a [B*H*Lq, Lk] tensor with the same seed / offset */
 } RfAttnParams;
 int rf_attention_fwd(const RfAttnParams* p, void* stream);
 typedef struct {
@@ -250,6 +252,12 @@ int rf_median_downsample(const float* x, float* y, int B, int S, int C, int targ
  * result[1] = reference "FDE" = Frobenius norm of the LAST batch element's [T,2] error;
  * per_sample (optional, [B,2]) = per-clip (ADE, FDE) as computed by full_comparison.py:667-674. */
 int rf_ade_fde(const float* pred, const float* truth, int B, int T, float* result, float* per_sample, void* stream);
+/* replaces: nn.Dropout in training mode (cross_modal_transformer.py:224-231,295-299): out = residual + keep * x / (1 - p), keep
+ * drawn per element from Philox4x32-10(seed; element index / 4, offset).  x, out: [M,N] with row pitches ldx / ldo (out may alias
+ * x); residual optional.  The same call with x = dy and residual = NULL is the backward pass (the mask is a function of
+ * seed / offset / logical element index only). */
+int rf_dropout(const float* x, long long ldx, const float* residual, long long ldr, float* out, long long ldo, int M, int N,
+               float p, unsigned long long seed, unsigned long long offset, void* stream);
 /* replaces: experiments/full_comparison.py:654-679 (_eval_step): mean of S stochastic forwards, then per clip the
  * FutureDiscountedLoss, ADE and "FDE" of the [1,T,2] slices.  preds [S,B,T,2] (sample-major), truth [B,T,2];
  * mean_pred (optional, [B,T,2]) = stack(preds).mean(0); per_clip [B,3] = (loss, ade, fde).  kind / gamma / epsilon as below. */

@@ -236,11 +236,36 @@ def prob_attention(
     return ctx, top, measure
 
 
-def full_attention(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
+# Training-mode feature dropout of the Perceive modules (nn.Dropout at cross_modal_transformer.py:63,224-231,295-299).  The masks
+# come from a caller-installed hook `fn(x, where) -> dropped x` (tests replay the CUDA path's Philox masks through it); without a
+# hook dropout is the identity, i.e. the parity configuration feature_dropout = 0.
+_DROPOUT_HOOK: Optional[Callable] = None
+
+
+class dropout_hook:
+    def __init__(self, fn: Optional[Callable]):
+        self.fn = fn
+
+    def __enter__(self):
+        global _DROPOUT_HOOK
+        self.prev, _DROPOUT_HOOK = _DROPOUT_HOOK, self.fn
+
+    def __exit__(self, *exc):
+        global _DROPOUT_HOOK
+        _DROPOUT_HOOK = self.prev
+
+
+def _drop(x: Tensor, where: str, perceive: bool = True) -> Tensor:
+    return _DROPOUT_HOOK(x, where) if (_DROPOUT_HOOK is not None and perceive) else x
+
+
+def full_attention(q: Tensor, k: Tensor, v: Tensor, where: Optional[str] = None) -> Tensor:
     """Unmasked softmax attention (cross_modal_transformer.py:51-69).  Returns [B,Lq,H,Dv]."""
     E = q.shape[-1]
     scores = torch.einsum("blhe,bshe->bhls", q, k)
     attn = torch.softmax(scores * (1.0 / math.sqrt(E)), dim=-1)
+    if where is not None:
+        attn = _drop(attn, where + ".prob")  # :63
     return torch.einsum("bhls,bshd->blhd", attn, v).contiguous()
 
 
@@ -281,7 +306,7 @@ def attention_layer(
     k = _lin(sd, p + ".key_projection", xkv).view(B, S, n_heads, -1)
     v = _lin(sd, p + ".value_projection", xkv).view(B, S, n_heads, -1)
     if kind == "full":
-        out = full_attention(q, k, v)
+        out = full_attention(q, k, v, None if informer_layout else p)
     else:
         idx = draw(S, L, sparse_budget(S, factor))
         forced = draw.next_top(p) if hasattr(draw, "next_top") else None
@@ -292,28 +317,32 @@ def attention_layer(
     return _lin(sd, p + ".out_projection", out.view(B, L, -1))
 
 
-def ffn(sd: SD, p: str, x: Tensor, act: str) -> Tensor:
-    """1x1 Conv1d -> act -> 1x1 Conv1d (cross_modal_transformer.py:297-299)."""
+def ffn(sd: SD, p: str, x: Tensor, act: str, perceive: bool = False) -> Tensor:
+    """1x1 Conv1d -> act -> dropout -> 1x1 Conv1d -> dropout (cross_modal_transformer.py:297-299)."""
     # same ATen ops as the reference (conv1d over the transposed tensor) so the pin is bit-exact;
     # mathematically h = act(x W1^T + b1), y = h W2^T + b2.
     h = _act(act, F.conv1d(x.transpose(-1, 1), sd[p + ".conv1.weight"], sd[p + ".conv1.bias"]))
-    return F.conv1d(h, sd[p + ".conv2.weight"], sd[p + ".conv2.bias"]).transpose(-1, 1)
+    h = _drop(h.transpose(-1, 1), p + ".ffn_hidden", perceive).transpose(-1, 1)
+    y = F.conv1d(h, sd[p + ".conv2.weight"], sd[p + ".conv2.bias"]).transpose(-1, 1)
+    return _drop(y, p + ".ffn_out", perceive)
 
 
 def encoder_layer(sd, p, x, n_heads, factor, act, draw, informer_layout, tops=None) -> Tensor:
     """Post-norm encoder block (cross_modal_transformer.py:288-301; TransformerEncoderDecoder.py:43-53)."""
+    perceive = not informer_layout
     a = attention_layer(sd, p + ".attention", x, x, n_heads, "prob", factor, draw, informer_layout, tops)
-    x = _ln(sd, p + ".norm1", x + a)
-    return _ln(sd, p + ".norm2", x + ffn(sd, p, x, act))
+    x = _ln(sd, p + ".norm1", x + _drop(a, p + ".attention.out", perceive))
+    return _ln(sd, p + ".norm2", x + ffn(sd, p, x, act, perceive))
 
 
 def decoder_layer(sd, p, x, cross, n_heads, factor, act, draw, informer_layout, cross_kind, tops=None) -> Tensor:
     """Decoder block (cross_modal_transformer.py:223-233; TransformerEncoderDecoder.py:104-116)."""
+    perceive = not informer_layout
     a = attention_layer(sd, p + ".self_attention", x, x, n_heads, "prob_masked", factor, draw, informer_layout, tops)
-    x = _ln(sd, p + ".norm1", x + a)
+    x = _ln(sd, p + ".norm1", x + _drop(a, p + ".self_attention.out", perceive))
     c = attention_layer(sd, p + ".cross_attention", x, cross, n_heads, cross_kind, factor, draw, informer_layout, tops)
-    x = _ln(sd, p + ".norm2", x + c)
-    return _ln(sd, p + ".norm3", x + ffn(sd, p, x, act))
+    x = _ln(sd, p + ".norm2", x + _drop(c, p + ".cross_attention.out", perceive))
+    return _ln(sd, p + ".norm3", x + ffn(sd, p, x, act, perceive))
 
 
 # --------------------------------------------------------------------------------------

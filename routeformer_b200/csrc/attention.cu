@@ -277,6 +277,13 @@ __global__ void __launch_bounds__(THREADS) attention_fwd_kernel(const RfAttnPara
   select_and_softmax(p, d, sm, b, u, true, p.forced_top ? p.forced_top + bh * u : nullptr, p.measure ? p.measure + bh * Lq : nullptr);
   if (p.mode != RF_ATTN_FULL && p.top)
     for (int r = threadIdx.x; r < u; r += THREADS) p.top[bh * u + r] = sm.top[r];
+  if (p.mode == RF_ATTN_FULL && p.dropout_p > 0.f) {  // dropout on the probabilities (cross_modal_transformer.py:63)
+    const uint32_t thr = dropout_threshold(p.dropout_p);
+    const float keep_scale = 1.f / (1.f - p.dropout_p);
+    const unsigned long long base = static_cast<unsigned long long>(bh) * Lq * Lk;
+    for (int i = threadIdx.x; i < Lq * Lk; i += THREADS) sm.s[i] *= dropout_factor(p.dropout_seed, p.dropout_offset, base + i, thr, keep_scale);
+    __syncthreads();
+  }
 
   // selected queries: context[top_r] = P[r] . V, one thread per (r, 4 channels)
   for (int i = threadIdx.x; i < u * dh4; i += THREADS) {
@@ -337,6 +344,11 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
   const long long bh = static_cast<long long>(b) * p.H + h;
   select_and_softmax(p, d, sm, b, u, false, p.mode == RF_ATTN_FULL ? nullptr : p.top + bh * u, nullptr);
 
+  // probability dropout (full attention only): P' = P o mask / (1-p) was used for the context, so dP = dP' o mask / (1-p)
+  const bool drop = p.mode == RF_ATTN_FULL && p.dropout_p > 0.f;
+  const uint32_t drop_thr = dropout_threshold(p.dropout_p);
+  const float drop_scale = 1.f / (1.f - p.dropout_p);
+  const unsigned long long drop_base = static_cast<unsigned long long>(bh) * Lq * Lk;
   // dP -> dS, one warp per selected query (row sums by shuffle)
   const float scale = rsqrtf(static_cast<float>(dh));
   for (int r = warp; r < u; r += NWARPS) {
@@ -350,6 +362,7 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
       float v = 0.f;
       if (j < Lk) {
         v = dot4(d, dorow, sm.v + j * pitch);
+        if (drop) v *= dropout_factor(p.dropout_seed, p.dropout_offset, drop_base + static_cast<unsigned long long>(r) * Lk + j, drop_thr, drop_scale);
         acc = fmaf(sm.s[r * Lk + j], v, acc);
       }
       dp[t] = v;
@@ -390,7 +403,9 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
     for (int r = 0; r < u; ++r) {
       const int qi = sm.top[r];
       acck.fma(s_ds[r * Lk + j], sm.q + qi * pitch + 4 * c);
-      accv.fma(sm.s[r * Lk + j], s_do + qi * pitch + 4 * c);
+      float wp = sm.s[r * Lk + j];
+      if (drop) wp *= dropout_factor(p.dropout_seed, p.dropout_offset, drop_base + static_cast<unsigned long long>(r) * Lk + j, drop_thr, drop_scale);
+      accv.fma(wp, s_do + qi * pitch + 4 * c);
     }
     float4 ak = acck.get(), av = accv.get();
     if (p.mode == RF_ATTN_PROB) {
@@ -904,6 +919,9 @@ static int validate(const RfAttnParams* p, const char* who, bool forward) {
     RF_CHECK_ARG(p->top, "%s: top buffer missing", who);
   }
   RF_CHECK_ARG(p->mode != RF_ATTN_PROB_MASKED || p->Lq == p->Lk, "%s: masked ProbSparse attention requires Lq == Lk", who);
+  RF_CHECK_ARG(p->dropout_p >= 0.f && p->dropout_p < 1.f, "%s: dropout_p=%f must be in [0, 1)", who, p->dropout_p);
+  RF_CHECK_ARG(p->dropout_p == 0.f || p->mode == RF_ATTN_FULL, "%s: probability dropout exists for full attention only (the reference's "
+               "ProbAttention never applies its dropout)", who);
   RF_CHECK_ARG(static_cast<long long>(p->B) * p->H <= 2147483647LL, "%s: too many problems", who);
   return RF_OK;
 }

@@ -98,4 +98,33 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {  // Phi(x) + x phi(x)
   return 0.5f * (1.0f + erf_as(z, e)) + x * 0.39894228040143267794f * e;
 }
 
+// ---- counter-based RNG for dropout: Philox4x32-10 keyed by `seed`, counter = (index of a 4-element group, call offset).
+// Stateless, so the backward pass regenerates the forward mask from (seed, offset) instead of storing it.
+__device__ __forceinline__ uint4 philox4x32_10(unsigned long long seed, unsigned long long group, unsigned long long offset) {
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  uint32_t c0 = static_cast<uint32_t>(group), c1 = static_cast<uint32_t>(group >> 32);
+  uint32_t c2 = static_cast<uint32_t>(offset), c3 = static_cast<uint32_t>(offset >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// keep-factor (0 or 1/(1-p)) of logical element `index` of the tensor a dropout call covers
+__device__ __forceinline__ float dropout_factor(unsigned long long seed, unsigned long long offset, unsigned long long index,
+                                                uint32_t threshold, float scale) {
+  const uint4 r = philox4x32_10(seed, index >> 2, offset);
+  const uint32_t lane = static_cast<uint32_t>(index & 3);
+  const uint32_t v = lane == 0 ? r.x : (lane == 1 ? r.y : (lane == 2 ? r.z : r.w));
+  return v >= threshold ? scale : 0.0f;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {  // P(u32 < threshold) = p
+  const double t = static_cast<double>(p) * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+}
+
 }  // namespace rf

@@ -624,6 +624,40 @@ extern "C" int rf_ade_fde(const float* pred, const float* truth, int B, int T, f
   return RF_OK;
 }
 
+__global__ void dropout_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ residual, long long ldr,
+                               float* __restrict__ out, long long ldo, int M, int N, uint32_t threshold, float scale,
+                               unsigned long long seed, unsigned long long offset) {
+  // one thread per group of 4 consecutive LOGICAL elements (row-major over [M,N]): one Philox call, 4 keep decisions
+  const long long total = static_cast<long long>(M) * N;
+  const long long groups = (total + 3) >> 2;
+  for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < groups; g += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 r = philox4x32_10(seed, static_cast<unsigned long long>(g), offset);
+    const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long e = 4 * g + i;
+      if (e < total) {
+        const long long row = e / N;
+        const int col = static_cast<int>(e - row * N);
+        float v = rv[i] >= threshold ? x[row * ldx + col] * scale : 0.0f;
+        if (residual) v += residual[row * ldr + col];
+        out[row * ldo + col] = v;
+      }
+    }
+  }
+}
+
+extern "C" int rf_dropout(const float* x, long long ldx, const float* residual, long long ldr, float* out, long long ldo, int M, int N, float p,
+                          unsigned long long seed, unsigned long long offset, void* stream) {
+  RF_CHECK_ARG(x && out && M > 0 && N > 0 && ldx >= N && ldo >= N, "rf_dropout: bad arguments");
+  RF_CHECK_ARG(p >= 0.0f && p < 1.0f, "rf_dropout: p=%f must be in [0, 1)", p);
+  const long long groups = (static_cast<long long>(M) * N + 3) / 4;
+  dropout_kernel<<<blocks_for(groups, TPB, 148 * 16), TPB, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ldx, residual, ldr, out, ldo, M, N, dropout_threshold(p), 1.0f / (1.0f - p), seed, offset);
+  RF_LAUNCH_OK();
+  return RF_OK;
+}
+
 extern "C" int rf_eval_samples(const float* preds, const float* truth, int S, int B, int T, float gamma, float epsilon, int kind,
                                float* mean_pred, float* per_clip, void* stream) {
   RF_CHECK_ARG(preds && truth && per_clip && S > 0 && B > 0 && T > 0 && kind >= 0 && kind <= 2, "rf_eval_samples: bad arguments");

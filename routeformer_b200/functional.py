@@ -100,12 +100,18 @@ class AttentionBlock(Function):
         u = meta["u"]
         top = torch.empty(B, H, max(u, 1), device=dev, dtype=torch.int32) if meta["mode"] != ops.ATTN_FULL else None
         measure = torch.empty(B, H, Lq, device=dev, dtype=torch.float32) if meta.get("record") is not None and top is not None else None
+        drop = meta.get("drop")  # training-mode feature dropout: {"p", "out": (seed, off), "prob": (seed, off) | None}
         ops.attention_fwd(q, k, v, B, H, Lq, Lk, dh, meta["mode"], meta["layout"], idx, meta["idx_group"], meta["U"], u, context, top,
-                          measure=measure, forced_top=meta.get("forced_top"))
+                          measure=measure, forced_top=meta.get("forced_top"),
+                          dropout=(drop["p"], *drop["prob"]) if drop and drop.get("prob") else None)
         if meta.get("record") is not None and top is not None:
             meta["record"].append({"where": meta.get("name", ""), "top": top, "measure": measure})
         y = torch.empty(M, D, device=dev, dtype=torch.float32)
-        ops.gemm(context, wo, y, bias=bo, residual=x)
+        if drop:  # x + dropout(out_projection(context))   (cross_modal_transformer.py:224,227,295)
+            ops.gemm(context, wo, y, bias=bo)
+            ops.dropout(y, y, drop["p"], *drop["out"], residual=x)
+        else:
+            ops.gemm(context, wo, y, bias=bo, residual=x)
         ctx.meta = meta
         ctx.params = (wq, bq, wk, bk, wv, bv, wo, bo)
         ctx.self_attn = self_attn
@@ -123,14 +129,19 @@ class AttentionBlock(Function):
         M = x.shape[0]
         dev = x.device
         dy = dy.contiguous()
+        drop = meta.get("drop")
+        dproj = dy  # gradient of the out-projection output; dy itself stays the gradient of the residual branch
+        if drop:
+            dproj = ops.dropout(dy, torch.empty_like(dy), drop["p"], *drop["out"])
+        attn_drop = (drop["p"], *drop["prob"]) if drop and drop.get("prob") else None
         g = grad_buffer(wo)
         if g is not None:
-            ops.gemm(dy, context, g, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(dproj, context, g, a_mn=True, b_mn=True, accumulate=True)
         g = grad_buffer(bo)
         if g is not None:
-            ops.colsum_accumulate(dy, g)
+            ops.colsum_accumulate(dproj, g)
         dcontext = torch.empty(M, D, device=dev, dtype=torch.float32)
-        ops.gemm(dy, wo, dcontext, b_mn=True)
+        ops.gemm(dproj, wo, dcontext, b_mn=True)
         need_dx = ctx.needs_input_grad[0]
         dx = dcross = None
         if ctx.self_attn:
@@ -140,7 +151,7 @@ class AttentionBlock(Function):
             k = (qkv[:, D:], Lk * 3 * D, 3 * D)
             v = (qkv[:, 2 * D:], Lk * 3 * D, 3 * D)
             ops.attention_bwd(q, k, v, B, H, Lq, Lk, dh, meta["mode"], meta["layout"], meta["U"], meta["u"], top, dcontext,
-                              dqkv, dqkv[:, D:], dqkv[:, 2 * D:])
+                              dqkv, dqkv[:, D:], dqkv[:, 2 * D:], dropout=attn_drop)
             w_all = _fused(wq, wk, wv)
             gw_all, gb_all = _fused_grads(wq, wk, wv), _fused_grads(bq, bk, bv)
             if gw_all is not None:
@@ -172,7 +183,7 @@ class AttentionBlock(Function):
             k = (kvb, Lk * 2 * D, 2 * D)
             v = (kvb[:, D:], Lk * 2 * D, 2 * D)
             ops.attention_bwd(q, k, v, B, H, Lq, Lk, dh, meta["mode"], meta["layout"], meta["U"], meta["u"], top, dcontext,
-                              dq, dkv, dkv[:, D:])
+                              dq, dkv, dkv[:, D:], dropout=attn_drop)
             g = grad_buffer(wq)
             if g is not None:
                 ops.gemm(dq, x, g, a_mn=True, b_mn=True, accumulate=True)
@@ -212,7 +223,8 @@ class FFNBlock(Function):
     """y = x + W2 act(W1 x + b1) + b2   (1x1 Conv1d pair; cross_modal_transformer.py:296-301, TransformerEncoderDecoder.py:48-52)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, act):
+    def forward(ctx, x, w1, b1, w2, b2, act, drop=None):
+        """drop = {"p", "hidden": (seed, off), "out": (seed, off)}: y = x + dropout(W2 dropout(act(W1 x + b1)) + b2)."""
         M, D = x.shape
         dff = w1.shape[0]
         w1m, w2m = w1.view(dff, D), w2.view(D, dff)
@@ -221,7 +233,13 @@ class FFNBlock(Function):
         pre = torch.empty(M, dff, device=x.device, dtype=torch.float32) if act == ops.ACT_GELU else None
         ops.gemm(x, w1m, h, bias=b1, act=ops.ACT_GELU_SAVE_GRAD if act == ops.ACT_GELU else act, preact=pre)
         y = torch.empty(M, D, device=x.device, dtype=torch.float32)
-        ops.gemm(h, w2m, y, bias=b2, residual=x)
+        if drop:
+            ops.dropout(h, h, drop["p"], *drop["hidden"])  # in place: the backward needs the dropped activations for dW2
+            ops.gemm(h, w2m, y, bias=b2)
+            ops.dropout(y, y, drop["p"], *drop["out"], residual=x)
+        else:
+            ops.gemm(h, w2m, y, bias=b2, residual=x)
+        ctx.drop = drop
         ctx.act = act
         ctx.params = (w1, b1, w2, b2)
         ctx.save_for_backward(x, h, pre)
@@ -234,17 +252,25 @@ class FFNBlock(Function):
         M, D = x.shape
         dff = w1.shape[0]
         dy = dy.contiguous()
+        drop = ctx.drop
+        dt = dy  # gradient of the conv2 output; dy itself stays the gradient of the residual branch
+        if drop:
+            dt = ops.dropout(dy, torch.empty_like(dy), drop["p"], *drop["out"])
         g = grad_buffer(w2)
         if g is not None:
-            ops.gemm(dy, h, g.view(D, dff), a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(dt, h, g.view(D, dff), a_mn=True, b_mn=True, accumulate=True)
         g = grad_buffer(b2)
         if g is not None:
-            ops.colsum_accumulate(dy, g)
+            ops.colsum_accumulate(dt, g)
         dpre = torch.empty(M, dff, device=x.device, dtype=torch.float32)
         if ctx.act == ops.ACT_GELU:
-            ops.gemm(dy, w2.view(D, dff), dpre, b_mn=True, dact=ops.DACT_SAVED, dact_aux=pre)
+            ops.gemm(dt, w2.view(D, dff), dpre, b_mn=True, dact=ops.DACT_SAVED, dact_aux=pre)
         else:
-            ops.gemm(dy, w2.view(D, dff), dpre, b_mn=True, dact=ctx.act, dact_aux=h)  # relu'(pre) = [h > 0]
+            # relu'(pre) = [h > 0]; with dropout h holds the DROPPED activations: a dropped unit reads as inactive, and its
+            # gradient is zeroed by the mask below anyway
+            ops.gemm(dt, w2.view(D, dff), dpre, b_mn=True, dact=ctx.act, dact_aux=h)
+        if drop:
+            ops.dropout(dpre, dpre, drop["p"], *drop["hidden"])
         g = grad_buffer(w1)
         if g is not None:
             ops.gemm(dpre, x, g.view(dff, D), a_mn=True, b_mn=True, accumulate=True)
@@ -255,7 +281,7 @@ class FFNBlock(Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, D, device=x.device, dtype=torch.float32)
             ops.gemm(dpre, w1.view(dff, D), dx, b_mn=True, residual=dy)
-        return dx, None, None, None, None, None
+        return dx, None, None, None, None, None, None
 
 
 class LayerNorm(Function):

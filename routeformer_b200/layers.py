@@ -73,8 +73,13 @@ class PlannedIndexSource:
 def _no_dropout(module: nn.Module, p: float):
     if p > 0.0 and module.training:
         raise NotImplementedError(
-            "feature dropout > 0 in training mode is not implemented in the CUDA path yet "
-            "(set feature_dropout=0; the reference's parity configuration does the same, SURVEY 7 hard part 3)")
+            "dropout > 0 in training mode is implemented for the Perceive encoder / decoder (feature_dropout) only; the Informer of "
+            "the Routeformer path is configured with dropout = 0.0 (full_comparison.py:171)")
+
+
+def _site(device, p: float, where: str, rows: int, cols: int):
+    """One dropout call site of this step: (seed, offset) of its Philox sub-stream."""
+    return ops.DropoutStream.next(device, where, rows, cols)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -122,7 +127,9 @@ class AttentionLayer(nn.Module):
         self.n_heads = n_heads
         self.informer_layout = informer_layout
 
-    def block(self, x2, cross2, B, Lq, Lk, draw, record=None, name=""):
+    def block(self, x2, cross2, B, Lq, Lk, draw, record=None, name="", p_drop: float = 0.0):
+        """p_drop > 0 (training): `x + dropout(attention(x))` of the calling layer and, for full attention, the dropout on the
+        softmax probabilities (cross_modal_transformer.py:63,224,227,295)."""
         kind, factor = self.inner_attention.kind, self.inner_attention.factor
         mode = {"prob": ops.ATTN_PROB, "prob_masked": ops.ATTN_PROB_MASKED, "full": ops.ATTN_FULL}[kind]
         meta = dict(B=B, H=self.n_heads, Lq=Lq, Lk=Lk, mode=mode,
@@ -133,6 +140,10 @@ class AttentionLayer(nn.Module):
             meta["U"], meta["u"] = sparse_budget(Lk, factor), sparse_budget(Lq, factor)
             idx, meta["idx_group"] = draw.take(Lk, Lq, meta["U"])
             meta["forced_top"] = draw.forced_top()
+        if p_drop > 0.0:
+            dev, D = x2.device, self.out_projection.weight.shape[0]
+            prob = _site(dev, p_drop, name + ".prob", B * self.n_heads * Lq, Lk) if kind == "full" else None
+            meta["drop"] = {"p": p_drop, "prob": prob, "out": _site(dev, p_drop, name + ".out", x2.shape[0], D)}
         q, k, v, o = self.query_projection, self.key_projection, self.value_projection, self.out_projection
         return Fn.AttentionBlock.apply(x2, cross2, q.weight, q.bias, k.weight, k.bias, v.weight, v.bias, o.weight, o.bias, idx, meta)
 
@@ -149,11 +160,20 @@ class EncoderLayer(nn.Module):
         self.p_drop = dropout
         self.act = ops.ACT_RELU if activation == "relu" else ops.ACT_GELU
 
+    def _ffn_drop(self, x2, name):
+        if not (self.training and self.p_drop > 0.0):
+            return None
+        M, dff, D = x2.shape[0], self.conv1.weight.shape[0], self.conv2.weight.shape[0]
+        return {"p": self.p_drop, "hidden": _site(x2.device, self.p_drop, name + ".ffn_hidden", M, dff),
+                "out": _site(x2.device, self.p_drop, name + ".ffn_out", M, D)}
+
     def run(self, x2, B, L, draw, record=None, name=""):
-        _no_dropout(self, self.p_drop)
-        x2 = self.attention.block(x2, None, B, L, L, draw, record, name + ".attention")
+        if self.attention.informer_layout:
+            _no_dropout(self, self.p_drop)
+        p = self.p_drop if self.training else 0.0
+        x2 = self.attention.block(x2, None, B, L, L, draw, record, name + ".attention", p)
         x2 = Fn.LayerNorm.apply(x2, self.norm1.weight, self.norm1.bias)
-        x2 = Fn.FFNBlock.apply(x2, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.act)
+        x2 = Fn.FFNBlock.apply(x2, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.act, self._ffn_drop(x2, name))
         return Fn.LayerNorm.apply(x2, self.norm2.weight, self.norm2.bias)
 
 
@@ -172,13 +192,17 @@ class DecoderLayer(nn.Module):
         self.p_drop = dropout
         self.act = ops.ACT_RELU if activation == "relu" else ops.ACT_GELU
 
+    _ffn_drop = EncoderLayer._ffn_drop
+
     def run(self, x2, cross2, B, L, S, draw, record=None, name=""):
-        _no_dropout(self, self.p_drop)
-        x2 = self.self_attention.block(x2, None, B, L, L, draw, record, name + ".self_attention")
+        if self.self_attention.informer_layout:
+            _no_dropout(self, self.p_drop)
+        p = self.p_drop if self.training else 0.0
+        x2 = self.self_attention.block(x2, None, B, L, L, draw, record, name + ".self_attention", p)
         x2 = Fn.LayerNorm.apply(x2, self.norm1.weight, self.norm1.bias)
-        x2 = self.cross_attention.block(x2, cross2, B, L, S, draw, record, name + ".cross_attention")
+        x2 = self.cross_attention.block(x2, cross2, B, L, S, draw, record, name + ".cross_attention", p)
         x2 = Fn.LayerNorm.apply(x2, self.norm2.weight, self.norm2.bias)
-        x2 = Fn.FFNBlock.apply(x2, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.act)
+        x2 = Fn.FFNBlock.apply(x2, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.act, self._ffn_drop(x2, name))
         return Fn.LayerNorm.apply(x2, self.norm3.weight, self.norm3.bias)
 
 

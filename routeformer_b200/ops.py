@@ -194,19 +194,54 @@ def _attn_params(q, k, v, B, H, Lq, Lk, dh, mode, layout, idx, idx_group, U, u, 
     return p
 
 
-def attention_fwd(q, k, v, B, H, Lq, Lk, dh, mode, layout, idx, idx_group, U, u, out, top, measure=None, forced_top=None):
+def _set_attn_dropout(p, dropout):
+    if dropout is not None and dropout[0] > 0.0:
+        p.dropout_p, p.dropout_seed, p.dropout_offset = float(dropout[0]), int(dropout[1]), int(dropout[2])
+
+
+def attention_fwd(q, k, v, B, H, Lq, Lk, dh, mode, layout, idx, idx_group, U, u, out, top, measure=None, forced_top=None, dropout=None):
+    """dropout = (p, seed, offset): probability dropout, full attention only."""
     p = _attn_params(q, k, v, B, H, Lq, Lk, dh, mode, layout, idx, idx_group, U, u, out, top, measure, forced_top)
+    _set_attn_dropout(p, dropout)
     check(_lib.load().rf_attention_fwd(C.byref(p), _stream()), "rf_attention_fwd")
     _count()
     return out
 
 
-def attention_bwd(q, k, v, B, H, Lq, Lk, dh, mode, layout, U, u, top, dout, dq, dk, dv):
+def attention_bwd(q, k, v, B, H, Lq, Lk, dh, mode, layout, U, u, top, dout, dq, dk, dv, dropout=None):
     bp = _lib.RfAttnBwdParams()
     bp.f = _attn_params(q, k, v, B, H, Lq, Lk, dh, mode, layout, None, 0, U, u, None, top, None, None)
+    _set_attn_dropout(bp.f, dropout)
     bp.dout, bp.dq, bp.dk, bp.dv = _ptr(dout), _ptr(dq), _ptr(dk), _ptr(dv)
     check(_lib.load().rf_attention_bwd(C.byref(bp), _stream()), "rf_attention_bwd")
     _count()
+
+
+def dropout(x: torch.Tensor, out: torch.Tensor, p: float, seed: int, offset: int, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = residual + keep * x / (1 - p) over a 2-D fp32 view (out may alias x).  The mask is a pure function of (seed, offset,
+    logical element index): calling it again on a gradient is the backward pass."""
+    M, N = x.shape
+    _f32(x, "x"), _f32(out, "out")
+    check(_lib.load().rf_dropout(_ptr(x), _row_pitch(x, "x"), _ptr(residual), _row_pitch(residual, "residual") if residual is not None else 0,
+                                 _ptr(out), _row_pitch(out, "out"), M, N, float(p), int(seed), int(offset), _stream()), "rf_dropout")
+    _count()
+    return out
+
+
+class DropoutStream:
+    """Hands out (seed, offset) pairs for dropout call sites.  seed = the CUDA generator's seed (torch.manual_seed sets it without
+    touching the CPU stream that feeds the ProbSparse index draws); offset = a process-wide call counter, so every site of every
+    step gets its own Philox sub-stream."""
+    counter = 0
+    log = None  # tests: list that receives (where, seed, offset, rows, cols)
+
+    @classmethod
+    def next(cls, device, where: str = "", rows: int = 0, cols: int = 0):
+        seed = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()].initial_seed()
+        cls.counter += 1
+        if cls.log is not None:
+            cls.log.append((where, seed, cls.counter, rows, cols))
+        return seed, cls.counter
 
 
 def layernorm_fwd(x, gamma, beta, y, mean, rstd):

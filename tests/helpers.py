@@ -126,3 +126,41 @@ def condition_weights(sd):
             v = v * 0.3
         out[k] = v
     return out
+
+
+class ReplayDropout:
+    """Oracle dropout hook that replays the CUDA path's Philox masks (oracle.dropout_hook).
+
+    `log` = routeformer_b200.ops.DropoutStream.log of the product run: (where, seed, offset, rows, cols) per call site, in call
+    order.  The product encodes all camera views in one batched frame-encoder pass, the oracle one view at a time: a product
+    record with k times the oracle's rows is consumed by k consecutive oracle calls of that site."""
+
+    def __init__(self, log, p: float, device="cuda"):
+        self.p, self.device = p, device
+        self.sites = {}
+        for where, seed, offset, rows, cols in log:
+            self.sites.setdefault(where, []).append([seed, offset, rows, cols, None, 0])
+        self.used = 0
+
+    def __call__(self, x, where):
+        import torch
+
+        from routeformer_b200 import ops
+
+        rec = self.sites[where][0]
+        seed, offset, rows, cols, mask, taken = rec
+        if mask is None:
+            ones = torch.ones(rows, cols, device=self.device)
+            mask = rec[4] = ops.dropout(ones, torch.empty_like(ones), self.p, seed, offset).cpu()
+        assert x.shape[-1] == cols, (where, tuple(x.shape), rows, cols)
+        n = x.numel() // cols
+        out = x * mask[taken:taken + n].reshape(x.shape)
+        rec[5] = taken + n
+        assert rec[5] <= rows, where
+        if rec[5] == rows:
+            self.sites[where].pop(0)
+        self.used += 1
+        return out
+
+    def exhausted(self) -> bool:
+        return all(len(v) == 0 for v in self.sites.values())

@@ -324,6 +324,64 @@ def test_reductions_eval_samples(ops):
             assert torch.allclose(per_clip[i].cpu(), ref, rtol=2e-5, atol=1e-6), (kind, i)
 
 
+def test_reductions_dropout(ops):
+    """rf_dropout: Philox mask as a pure function of (seed, offset, logical index); out = residual + keep * x / (1 - p)."""
+    gen = g(91)
+    M, N, p = 517, 130, 0.3
+    x = torch.randn(M, N, generator=gen).to(DEV)
+    res = torch.randn(M, N, generator=gen).to(DEV)
+    y = ops.dropout(x, torch.empty_like(x), p, 1234, 7)
+    keep = (y != 0)
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.01
+    assert torch.allclose(y[keep], x[keep] / (1 - p), rtol=1e-6)
+    assert torch.equal(ops.dropout(x, torch.empty_like(x), p, 1234, 7), y)                     # deterministic
+    assert not torch.equal(ops.dropout(x, torch.empty_like(x), p, 1234, 8) != 0, keep)         # another call site
+    assert not torch.equal(ops.dropout(x, torch.empty_like(x), p, 1235, 7) != 0, keep)         # another seed
+    wide = torch.zeros(M, N + 6, device=DEV)
+    wide[:, :N] = x
+    assert torch.equal(ops.dropout(wide[:, :N], torch.empty_like(x), p, 1234, 7), y)           # independent of the pitch
+    assert torch.allclose(ops.dropout(x, torch.empty_like(x), p, 1234, 7, residual=res), y + res)
+    z = x.clone()
+    ops.dropout(z, z, p, 1234, 7)                                                              # in place
+    assert torch.equal(z, y)
+    assert torch.equal(ops.dropout(x, torch.empty_like(x), 0.0, 1, 1), x)
+    # the backward pass is the same call on the gradient
+    dy = torch.randn(M, N, generator=gen).to(DEV)
+    assert torch.allclose(ops.dropout(dy, torch.empty_like(dy), p, 1234, 7), dy * keep / (1 - p), rtol=1e-6)
+
+
+def test_attention_full_probability_dropout(ops):
+    """Full attention with dropout on the softmax probabilities (cross_modal_transformer.py:63), forward and backward, against
+    autograd with the same mask (= rf_dropout's mask of a [B*H*Lq, Lk] tensor)."""
+    gen = g(92)
+    B, H, Lq, Lk, dh, p, seed, off = 3, 8, 40, 30, 8, 0.25, 99, 5
+    D = H * dh
+    q = torch.randn(B, Lq, H, dh, generator=gen, requires_grad=True)
+    k = torch.randn(B, Lk, H, dh, generator=gen, requires_grad=True)
+    v = torch.randn(B, Lk, H, dh, generator=gen, requires_grad=True)
+    ones = torch.ones(B * H * Lq, Lk, device=DEV)
+    mask = ops.dropout(ones, torch.empty_like(ones), p, seed, off).cpu().view(B, H, Lq, Lk)
+    attn = torch.softmax(torch.einsum("blhe,bshe->bhls", q, k) / math.sqrt(dh), dim=-1) * mask
+    ref = torch.einsum("bhls,bshd->blhd", attn, v)
+    dout = torch.randn(ref.shape, generator=gen)
+    ref.backward(dout)
+    mk = lambda t, L: (t.detach().reshape(B * L, D).to(DEV), L * D, D)
+    out = torch.empty(B, Lq, H, dh, device=DEV)
+    ops.attention_fwd(mk(q, Lq), mk(k, Lk), mk(v, Lk), B, H, Lq, Lk, dh, ops.ATTN_FULL, ops.LAYOUT_BLHD, None, 0, 0, 0, out, None,
+                      dropout=(p, seed, off))
+    assert rel_err(out.cpu(), ref.detach()) < 1e-5
+    dq, dk, dv = (torch.empty(B * L, D, device=DEV) for L in (Lq, Lk, Lk))
+    ops.attention_bwd(mk(q, Lq), mk(k, Lk), mk(v, Lk), B, H, Lq, Lk, dh, ops.ATTN_FULL, ops.LAYOUT_BLHD, 0, 0, None, dout.to(DEV),
+                      dq, dk, dv, dropout=(p, seed, off))
+    assert rel_err(dq.cpu().view(B, Lq, H, dh), q.grad) < 2e-5
+    assert rel_err(dk.cpu().view(B, Lk, H, dh), k.grad) < 2e-5
+    assert rel_err(dv.cpu().view(B, Lk, H, dh), v.grad) < 2e-5
+    with pytest.raises(RuntimeError):  # ProbSparse attention has no probability dropout in the reference
+        ops.attention_fwd(mk(q, Lq), mk(q, Lq), mk(q, Lq), B, H, Lq, Lq, dh, ops.ATTN_PROB, ops.LAYOUT_BLHD,
+                          torch.zeros(Lq, 20, dtype=torch.int32, device=DEV), 0, 20, 20, out, torch.zeros(B, H, 20, dtype=torch.int32, device=DEV),
+                          dropout=(p, seed, off))
+
+
 # ------------------------------------------------------------------------------------------------ norms
 @pytest.mark.parametrize("M,D", [(1000, 128), (77, 64), (300, 832), (33, 30)])
 def test_layernorm(ops, M, D):

@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from oracle import routeformer_oracle as O
-from tests.helpers import (ReplayDraw, build_product, case_from_golden, load_golden, rel_err, selection_violations, targets_for,
+from tests.helpers import (ReplayDraw, ReplayDropout, build_product, case_from_golden, load_golden, rel_err, selection_violations, targets_for,
                            to_device, tops_for_oracle)
 
 pytestmark = pytest.mark.gpu
@@ -302,3 +302,64 @@ def test_eval_step_caller():
     t = batch["target"]["gps"]
     ref_ade = torch.stack([O.ade(mean[i:i + 1], t[i:i + 1]) for i in range(mean.shape[0])])
     assert torch.allclose(ades.cpu(), ref_ade, rtol=2e-5)
+
+
+def test_training_step_with_feature_dropout():
+    """Training-mode feature dropout of the Perceive modules (paper config: 0.05; here 0.2 so that it matters): the oracle replays
+    the CUDA path's Philox masks and top-u selections, so loss and predictions must agree at TF32 level; eval mode is unaffected."""
+    import routeformer_b200 as R
+    from routeformer_b200 import ops
+
+    gold = load_golden("full_small_train")
+    cfg, spec, sd, batch = case_from_golden(gold)
+    t_wp, t_dense = targets_for(cfg, gold["B"], gold["dseed"] + 1000)
+    p = 0.2
+    model = build_product(cfg, spec, feature_dropout=p).to(DEV).train()
+    model.load_state_dict(sd)
+    model.record_tops = []
+    ops.DropoutStream.log = []
+    try:
+        lossf = R.FutureDiscountedLoss({0: 0.97}, epsilon=1.0, loss_function="smooth_l1")
+        torch.manual_seed(12345)
+        wp, dense = model(to_device(batch, DEV))
+        loss = lossf(wp, t_wp.to(DEV)) + 0.5 * lossf(dense, t_dense.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+        log = list(ops.DropoutStream.log)
+    finally:
+        ops.DropoutStream.log = None
+    # 2 frame-encoder + gaze-encoder + video-encoder layers x 3 sites, 2 decoder layers x 5 sites
+    assert len(log) == 3 * (3 * cfg.encoder_layers) + 5 * cfg.cross_modal_decoder_layers
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and not k.endswith(".pe") and
+                                          not k.startswith("video_backbone")) for k, v in sd.items()}
+    orc = O.Routeformer(params, cfg, spec)
+    hook = ReplayDropout(log, p)
+    torch.manual_seed(12345)
+    with O.dropout_hook(hook):
+        rwp, rdense = orc.forward(batch, training=True, draw=ReplayDraw(tops_for_oracle(model.record_tops, ["right", "left", "front"])))
+    assert hook.exhausted()
+    rloss = O.future_discounted_loss(rwp, t_wp) + 0.5 * O.future_discounted_loss(rdense, t_dense)
+    assert rel_err(wp.detach().cpu(), rwp.detach()) < 1e-3
+    assert rel_err(dense.detach().cpu(), rdense.detach()) < 2e-2
+    assert abs(loss.item() - rloss.item()) < 2e-3 * abs(rloss.item())
+    # dropout changes the result (vs the golden, dropout-free loss) and every trainable parameter still gets a finite gradient
+    assert abs(loss.item() - gold["loss"]) > 1e-4 * abs(gold["loss"])
+    named = dict(model.named_parameters())
+    assert all(named[k].grad is not None and torch.isfinite(named[k].grad).all() for k, v in params.items() if v.requires_grad)
+    # gradients against the oracle's autograd through the same masks (norm-wise; TF32 + top-u chaos bound as in the raw-weight test)
+    rloss.backward()
+    late = [k for k, v in params.items() if v.requires_grad and ("gps_backbone.projection" in k or "video_encoder.projection" in k)]
+    assert late
+    worst = max(((named[k].grad.cpu() - params[k].grad).norm() / params[k].grad.norm().clamp_min(1e-6)).item() for k in late)
+    assert worst < 0.1, worst
+    # eval mode: no dropout, identical to the dropout-free model (state reloaded: the training pass moved the BatchNorm statistics)
+    model.load_state_dict(sd)
+    model.eval()
+    ref_model = build_product(cfg, spec).to(DEV).eval()
+    ref_model.load_state_dict(sd)
+    with torch.no_grad():
+        torch.manual_seed(1)
+        a = model(to_device(batch, DEV))[0]
+        torch.manual_seed(1)
+        b = ref_model(to_device(batch, DEV))[0]
+    assert torch.equal(a, b)
