@@ -363,3 +363,33 @@ def test_training_step_with_feature_dropout():
         torch.manual_seed(1)
         b = ref_model(to_device(batch, DEV))[0]
     assert torch.equal(a, b)
+
+
+def test_view_and_gaze_dropout():
+    """routeformer.py:300-301,402-410: whole camera views / the gaze stream are dropped by CPU torch.rand draws interleaved with the
+    ProbSparse index draws; dropped views contribute zero features (and no frame-encoder work)."""
+    gold = load_golden("full_small_train")
+    cfg, spec, sd, batch = case_from_golden(gold)
+    import dataclasses
+
+    cfg = dataclasses.replace(cfg, view_dropout=0.6, gaze_dropout=0.5)
+    model = build_product(cfg, spec).to(DEV).train()
+    model.load_state_dict(sd)
+    F_frames = len(O.frame_indices(cfg.seq_len, cfg.output_fps // cfg.video_fps))
+    seen = set()
+    for seed in range(6):
+        model.record_tops = []
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            wp, dense = model(to_device(batch, DEV))
+        torch.cuda.synchronize()
+        fe = [r for r in model.record_tops if r["where"].startswith("frame_encoder")]
+        n_views = fe[0]["top"].shape[0] // (gold["B"] * F_frames) if fe else 0
+        seen.add(n_views)
+        torch.manual_seed(seed)
+        orc = O.Routeformer(sd, cfg, spec)
+        with torch.no_grad():
+            rwp, rdense = orc.forward(batch, training=True, draw=ReplayDraw(tops_for_oracle(model.record_tops, ["v"] * max(n_views, 1))))
+        assert rel_err(wp.cpu(), rwp) < 1e-3, seed
+        assert rel_err(dense.cpu(), rdense) < 2e-2, seed
+    assert len(seen) > 1, seen  # the seeds exercise different drop patterns
