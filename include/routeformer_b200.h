@@ -104,6 +104,11 @@ typedef struct {
   int ab_dtype;                              /* RF_F32: A, B are fp32, multiplied as TF32 (kind::tf32).  RF_F16: A, B point to fp16
                                                 (kind::f16, fp32 accumulate; the reference backbone runs under fp16 autocast,
                                                 TimmBackbone.py:106-145); K-major operands only, pitches multiples of 8 */
+  float* colsum_a;                           /* optional [K]: colsum_a[k] += sum_m A[m][k] (fp32, K-major A, no split-K).  In a dgrad
+                                                call A is the output gradient, so this is the bias gradient of the producing
+                                                layer, taken from the operand tiles already in shared memory instead of a
+                                                second pass over A (short reductions: sums of the TF32-rounded tiles; otherwise a separate
+                                                fp32 kernel runs) */
 } RfGemmParams;
 int rf_gemm_tf32(const RfGemmParams* p, void* stream);
 /* Profiling hook: installs (or clears with NULL) a device buffer of >= 8 u64; CTA (0,0,0) of every later GEMM launch records

@@ -53,6 +53,7 @@ struct Args {
   const float* dact_aux; long long ld_aux; int dact;
   int accumulate;
   int kb_total, kb_per_split;
+  float* colsum_a;  // persistent kernel: += column sums of A taken from the operand tiles in shared memory
   int f16;  // operands are fp16 (kind::f16, 64 elements per 128 B k-block row) instead of fp32 read as tf32
   int group_in, group_out, row_offset;
   int round_f16;
@@ -526,7 +527,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // and MMAs of tiles j+1, j+2: for the K=128 layers of the frame encoder (4 k-blocks per tile) the loads never drain.
 constexpr int P_STAGES = 3;
 constexpr int P_EPI_WARPS = 8;         // two warps per TMEM lane quarter: each takes one half of the tile's columns
-constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;
+constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS + 32;  // + one warp that sums the A tiles column-wise (bias gradients)
+constexpr int P_REDUCER_WARP = 2 + P_EPI_WARPS;
 constexpr int EPI_PAIR_BYTES = 32768;  // one (out, preact) staging pair of 2 x 16 KiB; 2 pairs per column half
 
 template <int BLOCK_N>
@@ -544,7 +546,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void epi_bar_sync(int half) { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(P_THREADS, 1)  // registers are granted per 4 warps: 320 threads count as 384 -> 168 per thread
+__global__ void __launch_bounds__(P_THREADS, 1)  // registers are granted per 4 warps: 352 threads count as 384 -> 168 per thread
 gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const Args a,
                             const int tiles_n, const int tiles_m, const int splits) {
@@ -568,7 +570,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     if (a.tma_store) prefetch_tensormap(&tmC);
     for (int s = 0; s < P_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], a.colsum_a ? 2 : 1);  // MMA commit (+ the reducer warp when it reads the A tiles)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
@@ -658,6 +660,56 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       }
     }
     __syncwarp();
+  } else if (warp == P_REDUCER_WARP) {
+    // ---------------- reducer warp: column sums of the A operand (= bias gradient when A is an output gradient) -----------
+    // Every A tile [128 rows x 32 k] passes through shared memory once per N-tile; the N-tile-0 pass is summed over its rows
+    // here (lane = (row group of 4, 16 B chunk), rows strided by 4, 128B-swizzle undone) and added to colsum_a with 32 fp32
+    // atomics per k-block.  The warp holds the ring slot until it has read it (second arrival on the empty barrier).
+    if (a.colsum_a) {
+      const int chunk = lane & 7, grp = lane >> 3;
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int m0, n0, kb_begin, nkb;
+        decode(t, m0, n0, kb_begin, nkb);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % P_STAGES;
+          const uint32_t ph = (it / P_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          if (n0 == 0) {
+            // all 32 row loads are issued back to back and the ring slot is handed back as soon as they are done (the arrive
+            // is a release: it orders the loads before it); the additions run after the slot is already free again.  Holding
+            // the slot through the arithmetic cost 16 % of the GEMM's bandwidth (3-stage ring, latency-bound recycle time).
+            const uint8_t* sa = smem + s * T::STAGE_BYTES;
+            float4 v[BLOCK_M / 4];
+#pragma unroll
+            for (int q = 0; q < BLOCK_M / 4; ++q) {
+              const int r = grp + 4 * q;
+              v[q] = *reinterpret_cast<const float4*>(sa + r * 128 + ((chunk ^ (r & 7)) << 4));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < BLOCK_M / 4; ++q) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+#pragma unroll
+            for (int off = 8; off < 32; off <<= 1) {
+              acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+              acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+            }
+            if (grp == 0) {
+              const int k = (kb_begin + i) * BLOCK_K + 4 * chunk;
+              if (k < a.K) atomicAdd(a.colsum_a + k, acc.x);
+              if (k + 1 < a.K) atomicAdd(a.colsum_a + k + 1, acc.y);
+              if (k + 2 < a.K) atomicAdd(a.colsum_a + k + 2, acc.z);
+              if (k + 3 < a.K) atomicAdd(a.colsum_a + k + 3, acc.w);
+            }
+          } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+          }
+        }
+      }
+    }
   } else {
     // ---------------- epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 -------------------
     // The K=128 layers are epilogue-bound (bias / GELU / derivative / two outputs per element), so 8 warps share one tile:
@@ -845,6 +897,10 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
     RF_LAUNCH_OK();
     return RF_OK;
   }
+  if (args.colsum_a) {  // long reductions: the tile-wise kernels have no reducer warp, the column sums take their own pass
+    rc = rf_colsum_accumulate(p->A, p->lda, p->M, p->K, p->colsum_a, stream);
+    if (rc != RF_OK) return rc;
+  }
   dim3 grid(tiles_n, tiles_m, splits);
   RF_CHECK_ARG(grid.y <= 65535, "rf_gemm_tf32: M=%d exceeds 65535 row tiles", p->M);
   static int deep = -1;
@@ -902,6 +958,8 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   RF_CHECK_ARG(!p->rowadd || p->rowadd_period > 0, "rf_gemm_tf32: rowadd needs rowadd_period > 0");
   RF_CHECK_ARG(!p->dact || p->dact_aux, "rf_gemm_tf32: dact needs dact_aux");
   RF_CHECK_ARG(p->act != RF_ACT_GELU_SAVE_GRAD || p->preact, "rf_gemm_tf32: RF_ACT_GELU_SAVE_GRAD needs the preact buffer");
+  RF_CHECK_ARG(!p->colsum_a || (!f16 && !p->a_mn_major && p->split_k <= 1 && !p->accumulate),
+               "rf_gemm_tf32: colsum_a needs a K-major fp32 A and no split-K");
   const int kb_total = ceil_div(p->K, f16 ? 2 * gemm::BLOCK_K : gemm::BLOCK_K);
   const bool plain = !p->bias && !p->rowadd && !p->residual && p->act == RF_ACT_NONE && !p->preact && !p->dact && !p->round_f16;
   int splits = p->split_k;
@@ -923,7 +981,7 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   a.bias = p->bias; a.rowadd = p->rowadd; a.rowadd_period = p->rowadd_period; a.ld_rowadd = p->ld_rowadd;
   a.residual = p->residual; a.ld_res = p->ld_res; a.act = p->act; a.preact = p->preact; a.ld_pre = p->ld_pre;
   a.dact_aux = p->dact_aux; a.ld_aux = p->ld_aux; a.dact = p->dact; a.accumulate = p->accumulate;
-  a.kb_total = kb_total; a.kb_per_split = kb_per_split; a.f16 = f16 ? 1 : 0;
+  a.kb_total = kb_total; a.kb_per_split = kb_per_split; a.f16 = f16 ? 1 : 0; a.colsum_a = p->colsum_a;
   a.group_in = p->out_group_in; a.group_out = p->out_group_out; a.row_offset = p->out_row_offset;
   a.round_f16 = p->round_f16;
   static int tma_store_enabled = -1;

@@ -137,11 +137,8 @@ class AttentionBlock(Function):
         g = grad_buffer(wo)
         if g is not None:
             ops.gemm(dproj, context, g, a_mn=True, b_mn=True, accumulate=True)
-        g = grad_buffer(bo)
-        if g is not None:
-            ops.colsum_accumulate(dproj, g)
         dcontext = torch.empty(M, D, device=dev, dtype=torch.float32)
-        ops.gemm(dproj, wo, dcontext, b_mn=True)
+        ops.gemm(dproj, wo, dcontext, b_mn=True, colsum_a=grad_buffer(bo))  # bias gradient from the operand tiles of the dgrad
         need_dx = ctx.needs_input_grad[0]
         dx = dcross = None
         if ctx.self_attn:
@@ -161,8 +158,10 @@ class AttentionBlock(Function):
                     g = grad_buffer(w)
                     if g is not None:
                         ops.gemm(dqkv[:, i * D:(i + 1) * D], x, g, a_mn=True, b_mn=True, accumulate=True)
+            fuse_bias = need_dx and w_all is not None and gb_all is not None  # the dx dgrad below reads all of dqkv
             if gb_all is not None:
-                ops.colsum_accumulate(dqkv, gb_all)
+                if not fuse_bias:
+                    ops.colsum_accumulate(dqkv, gb_all)
             else:
                 for i, b in enumerate((bq, bk, bv)):
                     g = grad_buffer(b)
@@ -171,7 +170,7 @@ class AttentionBlock(Function):
             if need_dx:
                 dx = torch.empty(M, D, device=dev, dtype=torch.float32)
                 if w_all is not None:
-                    ops.gemm(dqkv, w_all, dx, b_mn=True, residual=dy)
+                    ops.gemm(dqkv, w_all, dx, b_mn=True, residual=dy, colsum_a=gb_all if fuse_bias else None)
                 else:
                     ops.gemm(dqkv[:, :D], wq, dx, b_mn=True, residual=dy)
                     ops.gemm(dqkv[:, D:2 * D], wk, dx, b_mn=True, residual=dx)
@@ -259,28 +258,26 @@ class FFNBlock(Function):
         g = grad_buffer(w2)
         if g is not None:
             ops.gemm(dt, h, g.view(D, dff), a_mn=True, b_mn=True, accumulate=True)
-        g = grad_buffer(b2)
-        if g is not None:
-            ops.colsum_accumulate(dt, g)
         dpre = torch.empty(M, dff, device=x.device, dtype=torch.float32)
+        gb2 = grad_buffer(b2)  # bias gradients ride on the dgrad GEMMs that read the same tensor as their A operand
         if ctx.act == ops.ACT_GELU:
-            ops.gemm(dt, w2.view(D, dff), dpre, b_mn=True, dact=ops.DACT_SAVED, dact_aux=pre)
+            ops.gemm(dt, w2.view(D, dff), dpre, b_mn=True, dact=ops.DACT_SAVED, dact_aux=pre, colsum_a=gb2)
         else:
             # relu'(pre) = [h > 0]; with dropout h holds the DROPPED activations: a dropped unit reads as inactive, and its
             # gradient is zeroed by the mask below anyway
-            ops.gemm(dt, w2.view(D, dff), dpre, b_mn=True, dact=ctx.act, dact_aux=h)
+            ops.gemm(dt, w2.view(D, dff), dpre, b_mn=True, dact=ctx.act, dact_aux=h, colsum_a=gb2)
         if drop:
             ops.dropout(dpre, dpre, drop["p"], *drop["hidden"])
         g = grad_buffer(w1)
         if g is not None:
             ops.gemm(dpre, x, g.view(dff, D), a_mn=True, b_mn=True, accumulate=True)
-        g = grad_buffer(b1)
-        if g is not None:
-            ops.colsum_accumulate(dpre, g)
+        gb1 = grad_buffer(b1)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, D, device=x.device, dtype=torch.float32)
-            ops.gemm(dpre, w1.view(dff, D), dx, b_mn=True, residual=dy)
+            ops.gemm(dpre, w1.view(dff, D), dx, b_mn=True, residual=dy, colsum_a=gb1)
+        elif gb1 is not None:
+            ops.colsum_accumulate(dpre, gb1)
         return dx, None, None, None, None, None, None
 
 

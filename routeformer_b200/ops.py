@@ -95,7 +95,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
          bias: Optional[torch.Tensor] = None, rowadd: Optional[torch.Tensor] = None, rowadd_period: int = 0,
          residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, preact: Optional[torch.Tensor] = None,
          dact_aux: Optional[torch.Tensor] = None, dact: int = ACT_NONE, accumulate: bool = False, split_k: int = 0,
-         out_group=(0, 0, 0), round_f16: bool = False, M: Optional[int] = None) -> torch.Tensor:
+         out_group=(0, 0, 0), round_f16: bool = False, M: Optional[int] = None, colsum_a: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] (+)= epilogue(A . B^T) on the tcgen05 kernel.  A, B are 2-D fp32 views (multiplied as TF32) or both fp16
     (kind::f16, K-major only); out and the epilogue operands are fp32.
 
@@ -139,6 +139,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
     p.out_group_in, p.out_group_out, p.out_row_offset = out_group
     p.round_f16 = int(round_f16)
     p.ab_dtype = F16 if f16 else F32
+    if colsum_a is not None:  # colsum_a[k] += sum_m A[m, k]: the bias gradient when A is an output gradient
+        if colsum_a.numel() != K or not colsum_a.is_contiguous():
+            raise ValueError("gemm: colsum_a must be a contiguous [K] vector")
+        p.colsum_a = _ptr(_f32(colsum_a, "colsum_a"))
     check(lib.rf_gemm_tf32(C.byref(p), _stream()), "rf_gemm_tf32")
     _count()
     return out

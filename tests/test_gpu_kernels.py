@@ -87,6 +87,23 @@ def test_gemm_fp16_operands(ops):
         ops.gemm(A.to(DEV), W.to(DEV), buf, b_mn=True)
 
 
+def test_gemm_operand_column_sums(ops):
+    """colsum_a: bias gradients taken from the A tiles of a dgrad GEMM (persistent kernel: reducer warp; long K: separate pass)."""
+    gen = g(6)
+    for (M, N, K) in [(5000, 160, 96), (777, 384, 132), (99, 64, 40), (300, 128, 1000)]:
+        A = torch.randn(M, K, generator=gen)
+        B = torch.randn(K, N, generator=gen) / math.sqrt(K)   # dgrad form: B is [K][N] memory (b_mn)
+        res = torch.randn(M, N, generator=gen)
+        out = torch.empty(M, N, device=DEV)
+        cs = torch.full((K,), 3.0, device=DEV)
+        ops.gemm(A.to(DEV), B.to(DEV), out, b_mn=True, residual=res.to(DEV), colsum_a=cs)
+        assert rel_err(out.cpu(), (A.double() @ B.double()).float() + res) < 2e-3
+        # short reductions sum the TF32-rounded operand tiles (unbiased RN rounding, 2^-11 per element), long ones the fp32 data
+        assert rel_err(cs.cpu() - 3.0, A.sum(0)) < 1e-3, (M, N, K)
+    with pytest.raises(RuntimeError):
+        ops.gemm(A.t().contiguous().to(DEV), B.to(DEV), out, a_mn=True, b_mn=True, colsum_a=cs)
+
+
 def test_gemm_strided_rows_and_row_remap(ops):
     gen = g(2)
     n, K, N = 6, 96, 40
