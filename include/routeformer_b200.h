@@ -98,7 +98,10 @@ typedef struct {
   float* preact; long long ld_pre;           /* if non-NULL the pre-activation value is also stored here */
   const float* dact_aux; long long ld_aux; int dact; /* if dact!=0: result *= act'(dact_aux[m][n]) (RELU: aux>0) */
   int accumulate;                            /* 1: C += result with fp32 atomics (C must be initialised) */
-  int split_k;                               /* 0 = auto (only >1 when accumulate=1) */
+  int split_k;                               /* 0 = auto: >1 for accumulate=1 (wgrad), and for few-tile / long-K GEMMs whose epilogue is
+                                                linear (bias, rowadd, residual): output zero-filled, split 0 adds the linear terms,
+                                                splits meet in fp32 reduce-adds (order not fixed).  -1 = auto, but bit-reproducible:
+                                                non-accumulating calls are never split.  >1 = explicit (accumulate=1 only) */
   int out_group_in, out_group_out, out_row_offset; /* if out_group_in>0: row m is stored at (m/gi)*go + m%gi + offset */
   int round_f16;                             /* 1: round the result through fp16 (backbone plugin returns input dtype) */
   int ab_dtype;                              /* RF_F32: A, B are fp32, multiplied as TF32 (kind::tf32).  RF_F16: A, B point to fp16

@@ -53,6 +53,7 @@ struct Args {
   const float* dact_aux; long long ld_aux; int dact;
   int accumulate;
   int kb_total, kb_per_split;
+  int split_epilogue;  // split-K of a GEMM with a LINEAR epilogue: bias / rowadd / residual are added by split 0 only
   float* colsum_a;  // persistent kernel: += column sums of A taken from the operand tiles in shared memory
   int f16;  // operands are fp16 (kind::f16, 64 elements per 128 B k-block row) instead of fp32 read as tf32
   int group_in, group_out, row_offset;
@@ -202,13 +203,15 @@ struct RowEpilogue {
   float* pre_row;
   float* c_row;
 
-  __device__ __forceinline__ void init(const Args& a, int m) {
+  bool add_linear;  // this CTA adds the bias / positional / residual terms (all CTAs, or split 0 of a split linear epilogue)
+  __device__ __forceinline__ void init(const Args& a, int m, int z = 0) {
     row_ok = m < a.M;
+    add_linear = !a.split_epilogue || z == 0;
     long long out_row = m;
     if (a.group_in > 0) out_row = static_cast<long long>(m / a.group_in) * a.group_out + (m % a.group_in) + a.row_offset;
     c_row = a.C + out_row * a.ldc;
-    rowadd_row = a.rowadd ? a.rowadd + static_cast<long long>(m % a.rowadd_period) * a.ld_rowadd : nullptr;
-    res_row = a.residual ? a.residual + static_cast<long long>(m) * a.ld_res : nullptr;
+    rowadd_row = (a.rowadd && add_linear) ? a.rowadd + static_cast<long long>(m % a.rowadd_period) * a.ld_rowadd : nullptr;
+    res_row = (a.residual && add_linear) ? a.residual + static_cast<long long>(m) * a.ld_res : nullptr;
     pre_row = a.preact ? a.preact + static_cast<long long>(m) * a.ld_pre : nullptr;
     aux_row = a.dact ? a.dact_aux + static_cast<long long>(m) * a.ld_aux : nullptr;
     al16 = ((reinterpret_cast<uintptr_t>(a.bias) | reinterpret_cast<uintptr_t>(a.rowadd) | reinterpret_cast<uintptr_t>(a.residual) |
@@ -247,7 +250,7 @@ struct RowEpilogue {
     const bool side_is_res = have_side && !a.dact;
     const bool side_is_aux = have_side && a.dact;
     if (row_ok) {
-      if (a.bias) add_row(x, a.bias + nb, ncols, vec, true);
+      if (a.bias && add_linear) add_row(x, a.bias + nb, ncols, vec, true);
       if (rowadd_row) add_row(x, rowadd_row + nb, ncols, vec, true);
       if (side_is_res) {
 #pragma unroll
@@ -442,7 +445,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   long long out_row = m;
   if (a.group_in > 0) out_row = static_cast<long long>(m / a.group_in) * a.group_out + (m % a.group_in) + a.row_offset;
   RowEpilogue re;
-  re.init(a, m);
+  re.init(a, m, blockIdx.z);
 
   if (a.tma_store) {
     // ---- staged path: 128x32 fp32 chunks -> 128B-swizzled smem (the idle pipeline stages) -> TMA bulk store --------
@@ -588,7 +591,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const int nt = t % tiles_n;
     const int r = t / tiles_n;
     const int mt = r % tiles_m;
-    const int z = r / tiles_m;
+    const int z = r / tiles_m;  // split index (== kb_begin / kb_per_split)
     m0 = mt * BLOCK_M;
     n0 = nt * BLOCK_N;
     kb_begin = z * a.kb_per_split;
@@ -727,7 +730,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int ab = j & 1;
       const uint32_t aph = (j >> 1) & 1;
       RowEpilogue re;
-      re.init(a, m0 + row_in_tile);
+      re.init(a, m0 + row_in_tile, kb_begin / a.kb_per_split);
       const int nh = n0 + half * HALF_N;
       int n_chunks = 0;
 #pragma unroll
@@ -973,14 +976,36 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
     }
   }
   RF_CHECK_ARG(splits == 1 || (p->accumulate && plain), "rf_gemm_tf32: split_k>1 needs accumulate=1 and a plain epilogue");
+  // Few output tiles and a long reduction (the Informer layers at 64 clips per GPU: 14-80 tiles, 26-104 k-blocks): every CTA
+  // walks its K loop at the pace of one TMA round trip per stage while most SMs idle.  If the epilogue is linear in the
+  // accumulator (bias / positional rows / residual only), split the reduction over more CTAs: the output is zero-filled, split
+  // 0 adds the linear terms, and all splits meet in the TMA reduce-add.
+  bool split_linear = false;
+  if (p->split_k == 0 && !p->accumulate && !f16 && p->act == RF_ACT_NONE && !p->preact && !p->dact && !p->round_f16 &&
+      p->out_group_in == 0 && 2 * tiles <= num_sms() && kb_total >= 8) {
+    const char* cb = reinterpret_cast<const char*>(p->C);
+    const char* ce = cb + (static_cast<long long>(p->M - 1) * p->ldc + p->N) * 4;
+    const char* rb = reinterpret_cast<const char*>(p->residual);
+    const bool res_aliases = rb && rb < ce && rb + (static_cast<long long>(p->M - 1) * p->ld_res + p->N) * 4 > cb;
+    static const bool enabled = [] { const char* e = getenv("RF_GEMM_SPLIT_LINEAR"); return !(e && e[0] == '0'); }();
+    const int want = min(num_sms() / tiles, kb_total / 4);
+    if (enabled && !res_aliases && want >= 2) {
+      splits = want;
+      split_linear = true;
+    }
+  }
   int kb_per_split = ceil_div(kb_total, splits);
   splits = ceil_div(kb_total, kb_per_split);
+  if (split_linear && splits < 2) split_linear = false;
+  if (split_linear)
+    RF_CUDA_OK(cudaMemset2DAsync(p->C, static_cast<size_t>(p->ldc) * 4, 0, static_cast<size_t>(p->N) * 4, p->M, static_cast<cudaStream_t>(stream)));
   gemm::Args a;
   a.C = p->C; a.ldc = p->ldc; a.M = p->M; a.N = p->N; a.K = p->K;
   a.a_mn = p->a_mn_major ? 1 : 0; a.b_mn = p->b_mn_major ? 1 : 0;
   a.bias = p->bias; a.rowadd = p->rowadd; a.rowadd_period = p->rowadd_period; a.ld_rowadd = p->ld_rowadd;
   a.residual = p->residual; a.ld_res = p->ld_res; a.act = p->act; a.preact = p->preact; a.ld_pre = p->ld_pre;
-  a.dact_aux = p->dact_aux; a.ld_aux = p->ld_aux; a.dact = p->dact; a.accumulate = p->accumulate;
+  a.dact_aux = p->dact_aux; a.ld_aux = p->ld_aux; a.dact = p->dact; a.accumulate = (p->accumulate || split_linear) ? 1 : 0;
+  a.split_epilogue = split_linear ? 1 : 0;
   a.kb_total = kb_total; a.kb_per_split = kb_per_split; a.f16 = f16 ? 1 : 0; a.colsum_a = p->colsum_a;
   a.group_in = p->out_group_in; a.group_out = p->out_group_out; a.row_offset = p->out_row_offset;
   a.round_f16 = p->round_f16;

@@ -135,7 +135,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
         p.preact, p.ld_pre = _ptr(preact), _row_pitch(preact, "preact")
     if dact != ACT_NONE:
         p.dact_aux, p.ld_aux, p.dact = _ptr(dact_aux), _row_pitch(dact_aux, "dact_aux"), dact
-    p.accumulate, p.split_k = int(accumulate), split_k
+    # inference (no_grad) asks for the bit-reproducible policy (forward GEMMs are never split): metrics repeat exactly run to run
+    p.accumulate, p.split_k = int(accumulate), (-1 if (split_k == 0 and not accumulate and not torch.is_grad_enabled()) else split_k)
     p.out_group_in, p.out_group_out, p.out_row_offset = out_group
     p.round_f16 = int(round_f16)
     p.ab_dtype = F16 if f16 else F32

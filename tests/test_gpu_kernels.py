@@ -104,6 +104,34 @@ def test_gemm_operand_column_sums(ops):
         ops.gemm(A.t().contiguous().to(DEV), B.to(DEV), out, a_mn=True, b_mn=True, colsum_a=cs)
 
 
+def test_gemm_split_linear_epilogue(ops):
+    """Few tiles + long reduction + linear epilogue (the Informer layers): the library splits K on its own; bias, positional
+    rows and the residual must be added exactly once, and a residual aliasing the output must keep working."""
+    gen = g(8)
+    for (M, N, K, period) in [(192, 832, 3328, 0), (704, 832, 832, 64), (130, 136, 2000, 0)]:
+        A, B = torch.randn(M, K, generator=gen), torch.randn(N, K, generator=gen) / math.sqrt(K)
+        bias, res = torch.randn(N, generator=gen), torch.randn(M, N, generator=gen)
+        pe = torch.randn(max(period, 1), N, generator=gen)
+        ref = (A.double() @ B.double().t()).float() + bias + res + (pe.repeat(M // period, 1) if period else 0)
+        out = torch.full((M, N), float("nan"), device=DEV)
+        ops.gemm(A.to(DEV), B.to(DEV), out, bias=bias.to(DEV), residual=res.to(DEV),
+                 rowadd=pe.to(DEV) if period else None, rowadd_period=period)
+        assert rel_err(out.cpu(), ref) < 2e-3, (M, N, K)
+        with torch.no_grad():  # inference policy: no split -> bit-reproducible
+            o1, o2 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+            for o in (o1, o2):
+                ops.gemm(A.to(DEV), B.to(DEV), o, bias=bias.to(DEV), residual=res.to(DEV), rowadd=pe.to(DEV) if period else None,
+                         rowadd_period=period)
+            assert torch.equal(o1, o2) and rel_err(o1.cpu(), ref) < 2e-3
+        acc = res.to(DEV).clone()  # out aliases the residual (dx += ... chains): must not be zero-filled
+        ops.gemm(A.to(DEV), B.to(DEV), acc, bias=bias.to(DEV), residual=acc)
+        assert rel_err(acc.cpu(), (A.double() @ B.double().t()).float() + bias + res) < 2e-3
+        wide = torch.full((M, N + 8), 7.0, device=DEV)  # strided output: the columns beyond N stay untouched
+        ops.gemm(A.to(DEV), B.to(DEV), wide[:, :N], bias=bias.to(DEV))
+        assert rel_err(wide[:, :N].cpu(), (A.double() @ B.double().t()).float() + bias) < 2e-3
+        assert torch.equal(wide[:, N:].cpu(), torch.full((M, 8), 7.0))
+
+
 def test_gemm_strided_rows_and_row_remap(ops):
     gen = g(2)
     n, K, N = 6, 96, 40

@@ -2,4 +2,4 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "gemm or conv3" --timeout 300 -p no:cacheprovider 2>&1 | tail -12
 timeout 900 python -m pytest tests/test_gpu_model.py -q -m gpu --timeout 300 -p no:cacheprovider 2>&1 | tail -12
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v21.log 2>&1; grep "^{" gpurun_out/bench_v21.log | cut -c1-200; tail -2 gpurun_out/bench_v21.log | cut -c1-300
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v24.log 2>&1; grep "^{" gpurun_out/bench_v24.log | cut -c1-200; tail -2 gpurun_out/bench_v24.log | cut -c1-300
