@@ -124,7 +124,8 @@ def run_ours(args):
         wp, dense = out
         return lossf(wp, tgt[0]) + 0.5 * lossf(dense, tgt[1])
 
-    trainer = DataParallelTrainer(model, loss_fn, lr=1e-5, weight_decay=1e-4, max_grad_norm=2.5, use_cuda_graph=not args.no_graph)
+    trainer = DataParallelTrainer(model, loss_fn, lr=1e-5, weight_decay=1e-4, max_grad_norm=2.5, use_cuda_graph=not args.no_graph,
+                                  overlap_wgrad=not args.no_wgrad_overlap)
     trainer.broadcast_parameters()
     # inputs: pinned host batch in the reference layout; the device batch holds the frames the model consumes (8 of 40 per view)
     pinned = {k: v.contiguous().pin_memory() for k, v in host_batch.items()}
@@ -424,6 +425,7 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=64)
     ap.add_argument("--fov", default="gaze", choices=["gaze", "frame"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-wgrad-overlap", action="store_true", help="keep the weight-gradient GEMMs on the main stream")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one captured CUDA graph")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up + --steps steps, no e2e / roofline / CPU legs")
     args = ap.parse_args()

@@ -23,6 +23,27 @@ def grad_buffer(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return p.grad
 
 
+class WgradStream:
+    """Optional side stream for the weight-gradient GEMMs.  dW = dY^T X only has to be ready when the optimiser runs, while the
+    backward chain waits for dX = dY W: with a side stream the two run concurrently, which matters for the small layers (Informer,
+    gaze / video encoders) whose GEMMs fill a fraction of the SMs.  Set for the duration of a step by DataParallelTrainer, which
+    also joins the stream before touching the gradients; None = everything on the caller's stream."""
+    stream: Optional[torch.cuda.Stream] = None
+
+
+def wgrad(dy_t: torch.Tensor, x: torch.Tensor, g: torch.Tensor) -> None:
+    """g[N,K] += dy_t[M,N]^T x[M,K] (split over the long reduction, accumulated straight into the gradient arena)."""
+    side = WgradStream.stream
+    if side is None:
+        ops.gemm(dy_t, x, g, a_mn=True, b_mn=True, accumulate=True)
+        return
+    side.wait_stream(torch.cuda.current_stream())  # dy_t was produced on the main stream
+    dy_t.record_stream(side)
+    x.record_stream(side)
+    with torch.cuda.stream(side):
+        ops.gemm(dy_t, x, g, a_mn=True, b_mn=True, accumulate=True)
+
+
 def _adjacent(*ts: torch.Tensor) -> bool:
     """True if the (contiguous) tensors sit back to back in ONE storage (the arena), i.e. can be addressed as one matrix."""
     base = ts[0].untyped_storage().data_ptr()
@@ -136,7 +157,7 @@ class AttentionBlock(Function):
         attn_drop = (drop["p"], *drop["prob"]) if drop and drop.get("prob") else None
         g = grad_buffer(wo)
         if g is not None:
-            ops.gemm(dproj, context, g, a_mn=True, b_mn=True, accumulate=True)
+            wgrad(dproj, context, g)
         dcontext = torch.empty(M, D, device=dev, dtype=torch.float32)
         ops.gemm(dproj, wo, dcontext, b_mn=True, colsum_a=grad_buffer(bo))  # bias gradient from the operand tiles of the dgrad
         need_dx = ctx.needs_input_grad[0]
@@ -152,12 +173,12 @@ class AttentionBlock(Function):
             w_all = _fused(wq, wk, wv)
             gw_all, gb_all = _fused_grads(wq, wk, wv), _fused_grads(bq, bk, bv)
             if gw_all is not None:
-                ops.gemm(dqkv, x, gw_all, a_mn=True, b_mn=True, accumulate=True)
+                wgrad(dqkv, x, gw_all)
             else:
                 for i, w in enumerate((wq, wk, wv)):
                     g = grad_buffer(w)
                     if g is not None:
-                        ops.gemm(dqkv[:, i * D:(i + 1) * D], x, g, a_mn=True, b_mn=True, accumulate=True)
+                        wgrad(dqkv[:, i * D:(i + 1) * D], x, g)
             fuse_bias = need_dx and w_all is not None and gb_all is not None  # the dx dgrad below reads all of dqkv
             if gb_all is not None:
                 if not fuse_bias:
@@ -185,18 +206,18 @@ class AttentionBlock(Function):
                               dq, dkv, dkv[:, D:], dropout=attn_drop)
             g = grad_buffer(wq)
             if g is not None:
-                ops.gemm(dq, x, g, a_mn=True, b_mn=True, accumulate=True)
+                wgrad(dq, x, g)
             g = grad_buffer(bq)
             if g is not None:
                 ops.colsum_accumulate(dq, g)
             gw_kv, gb_kv = _fused_grads(wk, wv), _fused_grads(bk, bv)
             if gw_kv is not None:
-                ops.gemm(dkv, cross, gw_kv, a_mn=True, b_mn=True, accumulate=True)
+                wgrad(dkv, cross, gw_kv)
             else:
                 for i, w in enumerate((wk, wv)):
                     g = grad_buffer(w)
                     if g is not None:
-                        ops.gemm(dkv[:, i * D:(i + 1) * D], cross, g, a_mn=True, b_mn=True, accumulate=True)
+                        wgrad(dkv[:, i * D:(i + 1) * D], cross, g)
             if gb_kv is not None:
                 ops.colsum_accumulate(dkv, gb_kv)
             else:
@@ -257,7 +278,7 @@ class FFNBlock(Function):
             dt = ops.dropout(dy, torch.empty_like(dy), drop["p"], *drop["out"])
         g = grad_buffer(w2)
         if g is not None:
-            ops.gemm(dt, h, g.view(D, dff), a_mn=True, b_mn=True, accumulate=True)
+            wgrad(dt, h, g.view(D, dff))
         dpre = torch.empty(M, dff, device=x.device, dtype=torch.float32)
         gb2 = grad_buffer(b2)  # bias gradients ride on the dgrad GEMMs that read the same tensor as their A operand
         if ctx.act == ops.ACT_GELU:
@@ -270,7 +291,7 @@ class FFNBlock(Function):
             ops.dropout(dpre, dpre, drop["p"], *drop["hidden"])
         g = grad_buffer(w1)
         if g is not None:
-            ops.gemm(dpre, x, g.view(dff, D), a_mn=True, b_mn=True, accumulate=True)
+            wgrad(dpre, x, g.view(dff, D))
         gb1 = grad_buffer(b1)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -331,7 +352,7 @@ class Linear(Function):
         g = grad_buffer(w)
         if g is not None:
             xc = x if x.stride(0) % 4 == 0 else x.contiguous()
-            ops.gemm(dy_p, xc, g, a_mn=True, b_mn=True, accumulate=True)
+            wgrad(dy_p, xc, g)
         g = grad_buffer(b)
         if g is not None:
             ops.colsum_accumulate(dy, g)

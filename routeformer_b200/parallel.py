@@ -57,7 +57,8 @@ class DataParallelTrainer:
     made on the host in reference order and reach the graph through a persistent pinned buffer."""
 
     def __init__(self, model, loss_fn: Callable, lr: float = 1e-5, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 max_grad_norm: float = 2.5, group=None, n_buckets: int = 4, use_cuda_graph: bool = False):
+                 max_grad_norm: float = 2.5, group=None, n_buckets: int = 4, use_cuda_graph: bool = False,
+                 overlap_wgrad: bool = True):
         self.model = model
         self.loss_fn = loss_fn
         self.group = group
@@ -72,6 +73,7 @@ class DataParallelTrainer:
         self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
         self.step_count = 0
         self.use_cuda_graph = use_cuda_graph
+        self.wgrad_stream = torch.cuda.Stream(dev) if (overlap_wgrad and dev.type == "cuda") else None
         self._graph = None
         self.static_batch = None
         self.static_targets = None
@@ -81,10 +83,23 @@ class DataParallelTrainer:
 
     # -- forward + backward ----------------------------------------------------------------------
     def _fwd_bwd(self, batch, targets) -> torch.Tensor:
+        from . import functional as Fn
+
         self.arena.zero_grad()
         out = self.model(batch)
         loss = self.loss_fn(out, targets)
-        loss.backward()
+        if self.wgrad_stream is None:
+            loss.backward()
+            return loss
+        # weight-gradient GEMMs on a side stream, concurrent with the dgrad chain; joined before anyone reads the gradients
+        main = torch.cuda.current_stream()
+        self.wgrad_stream.wait_stream(main)  # the zero-fill of the gradient arena precedes the first accumulation
+        Fn.WgradStream.stream = self.wgrad_stream
+        try:
+            loss.backward()
+        finally:
+            Fn.WgradStream.stream = None
+            main.wait_stream(self.wgrad_stream)
         return loss
 
     def _capture(self, batch, targets) -> None:
