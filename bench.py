@@ -118,6 +118,8 @@ def run_ours(args):
     cfg, spec, host_batch, host_targets = build_case(B, seed=100 + rank, fov=args.fov)
     torch.manual_seed(0)
     model = build_model(cfg, spec, args.fov).to(dev).train()
+    if args.no_branch_overlap:
+        R.Routeformer.overlap_branches = False
     lossf = R.FutureDiscountedLoss({0: 0.97}, epsilon=1.0, loss_function="smooth_l1")
 
     def loss_fn(out, tgt):
@@ -425,6 +427,7 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=64)
     ap.add_argument("--fov", default="gaze", choices=["gaze", "frame"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-branch-overlap", action="store_true", help="run the gaze encoder on the main stream instead of a side stream")
     ap.add_argument("--no-wgrad-overlap", action="store_true", help="keep the weight-gradient GEMMs on the main stream")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one captured CUDA graph")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up + --steps steps, no e2e / roofline / CPU legs")

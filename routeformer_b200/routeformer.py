@@ -316,14 +316,41 @@ class Routeformer(nn.Module):
             out[v["name"]] = feats[i * n_per_view:(i + 1) * n_per_view].view(v["B"], len(v["t_idx"]), E)
         return out
 
+    overlap_branches = True  # run the gaze encoder concurrently with the frame path (class-level switch, e.g. for debugging)
+
+    def _branch_stream(self, dev) -> torch.cuda.Stream:
+        s = getattr(self, "_side_stream", None)
+        if s is None or s.device != torch.device(dev):
+            s = self._side_stream = torch.cuda.Stream(dev)
+        return s
+
     def _visual_features(self, batch, training: bool, plan, dev_tables) -> torch.Tensor:
         c = self.configs
         E, T = c.image_embedding_size, plan["T_vid"]
         dev = self.device
         rel_v, rel_g = c.output_fps // c.video_fps, c.output_fps // c.gaze_fps
+        B = batch["gps"].shape[0]
+        # The gaze encoder (B*40 tokens: ~100 small launches forward, ~200 backward) depends on nothing the frame encoder
+        # produces: it is forked onto a side stream BEFORE the frame path is enqueued and joined where the gaze-video decoder
+        # needs both, so its launches fill the SMs the big frame-encoder kernels leave idle.  Autograd replays the same stream
+        # assignment in the backward pass.
+        gq = None
+        if self.with_gaze and not plan["drop_gaze"]:
+            Lg = c.gps_backbone_config.seq_len
+            gaze = batch["gaze"].to(torch.float32).contiguous()
+            src = self._source([(plan["log"][i], dev_tables[i]) for i in plan["entries"]["gaze_encoder"]])
+            main = torch.cuda.current_stream()
+            side = self._branch_stream(dev) if self.overlap_branches else None
+            if side is not None:
+                side.wait_stream(main)
+            with torch.cuda.stream(side if side is not None else main):
+                gaze_ds = ops.median_downsample(gaze, Lg)  # utils/filter.py:5-43 (raises if Lg >= samples)
+                gq = self.gaze_encoder.encode(torch.nn.functional.pad(gaze_ds.view(B * Lg, 2), (0, 2)), B, Lg, src, self.record_tops,
+                                              "gaze_encoder")  # [B*Lg, E]
+            if side is not None:
+                gaze.record_stream(side)
         feats = self._encode_frames(batch, plan, dev_tables, training)
         streams, srcs, embs = [], [], []
-        B = batch["gps"].shape[0]
 
         def frames_stream(name, rel):
             idx = frame_indices(T, rel)
@@ -345,16 +372,13 @@ class Routeformer(nn.Module):
                 streams.append((False, True, 0, 0, 1))
                 srcs.append(None)
             else:
-                Lg = c.gps_backbone_config.seq_len
-                gaze = batch["gaze"].to(torch.float32).contiguous()
-                gaze_ds = ops.median_downsample(gaze, Lg)  # utils/filter.py:5-43 (raises if Lg >= samples)
                 idx = frame_indices(T, rel_g)
                 meta = dict(B=B, T=T, E=E, streams=[(True, False, len(idx), int(idx[0]), int(idx[1] - idx[0]) if len(idx) > 1 else 1)])
                 front_full = Fn.TokenStreams.apply(meta, feats["front"].contiguous(), torch.zeros(E, device=dev))  # [B,T,E]
                 ent = plan["entries"]
-                src = self._source([(plan["log"][i], dev_tables[i]) for i in ent["gaze_encoder"]])
-                gq = self.gaze_encoder.encode(torch.nn.functional.pad(gaze_ds.view(B * Lg, 2), (0, 2)), B, Lg, src, self.record_tops,
-                                              "gaze_encoder")  # [B*Lg, E]
+                if self.overlap_branches:  # join: the decoder reads the gaze-encoder output on the main stream
+                    torch.cuda.current_stream().wait_stream(self._branch_stream(dev))
+                    gq.record_stream(torch.cuda.current_stream())
                 src = self._source([(plan["log"][i], dev_tables[i]) for i in ent["gaze_video_decoder"]])
                 g = self.gaze_video_decoder.decode(front_full.view(B * T, E), gq, B, T, Lg, src, self.record_tops, "gaze_video_decoder")
                 g = g.view(B, Lg, -1)[:, :T].contiguous()  # routeformer.py:327

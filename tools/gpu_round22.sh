@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_model.py -q -m gpu --timeout 300 -p no:cacheprovider 2>&1 | tail -12
-timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v25.log 2>&1; grep "^{" gpurun_out/bench_v25.log | cut -c1-200; tail -2 gpurun_out/bench_v25.log | cut -c1-300
-timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-wgrad-overlap > gpurun_out/bench_v25_nooverlap.log 2>&1; grep "^{" gpurun_out/bench_v25_nooverlap.log | cut -c1-200
+timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v26.log 2>&1; grep "^{" gpurun_out/bench_v26.log | cut -c1-200; tail -2 gpurun_out/bench_v26.log | cut -c1-300
+timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-branch-overlap > gpurun_out/bench_v26_nobranch.log 2>&1; grep "^{" gpurun_out/bench_v26_nobranch.log | cut -c1-200
