@@ -263,6 +263,8 @@ __device__ void select_and_softmax(const RfAttnParams& p, const Dims<DH> d, cons
 
 template <int DH>
 __global__ void __launch_bounds__(THREADS) attention_fwd_kernel(const RfAttnParams p) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) float smem_f[];
   const Dims<DH> d{p.dh};
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
@@ -323,6 +325,8 @@ __global__ void __launch_bounds__(THREADS) attention_fwd_kernel(const RfAttnPara
 //   dQ[top_r] = sum_j dS[r][j] K[j]   (other rows 0),   dK[j] = sum_r dS[r][j] Q[top_r]
 template <int DH>
 __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdParams bp) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) float smem_f[];
   const RfAttnParams& p = bp.f;
   const Dims<DH> d{p.dh};
@@ -531,6 +535,8 @@ __host__ __device__ __forceinline__ int small_nt(int Lk) { return (Lk >> 5) + ((
 
 template <int DH, int NT>
 __global__ void __launch_bounds__(THREADS, 7) attention_small_fwd_kernel(const RfAttnParams p) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) float smem_f[];
   constexpr int DH4 = DH / 4;
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
@@ -690,6 +696,8 @@ __global__ void __launch_bounds__(THREADS, 7) attention_small_fwd_kernel(const R
 
 template <int DH, int NT>
 __global__ void __launch_bounds__(THREADS, 7) attention_small_bwd_kernel(const RfAttnBwdParams bp) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) float smem_f[];
   constexpr int DH4 = DH / 4;
   const RfAttnParams& p = bp.f;
@@ -947,7 +955,7 @@ static int configure(K kernel, size_t smem) {
   {                                                                                \
     rc = attn::configure(attn::KERNEL<DHT>, SMEM);                                 \
     if (rc != RF_OK) return rc;                                                    \
-    attn::KERNEL<DHT><<<GRID, attn::THREADS, SMEM, STREAM>>>(ARG);                 \
+    rf::launch_pdl(attn::KERNEL<DHT>, dim3(GRID), dim3(attn::THREADS), SMEM, STREAM, ARG); \
   }
 #define RF_ATTN_DISPATCH(KERNEL, ARG, DHVAL, GRID, SMEM, STREAM)                   \
   switch (DHVAL) {                                                                 \
@@ -961,7 +969,7 @@ static int configure(K kernel, size_t smem) {
   {                                                                                \
     rc = attn::configure(attn::KERNEL<DHT, NTT>, SMEM);                            \
     if (rc != RF_OK) return rc;                                                    \
-    attn::KERNEL<DHT, NTT><<<GRID, attn::THREADS, SMEM, STREAM>>>(ARG);            \
+    rf::launch_pdl(attn::KERNEL<DHT, NTT>, dim3(GRID), dim3(attn::THREADS), SMEM, STREAM, ARG); \
   }
 #define RF_ATTN_SMALL_NT(KERNEL, DHT, ARG, NTVAL, GRID, SMEM, STREAM)              \
   switch (NTVAL) {                                                                 \

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/routeformer_b200.h"
@@ -55,6 +56,33 @@ inline int num_sms() {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch ------------------------------------------------------------
+// A training step is ~800 launches, most of them 5-30 us long: the gap between dependent kernels (the next grid's CTAs are only
+// scheduled after the previous grid has drained) is a measurable share of the step.  Kernels launched through launch_pdl may be
+// scheduled while their predecessor in the stream is still running; they must call pdl_wait() before touching global memory
+// (it returns once the predecessor has completed and flushed) and pdl_trigger() to let their own successor be scheduled.
+// RF_PDL=0 disables the attribute (then pdl_wait / pdl_trigger are no-ops by definition).
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("RF_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

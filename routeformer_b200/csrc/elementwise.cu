@@ -17,6 +17,8 @@ inline int blocks_for(long long n, int per_block = TPB, int cap = 148 * 16) {
 // (3) circular conv assembly
 // ---------------------------------------------------------------------------------------------
 __global__ void conv3_assemble_fwd_kernel(const RfConv3AssembleParams a, int L_out, long long total4) {
+  pdl_wait();
+  pdl_trigger();
   const int D4 = a.D >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -50,6 +52,8 @@ __global__ void conv3_assemble_fwd_kernel(const RfConv3AssembleParams a, int L_o
 }
 
 __global__ void conv3_assemble_bwd_kernel(const RfConv3AssembleBwdParams a, int L_out, long long total4) {
+  pdl_wait();
+  pdl_trigger();
   const int D4 = a.D >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -74,6 +78,8 @@ __global__ void conv3_assemble_bwd_kernel(const RfConv3AssembleBwdParams a, int 
 // 32 columns x 8 row-lanes per CTA; every thread keeps 4 independent loads in flight; one atomic per column per CTA.
 __global__ void colsum_kernel(const float* __restrict__ src, long long ld, int M, int N, float* __restrict__ dst,
                               int weight_period) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float part[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
@@ -109,7 +115,7 @@ static void launch_colsum(const float* src, long long ld, int M, int N, float* d
   int gy = ceil_div(M, 8 * 8);  // ~8 rows per thread
   gy = gy < 1 ? 1 : (gy > 1024 ? 1024 : gy);
   dim3 grid(ceil_div(N, 32), gy);
-  colsum_kernel<<<grid, block, 0, s>>>(src, ld, M, N, dst, weight_period);
+  launch_pdl(colsum_kernel, grid, block, 0, s, src, ld, M, N, dst, weight_period);
 }
 
 __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ wcat, int D, int C, long long ldw) {
@@ -503,8 +509,7 @@ extern "C" int rf_conv3_assemble_fwd(const RfConv3AssembleParams* p, void* strea
   RF_CHECK_ARG(p->D % 4 == 0 && p->ldz % 4 == 0 && p->ldy % 4 == 0 && (!p->pe || p->ld_pe % 4 == 0), "rf_conv3_assemble_fwd: D/ld must be multiples of 4");
   const int L_out = p->L + 2 * p->pad - 2;
   const long long total4 = static_cast<long long>(p->n_seq) * L_out * (p->D / 4);
-  conv3_assemble_fwd_kernel<<<blocks_for(total4), TPB, 0, static_cast<cudaStream_t>(stream)>>>(*p, L_out, total4);
-  RF_LAUNCH_OK();
+  RF_CUDA_OK(launch_pdl(conv3_assemble_fwd_kernel, dim3(blocks_for(total4)), dim3(TPB), 0, static_cast<cudaStream_t>(stream), *p, L_out, total4));
   return RF_OK;
 }
 
@@ -515,8 +520,7 @@ extern "C" int rf_conv3_assemble_bwd(const RfConv3AssembleBwdParams* p, void* st
   const int L_out = p->L + 2 * p->pad - 2;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long total4 = static_cast<long long>(p->n_seq) * p->L * 3 * (p->D / 4);
-  conv3_assemble_bwd_kernel<<<blocks_for(total4), TPB, 0, s>>>(*p, L_out, total4);
-  RF_LAUNCH_OK();
+  RF_CUDA_OK(launch_pdl(conv3_assemble_bwd_kernel, dim3(blocks_for(total4)), dim3(TPB), 0, s, *p, L_out, total4));
   const int rows = p->n_seq * L_out;
   if (p->dbias) { launch_colsum(p->dy, p->ldy, rows, p->D, p->dbias, 0, s); RF_LAUNCH_OK(); }
   if (p->dwtime) { launch_colsum(p->dy, p->ldy, rows, p->D, p->dwtime, L_out, s); RF_LAUNCH_OK(); }

@@ -376,6 +376,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // barriers, tensor-map prefetch and the TMEM allocation above overlap the tail of the previous kernel
+  pdl_trigger();
   if (stamps && threadIdx.x == 0) stamps[1] = gtime();
 
   if (warp == 0) {
@@ -586,6 +588,8 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // barriers, tensor-map prefetch and the TMEM allocation above overlap the tail of the previous kernel
+  pdl_trigger();
 
   auto decode = [&](int t, int& m0, int& n0, int& kb_begin, int& nkb) {
     const int nt = t % tiles_n;
@@ -896,8 +900,8 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
     const long long total = static_cast<long long>(tiles_n) * tiles_m * splits;
     RF_CHECK_ARG(total <= 2147483647LL, "rf_gemm_tf32: too many tiles");
     const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
-    gemm_tf32_persistent_kernel<BLOCK_N><<<grid, P_THREADS, PT::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmP, args, tiles_n, tiles_m, splits);
-    RF_LAUNCH_OK();
+    RF_CUDA_OK(launch_pdl(gemm_tf32_persistent_kernel<BLOCK_N>, dim3(grid), dim3(P_THREADS), PT::SMEM_BYTES, stream, tmA, tmB, tmC, tmP, args, tiles_n,
+                          tiles_m, splits));
     return RF_OK;
   }
   if (args.colsum_a) {  // long reductions: the tile-wise kernels have no reducer warp, the column sums take their own pass
@@ -920,8 +924,7 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
       RF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, STAGES_DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD::SMEM_BYTES));
       attr_deep = true;
     }
-    gemm_tf32_kernel<BLOCK_N, STAGES_DEEP><<<grid, NUM_THREADS, TD::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmP, args);
-    RF_LAUNCH_OK();
+    RF_CUDA_OK(launch_pdl(gemm_tf32_kernel<BLOCK_N, STAGES_DEEP>, grid, dim3(NUM_THREADS), TD::SMEM_BYTES, stream, tmA, tmB, tmC, tmP, args));
     return RF_OK;
   }
   static bool attr_set = false;
@@ -929,8 +932,7 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
     RF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, STAGES_SHALLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_tf32_kernel<BLOCK_N, STAGES_SHALLOW><<<grid, NUM_THREADS, T::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmP, args);
-  RF_LAUNCH_OK();
+  RF_CUDA_OK(launch_pdl(gemm_tf32_kernel<BLOCK_N, STAGES_SHALLOW>, grid, dim3(NUM_THREADS), T::SMEM_BYTES, stream, tmA, tmB, tmC, tmP, args));
   return RF_OK;
 }
 

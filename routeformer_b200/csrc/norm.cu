@@ -14,6 +14,8 @@ constexpr int WARPS = 8;
 __global__ void __launch_bounds__(WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
                      float* __restrict__ y, long long ldy, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const bool vec = ((D & 3) == 0) && ((ldx & 3) == 0) && ((ldy & 3) == 0);
@@ -72,6 +74,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      float* __restrict__ dx, long long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int D) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sh[];  // [2*D]: dgamma partial, dbeta partial
   float* sg = sh;
   float* sb = sh + D;
@@ -286,8 +290,8 @@ extern "C" int rf_layernorm_fwd(const float* x, long long ldx, const float* gamm
   RF_CHECK_ARG(x && gamma && beta && y && M > 0 && D > 0 && ldx >= D && ldy >= D, "rf_layernorm_fwd: bad arguments");
   int grid = ceil_div(M, WARPS);
   grid = grid > 148 * 8 ? 148 * 8 : grid;
-  layernorm_fwd_kernel<<<grid, WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, gamma, beta, y, ldy, mean, rstd, M, D);
-  RF_LAUNCH_OK();
+  RF_CUDA_OK(launch_pdl(layernorm_fwd_kernel, dim3(grid), dim3(WARPS * 32), 0, static_cast<cudaStream_t>(stream), x, ldx, gamma, beta, y, ldy, mean, rstd,
+                        M, D));
   return RF_OK;
 }
 
@@ -298,10 +302,10 @@ extern "C" int rf_layernorm_bwd(const float* dy, long long lddy, const float* x,
   grid = grid < 1 ? 1 : (grid > 148 * 4 ? 148 * 4 : grid);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t sm = 2 * D * sizeof(float);
-  if (D <= 64) layernorm_bwd_kernel<2><<<grid, WARPS * 32, sm, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D);
-  else if (D <= 128) layernorm_bwd_kernel<4><<<grid, WARPS * 32, sm, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D);
-  else if (D <= 256) layernorm_bwd_kernel<8><<<grid, WARPS * 32, sm, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D);
-  else if (D <= 1024) layernorm_bwd_kernel<32><<<grid, WARPS * 32, sm, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D);
+  if (D <= 64) RF_CUDA_OK(launch_pdl(layernorm_bwd_kernel<2>, dim3(grid), dim3(WARPS * 32), sm, st, dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D));
+  else if (D <= 128) RF_CUDA_OK(launch_pdl(layernorm_bwd_kernel<4>, dim3(grid), dim3(WARPS * 32), sm, st, dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D));
+  else if (D <= 256) RF_CUDA_OK(launch_pdl(layernorm_bwd_kernel<8>, dim3(grid), dim3(WARPS * 32), sm, st, dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D));
+  else if (D <= 1024) RF_CUDA_OK(launch_pdl(layernorm_bwd_kernel<32>, dim3(grid), dim3(WARPS * 32), sm, st, dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D));
   else { set_error("rf_layernorm_bwd: D=%d > 1024 not supported", D); return RF_ERR_UNSUPPORTED; }
   RF_LAUNCH_OK();
   return RF_OK;
