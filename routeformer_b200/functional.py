@@ -127,12 +127,21 @@ class AttentionBlock(Function):
                           dropout=(drop["p"], *drop["prob"]) if drop and drop.get("prob") else None)
         if meta.get("record") is not None and top is not None:
             meta["record"].append({"where": meta.get("name", ""), "top": top, "measure": measure})
-        y = torch.empty(M, D, device=dev, dtype=torch.float32)
-        if drop:  # x + dropout(out_projection(context))   (cross_modal_transformer.py:224,227,295)
-            ops.gemm(context, wo, y, bias=bo)
-            ops.dropout(y, y, drop["p"], *drop["out"], residual=x)
+        tail = bool(meta.get("tail")) and not drop
+        if tail:
+            # only the LAST token of every sequence is consumed downstream (PerceiveEncoder(out_len=1), cross_modal_transformer.py:433):
+            # project / add the residual for those B rows only; everything after this block then runs on B instead of B*L rows
+            ctx_tail, x_tail = context.view(B, Lq, D)[:, Lq - 1, :], x.view(B, Lq, D)[:, Lq - 1, :]
+            y = torch.empty(B, D, device=dev, dtype=torch.float32)
+            ops.gemm(ctx_tail, wo, y, bias=bo, residual=x_tail)
         else:
-            ops.gemm(context, wo, y, bias=bo, residual=x)
+            y = torch.empty(M, D, device=dev, dtype=torch.float32)
+            if drop:  # x + dropout(out_projection(context))   (cross_modal_transformer.py:224,227,295)
+                ops.gemm(context, wo, y, bias=bo)
+                ops.dropout(y, y, drop["p"], *drop["out"], residual=x)
+            else:
+                ops.gemm(context, wo, y, bias=bo, residual=x)
+        ctx.tail = tail
         ctx.meta = meta
         ctx.params = (wq, bq, wk, bk, wv, bv, wo, bo)
         ctx.self_attn = self_attn
@@ -156,10 +165,16 @@ class AttentionBlock(Function):
             dproj = ops.dropout(dy, torch.empty_like(dy), drop["p"], *drop["out"])
         attn_drop = (drop["p"], *drop["prob"]) if drop and drop.get("prob") else None
         g = grad_buffer(wo)
-        if g is not None:
-            wgrad(dproj, context, g)
-        dcontext = torch.empty(M, D, device=dev, dtype=torch.float32)
-        ops.gemm(dproj, wo, dcontext, b_mn=True, colsum_a=grad_buffer(bo))  # bias gradient from the operand tiles of the dgrad
+        if ctx.tail:  # dy is [B, D]: the gradient of the last-token rows; every other context row has zero gradient
+            if g is not None:
+                wgrad(dproj, context.view(B, Lq, D)[:, Lq - 1, :], g)
+            dcontext = torch.zeros(M, D, device=dev, dtype=torch.float32)
+            ops.gemm(dproj, wo, dcontext.view(B, Lq, D)[:, Lq - 1, :], b_mn=True, colsum_a=grad_buffer(bo))
+        else:
+            if g is not None:
+                wgrad(dproj, context, g)
+            dcontext = torch.empty(M, D, device=dev, dtype=torch.float32)
+            ops.gemm(dproj, wo, dcontext, b_mn=True, colsum_a=grad_buffer(bo))  # bias gradient from the operand tiles of the dgrad
         need_dx = ctx.needs_input_grad[0]
         dx = dcross = None
         if ctx.self_attn:
@@ -190,12 +205,15 @@ class AttentionBlock(Function):
                         ops.colsum_accumulate(dqkv[:, i * D:(i + 1) * D], g)
             if need_dx:
                 dx = torch.empty(M, D, device=dev, dtype=torch.float32)
+                res = None if ctx.tail else dy  # residual branch: all rows, or (tail mode) only the last-token rows, added below
                 if w_all is not None:
-                    ops.gemm(dqkv, w_all, dx, b_mn=True, residual=dy, colsum_a=gb_all if fuse_bias else None)
+                    ops.gemm(dqkv, w_all, dx, b_mn=True, residual=res, colsum_a=gb_all if fuse_bias else None)
                 else:
-                    ops.gemm(dqkv[:, :D], wq, dx, b_mn=True, residual=dy)
+                    ops.gemm(dqkv[:, :D], wq, dx, b_mn=True, residual=res)
                     ops.gemm(dqkv[:, D:2 * D], wk, dx, b_mn=True, residual=dx)
                     ops.gemm(dqkv[:, 2 * D:], wv, dx, b_mn=True, residual=dx)
+                if ctx.tail:
+                    dx.view(B, Lq, D)[:, Lq - 1, :].add_(dy)
         else:
             qb, kvb = proj
             dq, dkv = torch.empty_like(qb), torch.empty_like(kvb)

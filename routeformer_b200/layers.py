@@ -127,14 +127,14 @@ class AttentionLayer(nn.Module):
         self.n_heads = n_heads
         self.informer_layout = informer_layout
 
-    def block(self, x2, cross2, B, Lq, Lk, draw, record=None, name="", p_drop: float = 0.0):
+    def block(self, x2, cross2, B, Lq, Lk, draw, record=None, name="", p_drop: float = 0.0, tail: bool = False):
         """p_drop > 0 (training): `x + dropout(attention(x))` of the calling layer and, for full attention, the dropout on the
         softmax probabilities (cross_modal_transformer.py:63,224,227,295)."""
         kind, factor = self.inner_attention.kind, self.inner_attention.factor
         mode = {"prob": ops.ATTN_PROB, "prob_masked": ops.ATTN_PROB_MASKED, "full": ops.ATTN_FULL}[kind]
         meta = dict(B=B, H=self.n_heads, Lq=Lq, Lk=Lk, mode=mode,
                     layout=ops.LAYOUT_BHLD if self.informer_layout else ops.LAYOUT_BLHD,
-                    U=0, u=0, idx_group=0, record=record, name=name)
+                    U=0, u=0, idx_group=0, record=record, name=name, tail=tail and cross2 is None and not self.informer_layout)
         idx = None
         if kind != "full":
             meta["U"], meta["u"] = sparse_budget(Lk, factor), sparse_budget(Lq, factor)
@@ -167,11 +167,12 @@ class EncoderLayer(nn.Module):
         return {"p": self.p_drop, "hidden": _site(x2.device, self.p_drop, name + ".ffn_hidden", M, dff),
                 "out": _site(x2.device, self.p_drop, name + ".ffn_out", M, D)}
 
-    def run(self, x2, B, L, draw, record=None, name=""):
+    def run(self, x2, B, L, draw, record=None, name="", tail: bool = False):
+        """tail=True (last layer of an encoder whose caller keeps only the last token): returns [B, D] instead of [B*L, D]."""
         if self.attention.informer_layout:
             _no_dropout(self, self.p_drop)
         p = self.p_drop if self.training else 0.0
-        x2 = self.attention.block(x2, None, B, L, L, draw, record, name + ".attention", p)
+        x2 = self.attention.block(x2, None, B, L, L, draw, record, name + ".attention", p, tail=tail and p == 0.0)
         x2 = Fn.LayerNorm.apply(x2, self.norm1.weight, self.norm1.bias)
         x2 = Fn.FFNBlock.apply(x2, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.act, self._ffn_drop(x2, name))
         return Fn.LayerNorm.apply(x2, self.norm2.weight, self.norm2.bias)
@@ -263,9 +264,14 @@ class PerceiveEncoder(nn.Module):
         """x2 [n*L, Cp] (channel-padded) -> [n*min(L,out_len), out_channels]."""
         conv = self.value_embedding.tokenConv
         h = Fn.CircularConv3.apply(x2, conv.weight, conv.bias, self.position_embedding.table(), None, n, L, 1)
+        n_layers = len(self.encoder.attn_layers)
+        tail = False
         for i, layer in enumerate(self.encoder.attn_layers):
-            h = layer.run(h, n, L, draw, record, f"{name}.encoder.attn_layers.{i}")
-        h = _select_tail(h, n, L, self.pred_len)
+            # the frame encoder keeps one token of 65: its last layer computes LayerNorms / FFN / out-projection for that token only
+            tail = i == n_layers - 1 and self.pred_len == 1 and L > 1 and not (layer.training and layer.p_drop > 0.0)
+            h = layer.run(h, n, L, draw, record, f"{name}.encoder.attn_layers.{i}", tail=tail)
+        if not tail:
+            h = _select_tail(h, n, L, self.pred_len)
         h = Fn.LayerNorm.apply(h, self.encoder.norm.weight, self.encoder.norm.bias)
         return Fn.Linear.apply(h, self.projection.weight, self.projection.bias)
 

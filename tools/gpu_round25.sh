@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_model.py -q -m gpu --timeout 300 -p no:cacheprovider 2>&1 | tail -12
+timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v29.log 2>&1; grep "^{" gpurun_out/bench_v29.log | cut -c1-200; tail -2 gpurun_out/bench_v29.log | cut -c1-300
