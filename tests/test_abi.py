@@ -50,3 +50,21 @@ def test_only_sm100a_code_is_shipped():
     out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
+
+
+def test_build_stamp_is_location_independent(tmp_path):
+    """The in-tree library travels with the repository snapshot to the GPU box, where the tree sits under another path: the
+    freshness stamp must depend on file contents only, or every rank of a torchrun launch would rebuild (and race on) the .so."""
+    import glob
+    import os
+    import shutil
+
+    from routeformer_b200 import build as B
+
+    src = sorted(glob.glob(os.path.join(B.CSRC, "*.cu")) + glob.glob(os.path.join(B.CSRC, "*.cuh")))
+    copy_dir = tmp_path / "elsewhere" / "csrc"
+    copy_dir.mkdir(parents=True)
+    copies = [shutil.copy(p, copy_dir / os.path.basename(p)) for p in src]
+    assert B._digest(src) == B._digest([str(c) for c in copies])
+    (copy_dir / os.path.basename(src[0])).write_text("// changed")
+    assert B._digest(src) != B._digest([str(c) for c in copies])
