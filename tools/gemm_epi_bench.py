@@ -18,6 +18,7 @@ x = torch.randn(M, D, device=DEV); w1 = torch.randn(F, D, device=DEV) / 11; b1 =
 h = torch.empty(M, F, device=DEV); pre = torch.empty(M, F, device=DEV)
 dy = torch.randn(M, D, device=DEV); w2 = torch.randn(D, F, device=DEV) / 16; dpre = torch.empty(M, F, device=DEV)
 res = torch.randn(M, D, device=DEV); y = torch.empty(M, D, device=DEV); b2 = torch.randn(D, device=DEV)
+gb1 = torch.zeros(F, device=DEV); gb2 = torch.zeros(D, device=DEV)
 cases = {
     "ffn1 plain                 ": lambda: ops.gemm(x, w1, h),
     "ffn1 +bias                 ": lambda: ops.gemm(x, w1, h, bias=b1),
@@ -30,6 +31,10 @@ cases = {
     "dgrad +dgelu(aux)          ": lambda: ops.gemm(dy, w2, dpre, b_mn=True, dact=ops.ACT_GELU, dact_aux=pre),
     "dgrad *saved(aux)          ": lambda: ops.gemm(dy, w2, dpre, b_mn=True, dact=ops.DACT_SAVED, dact_aux=pre),
     "dgrad +drelu(aux)          ": lambda: ops.gemm(dy, w2, dpre, b_mn=True, dact=ops.ACT_RELU, dact_aux=h),
+    "dgrad *saved(aux) +colsum_a": lambda: ops.gemm(dy, w2, dpre, b_mn=True, dact=ops.DACT_SAVED, dact_aux=pre, colsum_a=gb2),
+    "dx dgrad +residual         ": lambda: ops.gemm(dpre, w1, y, b_mn=True, residual=res),
+    "dx dgrad +residual+colsum_a": lambda: ops.gemm(dpre, w1, y, b_mn=True, residual=res, colsum_a=gb1),
+    "separate colsum [M,256]    ": lambda: ops.colsum_accumulate(dpre, gb1),
 }
 for name, fn in cases.items():
     print(f"{name} {timeit(fn):8.1f} us", flush=True)
