@@ -175,6 +175,9 @@ typedef struct {
   const int* forced_top;   /* optional in [B,H,u]: use this selection instead (test hook) */
   float dropout_p;         /* RF_ATTN_FULL only: dropout on the softmax probabilities (cross_modal_transformer.py:63), 0 = off */
   unsigned long long dropout_seed, dropout_offset; /* mask = rf_dropout's for a [B*H*Lq, Lk] tensor with the same seed / offset */
+  int tail_only;           /* hint: the caller consumes only the context of the LAST query of every sequence (PerceiveEncoder with
+                              out_len = 1, cross_modal_transformer.py:433).  Forward: rows 0..Lq-2 of `out` may be left unwritten
+                              (top / measure are complete).  Backward: rows 0..Lq-2 of `dout` are taken as zero and not read. */
 } RfAttnParams;
 int rf_attention_fwd(const RfAttnParams* p, void* stream);
 typedef struct {

@@ -68,6 +68,7 @@ class RfAttnParams(C.Structure):
         ("idx", c_fp), ("idx_group", C.c_int), ("U", C.c_int), ("u", C.c_int),
         ("out", c_fp), ("top", c_fp), ("measure", c_fp), ("forced_top", c_fp),
         ("dropout_p", C.c_float), ("dropout_seed", C.c_ulonglong), ("dropout_offset", C.c_ulonglong),
+        ("tail_only", C.c_int),
     ]
 
 

@@ -507,6 +507,49 @@ __device__ __forceinline__ void warp_column_sum(const float* src, int L, float* 
   }
   if (lane < DH4) reinterpret_cast<float4*>(acc)[lane] = part;
 }
+// One warp: acc[0:DH] = sum_l w[l] * src[l][0:DH] (dense [L][DH] rows, weights in shared memory); fixed reduction order.
+template <int DH>
+__device__ __forceinline__ float4 warp_weighted_column_sum(const float* src, const float* w, int L) {
+  constexpr int DH4 = DH / 4, G = 32 / DH4;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / DH4, c = lane - g * DH4;
+  float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = g; l < L; l += G) {
+    const float wl = w[l];
+    const float4 v = reinterpret_cast<const float4*>(src)[l * DH4 + c];
+    part.x = fmaf(wl, v.x, part.x); part.y = fmaf(wl, v.y, part.y); part.z = fmaf(wl, v.z, part.z); part.w = fmaf(wl, v.w, part.w);
+  }
+#pragma unroll
+  for (int off = DH4; off < 32; off <<= 1) {
+    part.x += __shfl_xor_sync(0xffffffffu, part.x, off); part.y += __shfl_xor_sync(0xffffffffu, part.y, off);
+    part.z += __shfl_xor_sync(0xffffffffu, part.z, off); part.w += __shfl_xor_sync(0xffffffffu, part.w, off);
+  }
+  return part;  // valid in every lane; lane c < DH4 holds channels 4c..4c+3
+}
+// in-place softmax of one probability row by one warp (Lk <= 96); returns nothing, row[j] = softmax(scale * row)[j]
+__device__ __forceinline__ void warp_softmax_row(float* row, int Lk, float scale) {
+  const int lane = threadIdx.x & 31;
+  float sc[3];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int j = lane + 32 * t;
+    sc[t] = j < Lk ? row[j] * scale : -INFINITY;
+    mx = fmaxf(mx, sc[t]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    sc[t] = (lane + 32 * t < Lk) ? __expf(sc[t] - mx) : 0.f;
+    sum += sc[t];
+  }
+  const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+    if (lane + 32 * t < Lk) row[lane + 32 * t] = sc[t] * inv;
+}
+
 // out[rows of one 4-row tile][4c..4c+3] = sum_j W[row][j] * X[j][4c..4c+3]: the X row is loaded once per j for four output rows
 // (a shared-memory load costs one wavefront per 128 B quarter-warp whether or not lanes coincide, so operand re-use in
 // registers is the only way to cut shared-memory traffic).  wrow[k] = shared row of weights of output row k (clamped rows repeat).
@@ -640,8 +683,28 @@ __global__ void __launch_bounds__(THREADS, 7) attention_small_fwd_kernel(const R
   if (p.top)
     for (int r = threadIdx.x; r < u; r += THREADS) p.top[bh * u + r] = s_top[r];
 
-  // selected rows: probabilities in place (one warp per row, registers + shuffles)
   const float scale = rsqrtf(static_cast<float>(DH));
+  if (p.tail_only) {
+    // only the last query's context is consumed: one probability row (if that query was selected) or mean(V)
+    const int last = Lq - 1;
+    if (warp == 0) {
+      float4 o;
+      if (s_sel[last] >= 0) {  // warp-uniform
+        float* row = s_s + last * Lk;
+        warp_softmax_row(row, Lk, scale);
+        __syncwarp();
+        o = warp_weighted_column_sum<DH>(s_v, row, Lk);
+      } else {
+        const float inv = 1.f / Lk;
+        const float4 a4 = reinterpret_cast<const float4*>(s_acc)[lane < DH4 ? lane : 0];
+        o = make_float4(a4.x * inv, a4.y * inv, a4.z * inv, a4.w * inv);
+      }
+      if (lane < DH4) *reinterpret_cast<float4*>(p.out + out_offset(p, b, h, last) + 4 * lane) = o;
+    }
+    return;
+  }
+
+  // selected rows: probabilities in place (one warp per row, registers + shuffles)
   for (int r = warp; r < u; r += NWARPS) {
     float* row = s_s + s_top[r] * Lk;
     float sc[3];
@@ -717,6 +780,75 @@ __global__ void __launch_bounds__(THREADS, 7) attention_small_bwd_kernel(const R
   const float* gv = p.v + b * p.v_bs + h * DH;
   const long long bh = static_cast<long long>(b) * p.H + h;
   const int tail_start = min(Lk, NT * 32), tail = Lk - tail_start;
+
+  if (p.tail_only) {
+    // Only the last query's context carried a gradient.  If that query was not selected its context was mean(V):
+    // dV[j] = dO / Lk, dQ = dK = 0.  If it was, a single probability row is involved: everything is O(Lk * dh).
+    const int last = Lq - 1;
+    float* dq = bp.dq + b * p.q_bs + h * DH;
+    float* dk = bp.dk + b * p.k_bs + h * DH;
+    float* dv = bp.dv + b * p.v_bs + h * DH;
+    const float inv_lk = 1.f / Lk;
+    if (threadIdx.x == 0) s_sel[0] = -1;
+    if (threadIdx.x < DH4) reinterpret_cast<float4*>(s_acc)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(bp.dout + out_offset(p, b, h, last)) + threadIdx.x);
+    __syncthreads();
+    for (int r = threadIdx.x; r < u; r += THREADS)
+      if (p.top[bh * u + r] == last) s_sel[0] = r;
+    __syncthreads();
+    const bool selected = s_sel[0] >= 0;  // CTA-uniform
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < (Lq - (selected ? 1 : 0)) * DH4; i += THREADS) {  // dQ rows without a gradient
+      const int l = i / DH4, c = i - l * DH4;
+      *reinterpret_cast<float4*>(dq + static_cast<long long>(l) * p.q_ls + 4 * c) = zero4;
+    }
+    if (!selected) {
+      for (int i = threadIdx.x; i < Lk * DH4; i += THREADS) {
+        const int j = i / DH4, c = i - j * DH4;
+        const float4 g4 = reinterpret_cast<const float4*>(s_acc)[c];
+        *reinterpret_cast<float4*>(dk + static_cast<long long>(j) * p.k_ls + 4 * c) = zero4;
+        *reinterpret_cast<float4*>(dv + static_cast<long long>(j) * p.v_ls + 4 * c) = make_float4(g4.x * inv_lk, g4.y * inv_lk, g4.z * inv_lk, g4.w * inv_lk);
+      }
+      return;
+    }
+    stage_rows<DH>(s_k, gk, p.k_ls, Lk);
+    if (threadIdx.x < DH4) reinterpret_cast<float4*>(s_q)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(gq + static_cast<long long>(last) * p.q_ls) + threadIdx.x);
+    __syncthreads();
+    {
+      RegRow<DH> qr, dor;
+      qr.load(s_q, true);
+      dor.load(s_acc, true);
+      for (int j = threadIdx.x; j < Lk; j += THREADS) {  // raw scores and dP of the one row
+        RegRow<DH> kt, vt;
+        kt.load(s_k + j * DH, true);
+        vt.load(gv + static_cast<long long>(j) * p.v_ls, true);
+        s_p[j] = kt.dot(qr);
+        s_ds[j] = vt.dot(dor);
+      }
+    }
+    __syncthreads();
+    const float scale = rsqrtf(static_cast<float>(DH));
+    if (warp == 0) {
+      warp_softmax_row(s_p, Lk, scale);
+      __syncwarp();
+      float acc = 0.f;
+      for (int j = lane; j < Lk; j += 32) acc = fmaf(s_p[j], s_ds[j], acc);
+      acc = warp_sum(acc);
+      for (int j = lane; j < Lk; j += 32) s_ds[j] = s_p[j] * (s_ds[j] - acc) * scale;
+    }
+    __syncthreads();
+    if (warp == 0) {  // dQ[last] = dS K
+      const float4 o = warp_weighted_column_sum<DH>(s_k, s_ds, Lk);
+      if (lane < DH4) *reinterpret_cast<float4*>(dq + static_cast<long long>(last) * p.q_ls + 4 * lane) = o;
+    }
+    for (int i = threadIdx.x; i < Lk * DH4; i += THREADS) {  // dK[j] = dS[j] q_last, dV[j] = P[j] dO_last
+      const int j = i / DH4, c = i - j * DH4;
+      const float4 q4 = reinterpret_cast<const float4*>(s_q)[c], g4 = reinterpret_cast<const float4*>(s_acc)[c];
+      const float ws = s_ds[j], wp = s_p[j];
+      *reinterpret_cast<float4*>(dk + static_cast<long long>(j) * p.k_ls + 4 * c) = make_float4(ws * q4.x, ws * q4.y, ws * q4.z, ws * q4.w);
+      *reinterpret_cast<float4*>(dv + static_cast<long long>(j) * p.v_ls + 4 * c) = make_float4(wp * g4.x, wp * g4.y, wp * g4.z, wp * g4.w);
+    }
+    return;
+  }
 
   stage_rows<DH>(s_q, gq, p.q_ls, Lq);
   stage_rows<DH>(s_k, gk, p.k_ls, Lk);

@@ -124,7 +124,8 @@ class AttentionBlock(Function):
         drop = meta.get("drop")  # training-mode feature dropout: {"p", "out": (seed, off), "prob": (seed, off) | None}
         ops.attention_fwd(q, k, v, B, H, Lq, Lk, dh, meta["mode"], meta["layout"], idx, meta["idx_group"], meta["U"], u, context, top,
                           measure=measure, forced_top=meta.get("forced_top"),
-                          dropout=(drop["p"], *drop["prob"]) if drop and drop.get("prob") else None)
+                          dropout=(drop["p"], *drop["prob"]) if drop and drop.get("prob") else None,
+                          tail_only=bool(meta.get("tail")) and not drop)
         if meta.get("record") is not None and top is not None:
             meta["record"].append({"where": meta.get("name", ""), "top": top, "measure": measure})
         tail = bool(meta.get("tail")) and not drop
@@ -184,7 +185,7 @@ class AttentionBlock(Function):
             k = (qkv[:, D:], Lk * 3 * D, 3 * D)
             v = (qkv[:, 2 * D:], Lk * 3 * D, 3 * D)
             ops.attention_bwd(q, k, v, B, H, Lq, Lk, dh, meta["mode"], meta["layout"], meta["U"], meta["u"], top, dcontext,
-                              dqkv, dqkv[:, D:], dqkv[:, 2 * D:], dropout=attn_drop)
+                              dqkv, dqkv[:, D:], dqkv[:, 2 * D:], dropout=attn_drop, tail_only=ctx.tail)
             w_all = _fused(wq, wk, wv)
             gw_all, gb_all = _fused_grads(wq, wk, wv), _fused_grads(bq, bk, bv)
             if gw_all is not None:

@@ -204,19 +204,24 @@ def _set_attn_dropout(p, dropout):
         p.dropout_p, p.dropout_seed, p.dropout_offset = float(dropout[0]), int(dropout[1]), int(dropout[2])
 
 
-def attention_fwd(q, k, v, B, H, Lq, Lk, dh, mode, layout, idx, idx_group, U, u, out, top, measure=None, forced_top=None, dropout=None):
-    """dropout = (p, seed, offset): probability dropout, full attention only."""
+def attention_fwd(q, k, v, B, H, Lq, Lk, dh, mode, layout, idx, idx_group, U, u, out, top, measure=None, forced_top=None, dropout=None,
+                  tail_only: bool = False):
+    """dropout = (p, seed, offset): probability dropout, full attention only.  tail_only: only the last query's context is needed
+    (the other rows of `out` may stay unwritten)."""
     p = _attn_params(q, k, v, B, H, Lq, Lk, dh, mode, layout, idx, idx_group, U, u, out, top, measure, forced_top)
     _set_attn_dropout(p, dropout)
+    p.tail_only = int(tail_only)
     check(_lib.load().rf_attention_fwd(C.byref(p), _stream()), "rf_attention_fwd")
     _count()
     return out
 
 
-def attention_bwd(q, k, v, B, H, Lq, Lk, dh, mode, layout, U, u, top, dout, dq, dk, dv, dropout=None):
+def attention_bwd(q, k, v, B, H, Lq, Lk, dh, mode, layout, U, u, top, dout, dq, dk, dv, dropout=None, tail_only: bool = False):
+    """tail_only: rows 0..Lq-2 of `dout` are zero by construction and need not be read."""
     bp = _lib.RfAttnBwdParams()
     bp.f = _attn_params(q, k, v, B, H, Lq, Lk, dh, mode, layout, None, 0, U, u, None, top, None, None)
     _set_attn_dropout(bp.f, dropout)
+    bp.f.tail_only = int(tail_only)
     bp.dout, bp.dq, bp.dk, bp.dv = _ptr(dout), _ptr(dq), _ptr(dk), _ptr(dv)
     check(_lib.load().rf_attention_bwd(C.byref(bp), _stream()), "rf_attention_bwd")
     _count()

@@ -335,6 +335,40 @@ def test_attention_forward_backward(ops, B, H, Lq, Lk, dh, factor, mode, layout)
     assert rel_err(dqkv_k.cpu()[:, 2 * D:].reshape(B, Lk, H, dh), v.grad) < 2e-5
 
 
+@pytest.mark.parametrize("B,H,L,dh", [(6, 8, 65, 16), (4, 4, 40, 8), (3, 2, 20, 16)])
+def test_attention_last_query_only(ops, B, H, L, dh):
+    """tail_only: the caller keeps the last query's context only (PerceiveEncoder(out_len=1)); forward writes that row, the
+    backward treats every other row of dout as zero.  Both the selected and the mean-filled case occur over the (b, h) problems."""
+    gen = g(L + dh)
+    factor, D = 5, H * dh
+    q, k, v = (torch.randn(B, L, H, dh, generator=gen).requires_grad_() for _ in range(3))
+    U = u = O.sparse_budget(L, factor)
+    idx = torch.randint(L, (L, U), generator=gen)
+    ctx, tops, _ = O.prob_attention(q, k, v, idx, factor, False)
+    ref = ctx.transpose(1, 2)  # [B, L, H, dh]
+    selected_last = (tops == L - 1).any(-1)
+    assert selected_last.any() and (~selected_last).any()  # both code paths are exercised
+    dlast = torch.randn(B, H, dh, generator=gen)
+    dout = torch.zeros(B, L, H, dh)
+    dout[:, L - 1] = dlast
+    ref.backward(dout)
+    mk = lambda t: (t.detach().reshape(B * L, D).to(DEV), L * D, D)
+    out = torch.full((B, L, H, dh), float("nan"), device=DEV)
+    top = torch.zeros(B, H, u, dtype=torch.int32, device=DEV)
+    ops.attention_fwd(mk(q), mk(k), mk(v), B, H, L, L, dh, ops.ATTN_PROB, ops.LAYOUT_BLHD, idx.int().to(DEV), 0, U, u, out, top,
+                      tail_only=True)
+    assert torch.equal(top.cpu().long().sort(-1).values, tops.sort(-1).values)
+    assert rel_err(out[:, L - 1].cpu(), ref[:, L - 1].detach()) < 1e-5
+    dq, dk, dv = (torch.full((B * L, D), float("nan"), device=DEV) for _ in range(3))
+    garbage = torch.full((B, L, H, dh), float("nan"))  # rows other than the last must not be read
+    garbage[:, L - 1] = dlast
+    ops.attention_bwd(mk(q), mk(k), mk(v), B, H, L, L, dh, ops.ATTN_PROB, ops.LAYOUT_BLHD, U, u, top, garbage.to(DEV), dq, dk, dv,
+                      tail_only=True)
+    assert rel_err(dq.cpu().view(B, L, H, dh), q.grad) < 2e-5
+    assert rel_err(dk.cpu().view(B, L, H, dh), k.grad) < 2e-5
+    assert rel_err(dv.cpu().view(B, L, H, dh), v.grad) < 2e-5
+
+
 def test_attention_forced_selection(ops):
     B, H, L, dh, factor = 2, 4, 21, 16, 4
     gen = g(5)
