@@ -187,6 +187,7 @@ def run_ours(args):
         loss_t = trainer.step(b, t)
         prefetch.release(b)
         prefetch.submit(pinned, pinned_t)
+        trainer.prefetch_draws()  # host RNG work of the next step, hidden behind this step's device time
         return loss_t.item()
 
     prefetch.submit(pinned, pinned_t)

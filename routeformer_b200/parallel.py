@@ -131,11 +131,18 @@ class DataParallelTrainer:
                     dst.copy_(src, non_blocking=True)
         if self._replayed is not None:
             self._replayed.synchronize()  # the previous replay has consumed the pinned index buffer
-        self.model.prepare_draws(self.static_batch, refill_only=True)  # host only: this step's CPU random draws
+        if not self.model.commit_deferred_draws():  # draws made ahead of time by prefetch_draws(), else made now
+            self.model.prepare_draws(self.static_batch, refill_only=True)  # host only: this step's CPU random draws
         self._graph.replay()
         self._replayed = torch.cuda.Event()
         self._replayed.record()
         return self._static_loss
+
+    def prefetch_draws(self) -> None:
+        """Optional: makes the NEXT step's CPU random draws now (same order of the CPU RNG stream), while the current replay is
+        still running on the device, so that the next `step` only has to copy them into the pinned buffer and launch."""
+        if self._graph is not None and not self.model._deferred_tables:
+            self.model.prepare_draws(self.static_batch, refill_only="defer")
 
     def broadcast_parameters(self, src: int = 0) -> None:
         if self.world > 1:

@@ -84,6 +84,7 @@ class Routeformer(nn.Module):
         self.record_tops: Optional[list] = None
         self.last_draw_log: List[tuple] = []
         self._idx_slots = {}
+        self._deferred_tables: list = []
         self._pending_plan = None
 
     @property
@@ -219,6 +220,9 @@ class Routeformer(nn.Module):
                 host = host.pin_memory()
             self._idx_slots[key] = (host, torch.empty(n, dtype=torch.int32, device=device))
         host, dev = self._idx_slots[key]
+        if refill_only == "defer":  # draw now, write the pinned buffer later (commit_deferred_draws): it may still be in use
+            self._deferred_tables.append((host, torch.cat([t.reshape(-1) for t in tables]).to(torch.int32)))
+            return []
         off = 0
         for t in tables:
             host[off:off + t.numel()].copy_(t.reshape(-1))
@@ -232,11 +236,20 @@ class Routeformer(nn.Module):
             off += t.numel()
         return out
 
-    def prepare_draws(self, batch, training: bool = None, refill_only: bool = False, backbone: bool = True):
+    def commit_deferred_draws(self) -> bool:
+        """Writes the tables drawn by `prepare_draws(refill_only="defer")` into the pinned buffers the captured graph copies from."""
+        pending, self._deferred_tables = self._deferred_tables, []
+        for host, flat in pending:
+            host.copy_(flat)
+        return bool(pending)
+
+    def prepare_draws(self, batch, training: bool = None, refill_only=False, backbone: bool = True):
         """Makes every CPU random draw of one (non-autoregressive) forward, in reference order, and stages the index tables.
 
         Called implicitly by `preprocess_batch` / `_forward`; called explicitly with `refill_only=True` before replaying a
-        captured CUDA graph of the step (the graph contains the H2D copy, the host only has to refresh the pinned buffer)."""
+        captured CUDA graph of the step (the graph contains the H2D copy, the host only has to refresh the pinned buffer), or
+        with `refill_only="defer"` while the previous replay is still running (the draws are made now, in order, and reach
+        the pinned buffer through `commit_deferred_draws` once that replay has consumed it)."""
         if training is None:
             training = self.training
         dev = batch["gps"].device

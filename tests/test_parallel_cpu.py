@@ -98,3 +98,24 @@ def test_arena_round_trip_and_grad_reattach():
     assert g is not None and g.data_ptr() == arena.grad.data_ptr() + 4 * arena.offsets[id(att.out_projection.weight)]
     model.load_state_dict(O.fill_state_dict(sd, 99))  # in-place copy keeps the arena
     assert arena.valid()
+
+
+def test_deferred_draws_fill_the_same_pinned_tables():
+    """prepare_draws(refill_only="defer") + commit_deferred_draws() == prepare_draws(refill_only=True): same CPU RNG order, same
+    staging-buffer contents, and nothing is written before the commit (the previous graph replay may still read the buffer)."""
+    import torch
+
+    from tests.helpers import build_product, case_from_golden, load_golden
+
+    cfg, spec, sd, batch = case_from_golden(load_golden("full_small_train"))
+    model = build_product(cfg, spec)
+    torch.manual_seed(5)
+    model.prepare_draws(batch, training=True, refill_only=True)
+    ref = {k: v[0].clone() for k, v in model._idx_slots.items()}
+    for v in model._idx_slots.values():
+        v[0].zero_()
+    torch.manual_seed(5)
+    model.prepare_draws(batch, training=True, refill_only="defer")
+    assert all(bool((v[0] == 0).all()) for v in model._idx_slots.values())
+    assert model.commit_deferred_draws() and not model.commit_deferred_draws()
+    assert ref and all(torch.equal(ref[k], v[0]) for k, v in model._idx_slots.items())
