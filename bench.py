@@ -348,7 +348,7 @@ def run_ours(args):
         line = {
             "metric": "routeformer_fwd_bwd_clips_per_sec", "value": round(value, 2), "unit": "clips/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate; fp16 operands in the patch embedding like the reference's autocast backbone)", "data": "synthetic",
             "config": {"workload": "Routeformer GPS+scene video+gaze FoV training step (fwd+loss+bwd+allreduce+clip+AdamW), "
                                    "paper config, random-init patch backbone 256^2/p32/C1024, GEM-shaped clips",
                        "global_batch": world * B, "batch_per_gpu": B, "parallelism": f"dp{world}", "fov": args.fov,
