@@ -75,7 +75,7 @@ typedef struct {
 int rf_fov_crop(const RfFovCropParams* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * (2) TF32 tensor-core GEMM (tcgen05.mma kind::tf32, TMA-fed, TMEM accumulators, fp32 accumulate)
+ * (2) Tensor-core GEMM (tcgen05.mma kind::tf32, or kind::f16 for fp16 operands; TMA-fed, TMEM accumulators, fp32 accumulate)
  * replaces: every aten::addmm / mm / 1x1 aten::convolution on the path:
  *           cross_modal_transformer.py:177-198,297-299,356-368; SelfAttentionFamily.py:176-194;
  *           TransformerEncoderDecoder.py:12-18,48-50; Embedding.py:32-45; and their autograd.
@@ -97,7 +97,7 @@ typedef struct {
   int act;                                   /* RF_ACT_*; applied after bias/rowadd/residual */
   float* preact; long long ld_pre;           /* if non-NULL the pre-activation value is also stored here */
   const float* dact_aux; long long ld_aux; int dact; /* if dact!=0: result *= act'(dact_aux[m][n]) (RELU: aux>0) */
-  int accumulate;                            /* 1: C += result with fp32 atomics (C must be initialised) */
+  int accumulate;                            /* 1: C += result (TMA reduce-add in L2, or fp32 atomics for unaligned C); C must be initialised */
   int split_k;                               /* 0 = auto: >1 for accumulate=1 (wgrad), and for few-tile / long-K GEMMs whose epilogue is
                                                 linear (bias, rowadd, residual): output zero-filled, split 0 adds the linear terms,
                                                 splits meet in fp32 reduce-adds (order not fixed).  -1 = auto, but bit-reproducible:
