@@ -1,19 +1,25 @@
-// TF32 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
-// tcgen05.mma.kind::tf32 (one elected thread) -> fp32 accumulators in TMEM -> tcgen05.ld epilogue.
+// Tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
+// tcgen05.mma.kind::tf32 (or kind::f16 for fp16 operands), issued by one elected thread -> fp32 accumulators in
+// TMEM -> tcgen05.ld epilogue -> swizzled shared memory -> TMA bulk store / reduce-add.
 //
 //   C[M,N] (+)= epilogue( sum_k A[m,k] * B[n,k] )
 //
 // Either operand may be K-major (reduction dim contiguous) or MN-major (the other dim contiguous), so the
-// same kernel serves forward (x W^T), dgrad (dy W) and wgrad (dy^T x, split over the long reduction with
-// fp32 atomics into the gradient arena).  Operands stay fp32 in HBM; the TMA descriptor (TFLOAT32 type)
+// same kernels serve forward (x W^T), dgrad (dy W) and wgrad (dy^T x, split over the long reduction and
+// reduce-added into the gradient arena).  fp32 operands stay fp32 in HBM; the TMA descriptor (TFLOAT32 type)
 // rounds them to tf32 on the way into shared memory, accumulation is fp32.
 //
-// CTA = 128 threads, one 128 x BLOCK_N output tile, 2 CTAs resident per SM (one CTA's epilogue overlaps
-// the other's main loop):
-//   warp 0 / lane 0 : TMA producer over a STAGES-deep full/empty mbarrier ring
-//   warp 1 / lane 0 : tcgen05.mma issuer, tcgen05.commit releases ring slots and signals the epilogue
-//   warp 2          : TMEM allocate / free
-//   all 4 warps     : epilogue, thread t owns accumulator row t (TMEM lane t)
+// Two kernels share the pipeline pieces and the epilogue (RowEpilogue):
+//  * gemm_tf32_kernel<BLOCK_N, STAGES>: one 128 x BLOCK_N tile per CTA, 128 threads.
+//      warp 0 / lane 0 : TMA producer over a STAGES-deep full/empty mbarrier ring
+//      warp 1 / lane 0 : tcgen05.mma issuer, tcgen05.commit releases ring slots and signals the epilogue
+//      warp 2          : TMEM allocate / free;   all 4 warps: epilogue, thread t owns accumulator row t
+//    3 stages x 2 CTAs per SM for long reductions on big grids, 6 stages x 1 CTA per SM below one wave.
+//  * gemm_tf32_persistent_kernel<BLOCK_N>: one CTA per SM loops over tiles (<= 12 k-blocks per tile):
+//      producer warp, MMA warp, 8 epilogue warps on a double-buffered TMEM accumulator, and a reducer warp
+//      that sums the A tiles column-wise from shared memory (bias gradients ride on the dgrad GEMMs).
+// Host side (rf_gemm_tf32): tensor maps, kernel choice, automatic split-K (wgrad; few-tile / long-K calls
+// with a linear epilogue), programmatic dependent launch.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
