@@ -13,6 +13,10 @@
 //     rows are padded to dh+4 floats (16 B aligned, conflict-free for 128-bit shared loads);
 //   * no integer division by run-time values in inner loops: work is walked as (warp -> row, lane -> column);
 //   * scores + softmax of one selected query stay in the registers of one warp (shuffle reductions), P is written once.
+//
+// Two families: the generic kernels (any mode, L <= 256, any dh) described above, and -- further down -- register-blocked
+// kernels for the small ProbSparse problems that dominate the step (frame encoder: L = 65, dh = 16), with a last-query-only
+// variant for the encoder layer whose caller keeps one token.  Full attention optionally drops probabilities (Philox mask).
 #include <cstdlib>
 
 #include "common.cuh"
