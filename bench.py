@@ -321,6 +321,7 @@ def run_ours(args):
                     "bound": dom, "achieved": round(achieved, 1), "peak": peak, "unit": unit, "frac": round(achieved / peak, 4),
                     "traffic": traffic, "peak_source": src, "launches": n, "avg_launch_us": round(1e3 * ms_f / n, 2),
                     "algorithmic_bytes_per_launch": round(by / n), "algorithmic_flops_per_launch": round(fl / n),
+                    "share_of_step": round(ms_f / (ms / args.steps), 3),  # replayed launch time / timed step (compare with the ncu list)
                     "timing": "the step's own launches (same tensors and arguments), replayed back to back after the step with one CUDA "
                               "event pair per launch on the launching stream; launches below 8 us at the roofline are left out"}
         if "fov_crop" in kernels:
