@@ -43,7 +43,13 @@ CASES = {
     "autoregressive_dreyeve_small": ({**SMALL, "rotate_motion": True, "autoregressive": True, "autoregressive_step_size": 15},
                                      SMALL_SPEC, "tiny", 3, 15, 16, "eval"),
     "sparse_small": ({**SMALL, "dense_prediction": False, "decoder_mode": "vanilla"}, SMALL_SPEC, "tiny", 2, 11, 12, "eval"),
+    # round 2: the configurations BASELINE.json benches, at their own sizes
+    "full_paper_train": (PAPER_FULL, PAPER_SPEC, "gem", 8, 3, 5, "train"),        # configs[2] per-GPU shard shape, B = 8
+    "full_paper_b64_eval": (PAPER_FULL, PAPER_SPEC, "gem", 64, 3, 6, "eval"),     # configs[1]: batch 64 forward
+    "dreyeve_paper_eval": ({**PAPER_FULL, "rotate_motion": True}, PAPER_SPEC, "dreyeve", 2, 3, 7, "eval"),  # configs[3] shapes
 }
+# gradients of tensors up to this many elements are stored in full (the paper-size model keeps the fixture small)
+GRAD_SMALL_MAX = {"full_paper_train": 1024}
 
 
 class DrawLog:
@@ -107,7 +113,7 @@ def generate(name):
         gold["grad_norm"] = {k: p.grad.norm().item() for k, p in model.named_parameters() if p.grad is not None}
         gold["grad_none"] = [k for k, p in model.named_parameters() if p.grad is None]
         gold["grad_small"] = {k: p.grad.clone() for k, p in model.named_parameters()
-                              if p.grad is not None and p.numel() <= 8192}
+                              if p.grad is not None and p.numel() <= GRAD_SMALL_MAX.get(name, 8192)}
         new_sd = model.state_dict()
         gold["bn"] = {k: new_sd[k].clone() for k in new_sd if "running_" in k or "num_batches" in k}
     os.makedirs(OUT, exist_ok=True)

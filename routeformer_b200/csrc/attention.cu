@@ -1070,17 +1070,10 @@ static int validate(const RfAttnParams* p, const char* who, bool forward) {
   return RF_OK;
 }
 
-// Opt-in to > 48 KiB of dynamic shared memory once per kernel (not per launch: keeps launches capturable in CUDA graphs).
 template <typename K>
 static int configure(K kernel, size_t smem) {
-  static const void* configured[16] = {nullptr};
-  static int n_configured = 0;
   if (smem <= 48 * 1024) return RF_OK;
-  const void* key = reinterpret_cast<const void*>(kernel);
-  for (int i = 0; i < n_configured; ++i)
-    if (configured[i] == key) return RF_OK;
-  RF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  if (n_configured < 16) configured[n_configured++] = key;
+  RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), 220 * 1024));
   return RF_OK;
 }
 
@@ -1091,7 +1084,7 @@ static int configure(K kernel, size_t smem) {
   {                                                                                \
     rc = attn::configure(attn::KERNEL<DHT>, SMEM);                                 \
     if (rc != RF_OK) return rc;                                                    \
-    rf::launch_pdl(attn::KERNEL<DHT>, dim3(GRID), dim3(attn::THREADS), SMEM, STREAM, ARG); \
+    RF_CUDA_OK(rf::launch_pdl(attn::KERNEL<DHT>, dim3(GRID), dim3(attn::THREADS), SMEM, STREAM, ARG)); \
   }
 #define RF_ATTN_DISPATCH(KERNEL, ARG, DHVAL, GRID, SMEM, STREAM)                   \
   switch (DHVAL) {                                                                 \
@@ -1105,7 +1098,7 @@ static int configure(K kernel, size_t smem) {
   {                                                                                \
     rc = attn::configure(attn::KERNEL<DHT, NTT>, SMEM);                            \
     if (rc != RF_OK) return rc;                                                    \
-    rf::launch_pdl(attn::KERNEL<DHT, NTT>, dim3(GRID), dim3(attn::THREADS), SMEM, STREAM, ARG); \
+    RF_CUDA_OK(rf::launch_pdl(attn::KERNEL<DHT, NTT>, dim3(GRID), dim3(attn::THREADS), SMEM, STREAM, ARG)); \
   }
 #define RF_ATTN_SMALL_NT(KERNEL, DHT, ARG, NTVAL, GRID, SMEM, STREAM)              \
   switch (NTVAL) {                                                                 \

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/routeformer_b200.h"
 
@@ -52,6 +53,27 @@ inline int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// Opt-in to > 48 KiB of dynamic shared memory, once per (device, kernel): cudaFuncSetAttribute is a per-device setting, and
+// doing it per launch would break CUDA-graph capture.  Thread-safe (autograd's backward threads launch concurrently with the
+// main thread).
+inline cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static const void* done[128][2];
+  static int n_done = 0;
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const void* dkey = reinterpret_cast<const void*>(static_cast<uintptr_t>(dev) + 1);
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < n_done; ++i)
+    if (done[i][0] == kernel && done[i][1] == dkey) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) return e;
+  if (n_done < 128) { done[n_done][0] = kernel; done[n_done][1] = dkey; ++n_done; }
+  return cudaSuccess;
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -898,11 +898,7 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
   // bytes in flight (2 x 3 stages) and measured 25-35 % faster there (profiles/r1_microbench_gemm_*).
   if (persistent && args.kb_per_split <= 12 && !f16) {
     using PT = PTile<BLOCK_N>;
-    static bool attr_p = false;
-    if (!attr_p) {
-      RF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persistent_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT::SMEM_BYTES));
-      attr_p = true;
-    }
+    RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_tf32_persistent_kernel<BLOCK_N>), PT::SMEM_BYTES));
     const long long total = static_cast<long long>(tiles_n) * tiles_m * splits;
     RF_CHECK_ARG(total <= 2147483647LL, "rf_gemm_tf32: too many tiles");
     const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
@@ -925,19 +921,11 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
   // TMA round trip (measured 0.38 us per k-block with 3 stages): give those CTAs the whole SM's shared memory instead.
   if (deep && static_cast<long long>(tiles_n) * tiles_m * splits <= num_sms() && args.kb_per_split > STAGES_SHALLOW) {
     using TD = Tile<BLOCK_N, STAGES_DEEP>;
-    static bool attr_deep = false;
-    if (!attr_deep) {
-      RF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, STAGES_DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD::SMEM_BYTES));
-      attr_deep = true;
-    }
+    RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_tf32_kernel<BLOCK_N, STAGES_DEEP>), TD::SMEM_BYTES));
     RF_CUDA_OK(launch_pdl(gemm_tf32_kernel<BLOCK_N, STAGES_DEEP>, grid, dim3(NUM_THREADS), TD::SMEM_BYTES, stream, tmA, tmB, tmC, tmP, args));
     return RF_OK;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    RF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, STAGES_SHALLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-    attr_set = true;
-  }
+  RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_tf32_kernel<BLOCK_N, STAGES_SHALLOW>), T::SMEM_BYTES));
   RF_CUDA_OK(launch_pdl(gemm_tf32_kernel<BLOCK_N, STAGES_SHALLOW>, grid, dim3(NUM_THREADS), T::SMEM_BYTES, stream, tmA, tmB, tmC, tmP, args));
   return RF_OK;
 }

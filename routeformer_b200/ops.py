@@ -91,7 +91,75 @@ def fov_crop(frames: torch.Tensor, centers: torch.Tensor, windows: torch.Tensor,
     return out
 
 
+# ---- precise mode (parity instrument) ------------------------------------------------------------
+# RF_PRECISE=1 (or `with ops.precise():`) runs every fp32 GEMM as a 3xTF32 split on the SAME tcgen05 kernel:
+#   A = A_hi + A_lo, B = B_hi + B_lo (hi = operand rounded to tf32, lo = the remainder),
+#   A.B^T ~= A_hi.B_hi^T + A_lo.B_hi^T + A_hi.B_lo^T        (dropped term A_lo.B_lo^T ~ 2^-22 relative)
+# which restores fp32-level accuracy (fp32 accumulate throughout).  ProbSparse top-u selection is a discontinuous function of
+# the scores, so the raw (no-replay) comparison against the reference's golden outputs is asserted in this mode, where a
+# TF32 rounding cannot flip a marginal query.  3 launches + two elementwise splits per GEMM: a test mode, not a fast path.
+import os as _os
+
+PRECISE = _os.environ.get("RF_PRECISE", "0") == "1"
+
+
+class precise:
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        global PRECISE
+        self.prev, PRECISE = PRECISE, self.on
+        return self
+
+    def __exit__(self, *exc):
+        global PRECISE
+        PRECISE = self.prev
+
+
+def _tf32_split(t: torch.Tensor):
+    """(hi, lo): hi = t rounded to 10 mantissa bits (round-half-away in magnitude), lo = t - hi (exact in fp32)."""
+    c = t.contiguous()
+    hi = ((c.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return hi, c - hi
+
+
+def _gemm_precise(A, B, out, *, a_mn, b_mn, residual, accumulate, colsum_a, **kw):
+    a_hi, a_lo = _tf32_split(A)
+    b_hi, b_lo = _tf32_split(B)
+    if colsum_a is not None:  # the fused column sums would see the tf32-rounded tile: take them from the fp32 operand instead
+        colsum_accumulate(A, colsum_a)
+    if accumulate:
+        for x, y in ((a_lo, b_hi), (a_hi, b_lo), (a_hi, b_hi)):
+            _gemm(x, y, out, a_mn=a_mn, b_mn=b_mn, accumulate=True, **kw)
+        return out
+    Mv = kw.get("M") or (A.shape[1] if a_mn else A.shape[0])
+    N = B.shape[1] if b_mn else B.shape[0]
+    corr = torch.empty(Mv, N, device=out.device, dtype=torch.float32)
+    plain = dict(M=kw.get("M"), split_k=1)
+    _gemm(a_lo, b_hi, corr, a_mn=a_mn, b_mn=b_mn, **plain)
+    _gemm(a_hi, b_lo, corr, a_mn=a_mn, b_mn=b_mn, residual=corr, **plain)
+    if residual is not None:
+        corr.add_(residual)
+    return _gemm(a_hi, b_hi, out, a_mn=a_mn, b_mn=b_mn, residual=corr, **kw)
+
+
 def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
+         bias: Optional[torch.Tensor] = None, rowadd: Optional[torch.Tensor] = None, rowadd_period: int = 0,
+         residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, preact: Optional[torch.Tensor] = None,
+         dact_aux: Optional[torch.Tensor] = None, dact: int = ACT_NONE, accumulate: bool = False, split_k: int = 0,
+         out_group=(0, 0, 0), round_f16: bool = False, M: Optional[int] = None, colsum_a: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """See `_gemm`; in precise mode fp32 operands take the 3xTF32 route."""
+    if PRECISE and A.dtype == torch.float32:
+        return _gemm_precise(A, B, out, a_mn=a_mn, b_mn=b_mn, residual=residual, accumulate=accumulate, colsum_a=colsum_a, bias=bias,
+                             rowadd=rowadd, rowadd_period=rowadd_period, act=act, preact=preact, dact_aux=dact_aux, dact=dact,
+                             split_k=split_k, out_group=out_group, round_f16=round_f16, M=M)
+    return _gemm(A, B, out, a_mn=a_mn, b_mn=b_mn, bias=bias, rowadd=rowadd, rowadd_period=rowadd_period, residual=residual, act=act,
+                 preact=preact, dact_aux=dact_aux, dact=dact, accumulate=accumulate, split_k=split_k, out_group=out_group,
+                 round_f16=round_f16, M=M, colsum_a=colsum_a)
+
+
+def _gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
          bias: Optional[torch.Tensor] = None, rowadd: Optional[torch.Tensor] = None, rowadd_period: int = 0,
          residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, preact: Optional[torch.Tensor] = None,
          dact_aux: Optional[torch.Tensor] = None, dact: int = ACT_NONE, accumulate: bool = False, split_k: int = 0,

@@ -106,7 +106,21 @@ class DataParallelTrainer:
         m = self.model
         if m.training and (m.view_dropout > 0 or m.gaze_dropout > 0 or m.feature_dropout > 0 or m.motion_noise > 0):
             raise ValueError("CUDA-graph capture needs a static step: view/gaze/feature dropout and motion noise must be 0")
-        self.static_batch, self.static_targets = batch, targets  # the first batch's tensors become the static input buffers
+        # Dedicated static input buffers: the graph never reads a tensor somebody else owns (e.g. a BatchPrefetcher ring slot
+        # that the side-stream staging of a later step overwrites while a replay is reading it).  `static_inputs()` hands them
+        # out for callers that want to fill them in place and skip the per-step device copy.
+        static = type(batch)() if isinstance(batch, dict) else {}
+        for k, v in batch.items():
+            static[k] = v.clone()
+        if hasattr(batch, "video_len"):
+            static.video_len = dict(batch.video_len)
+        self.static_batch, self.static_targets = static, tuple(t.clone() for t in targets)
+        batch, targets = self.static_batch, self.static_targets
+        # The two eager warm-up passes and the capture pass are real training forwards without an optimiser step: without the
+        # snapshot below they would leave three momentum updates in the BatchNorm running statistics and advance the CPU RNG
+        # stream by three draw plans, so the graph path would diverge from the eager / reference path from step 1.
+        rng_state = torch.get_rng_state()
+        buffers = {name: b.clone() for name, b in m.named_buffers() if "running_" in name or name.endswith("num_batches_tracked")}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -119,6 +133,16 @@ class DataParallelTrainer:
         with torch.cuda.graph(self._graph):
             self._static_loss = self._fwd_bwd(batch, targets)
         self.graph_launches = ops.launch_count - before  # kernels of this library inside the captured step
+        with torch.no_grad():
+            for name, b in m.named_buffers():
+                if name in buffers:
+                    b.copy_(buffers[name])
+        torch.set_rng_state(rng_state)
+        torch.cuda.synchronize()
+
+    def static_inputs(self):
+        """(batch, targets) the captured graph reads (None before the first graph step): fill them in place to avoid the copy."""
+        return self.static_batch, self.static_targets
 
     def _replay(self, batch, targets) -> torch.Tensor:
         if batch is not self.static_batch:

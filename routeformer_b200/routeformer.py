@@ -39,6 +39,15 @@ class StagedBatch(dict):
     def __init__(self, *a, **k):
         super().__init__(*a, **k)
         self.video_len = {}
+        # (event, pinned temporaries) of staging copies that read host memory this object had to pin itself: the raw
+        # cudaMemcpy2DAsync of rf_stage_frames_h2d is invisible to PyTorch's caching host allocator, so the temporaries must
+        # stay referenced until the copies have run
+        self.keepalive = []
+
+    def retire_keepalive(self) -> None:
+        for ev, _ in self.keepalive:
+            ev.synchronize()
+        self.keepalive = []
 
 
 class Routeformer(nn.Module):
@@ -103,17 +112,26 @@ class Routeformer(nn.Module):
         device = device or self.device
         reuse = out is not None  # write into the tensors of an existing staged batch (static buffers of a CUDA graph)
         out = out if reuse else StagedBatch()
+        out.retire_keepalive()  # temporaries of the previous staging into this object (waits for those copies only)
+        temporaries = []
         for key, value in host_batch.items():
             if key.endswith("_video") and self.with_video:
                 rel = c.output_fps // (c.gaze_fps if key == "front_video" else c.video_fps)
                 T = value.shape[1]
-                src = value if value.is_pinned() else value.contiguous().pin_memory()
+                src = value
+                if not (value.is_pinned() and value.is_contiguous()):
+                    src = value.contiguous().pin_memory()
+                    temporaries.append(src)
                 out[key] = ops.stage_frames_h2d(src, frame_indices(T, rel).tolist(), device, out=out[key] if reuse else None)
                 out.video_len[key] = T
             elif reuse:
                 out[key].copy_(value, non_blocking=True)
             else:
                 out[key] = value.to(device, non_blocking=True)
+        if temporaries:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            out.keepalive.append((ev, temporaries))
         return out
 
     def _device_index(self, idx: torch.Tensor, device) -> torch.Tensor:
@@ -218,11 +236,16 @@ class Routeformer(nn.Module):
             host = torch.empty(n, dtype=torch.int32)
             if device.type == "cuda":
                 host = host.pin_memory()
-            self._idx_slots[key] = (host, torch.empty(n, dtype=torch.int32, device=device))
-        host, dev = self._idx_slots[key]
+            self._idx_slots[key] = [host, torch.empty(n, dtype=torch.int32, device=device), None]
+        host, dev, copied = self._idx_slots[key]
         if refill_only == "defer":  # draw now, write the pinned buffer later (commit_deferred_draws): it may still be in use
             self._deferred_tables.append((host, torch.cat([t.reshape(-1) for t in tables]).to(torch.int32)))
             return []
+        if copied is not None:
+            # eager path: the previous H2D copy out of this pinned buffer (an earlier forward, the target pass, the previous
+            # autoregressive window) may still be queued -- rewriting the buffer now would hand that forward torn index tables
+            copied.synchronize()
+            self._idx_slots[key][2] = None
         off = 0
         for t in tables:
             host[off:off + t.numel()].copy_(t.reshape(-1))
@@ -230,6 +253,10 @@ class Routeformer(nn.Module):
         if refill_only:
             return []
         dev.copy_(host, non_blocking=True)
+        if device.type == "cuda" and not torch.cuda.is_current_stream_capturing():
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._idx_slots[key][2] = ev
         out, off = [], 0
         for t in tables:
             out.append(dev[off:off + t.numel()].view(1, *t.shape))

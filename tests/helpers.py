@@ -74,11 +74,22 @@ def tops_for_oracle(recorded, view_order):
     return out
 
 
-def selection_violations(recorded, oracle_tops, view_order, rel_tol=2e-2):
-    """Counts product selections that are NOT explained by a near-tie in the oracle's sparsity measure."""
+# TF32-derived near-tie bound for the ProbSparse sparsity measure M = max_j s - sum_j s / L_K, s = q.k:
+# q and k leave a tcgen05 kind::tf32 GEMM whose operands carry a unit round-off of 2^-11 each, i.e. ~2^-10 relative on every
+# product, and the activations feeding it have crossed up to 8 such layers (x sqrt(8) if the errors were independent, x 8 if
+# they all lined up).  A pick is "explained" when it lies within 2^-8 (= 4 x 2^-10) of the u-th largest measure, relative to
+# the largest |M| of that (b, h) problem.  Round 1 used 2e-2 here; the worst gap actually observed is logged by the tests.
+SELECTION_REL_TOL = 2.0 ** -8
+
+
+def selection_violations(recorded, oracle_tops, view_order, rel_tol=SELECTION_REL_TOL, stats=None):
+    """Counts product selections that are NOT explained by a near-tie in the oracle's sparsity measure.
+    `stats` (dict, optional) receives "worst_gap": the largest distance of a mismatching pick from the u-th measure, in
+    units of max|M|, and "mismatches": picks that differ from the oracle's own top-u set at all."""
     import torch
 
-    bad = total = 0
+    bad = total = mism = 0
+    worst = 0.0
     queues = {}
     for t in oracle_tops:
         queues.setdefault(t["where"], []).append(t["measure"])
@@ -91,11 +102,40 @@ def selection_violations(recorded, oracle_tops, view_order, rel_tol=2e-2):
         top = rec["top"].cpu().long()
         u = top.shape[-1]
         kth = m.topk(u, dim=-1).values[..., -1:]                    # u-th largest measure per (b,h)
-        tol = rel_tol * m.abs().amax(dim=-1, keepdim=True).clamp_min(1.0)
+        scale = m.abs().amax(dim=-1, keepdim=True).clamp_min(1.0)
+        tol = rel_tol * scale
         sel = torch.zeros_like(m, dtype=torch.bool).scatter(-1, top, True)
         bad += int(((m < kth - tol) & sel).sum() + ((m > kth + tol) & ~sel).sum())
+        wrong = ((m < kth) & sel) | ((m > kth) & ~sel)
+        mism += int(wrong.sum())
+        if wrong.any():
+            worst = max(worst, float((((m - kth).abs() / scale)[wrong]).max()))
         total += sel.numel()
+    if stats is not None:
+        stats["worst_gap"] = max(stats.get("worst_gap", 0.0), worst)
+        stats["mismatches"] = stats.get("mismatches", 0) + mism
     return bad, total
+
+
+def same_selections(rec_a, rec_b) -> bool:
+    """True if two recorded runs picked the same top-u SETS in every ProbSparse call."""
+    if len(rec_a) != len(rec_b):
+        return False
+    for a, b in zip(rec_a, rec_b):
+        if a["where"] != b["where"] or not torch.equal(a["top"].sort(-1).values, b["top"].sort(-1).values):
+            return False
+    return True
+
+
+def log_parity(line: str, path: str = "gpurun_out/parity_raw_errors.txt") -> None:
+    """Raw (no-replay) errors against the reference goldens: printed (pytest -s / -rP) and appended to a file that travels back."""
+    print(line)
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
 
 
 class ReplayDraw:

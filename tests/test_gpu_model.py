@@ -12,38 +12,55 @@ import pytest
 import torch
 
 from oracle import routeformer_oracle as O
-from tests.helpers import (ReplayDraw, ReplayDropout, build_product, case_from_golden, load_golden, rel_err, selection_violations, targets_for,
-                           to_device, tops_for_oracle)
+from tests.helpers import (ReplayDraw, ReplayDropout, build_product, case_from_golden, load_golden, log_parity, rel_err, same_selections,
+                           selection_violations, targets_for, to_device, tops_for_oracle)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 CASES = ["gps_only_paper", "full_small_eval", "dreyeve_small", "normalized_small", "no_gaze_small", "no_scene_small", "sparse_small",
-         "full_paper_eval", "autoregressive_small", "autoregressive_dreyeve_small"]
+         "full_paper_eval", "autoregressive_small", "autoregressive_dreyeve_small",
+         "dreyeve_paper_eval",     # BASELINE configs[3]: real DR(eye)VE frame shapes 216x768 / 216x384 / 240x320, rotate_motion
+         "full_paper_b64_eval"]    # BASELINE configs[1]: paper configuration, batch 64
 
 
 def view_order(cfg):
     return (["right", "left"] if cfg.with_scene and cfg.with_video else []) + (["front"] if cfg.with_gaze else [])
 
 
+def _forward(model, batch, precise: bool):
+    from routeformer_b200 import ops
+
+    model.record_tops = []
+    torch.manual_seed(12345)
+    with torch.no_grad(), ops.precise(precise):
+        out = model(batch)
+    torch.cuda.synchronize()
+    wp, dense = out if isinstance(out, tuple) else (out, None)
+    return wp, dense, model.record_tops
+
+
+def metric_tol(v):
+    """"identical to 4 decimal places" at fp32 resolution: 5e-5 absolute plus the spacing of fp32 at the metric's magnitude."""
+    return 5e-5 + 2e-6 * abs(v)
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_eval_forward(name):
+    import routeformer_b200 as R
+
     gold = load_golden(name)
     cfg, spec, sd, batch = case_from_golden(gold)
     model = build_product(cfg, spec).to(DEV).eval()
     model.load_state_dict(sd)
-    model.record_tops = []
-    torch.manual_seed(12345)
-    with torch.no_grad():
-        out = model(to_device(batch, DEV))
-    torch.cuda.synchronize()
-    wp, dense = out if isinstance(out, tuple) else (out, None)
+    dev_batch = to_device(batch, DEV)
+    wp, dense, tops = _forward(model, dev_batch, precise=False)
     # the CPU RNG stream is consumed exactly like the reference does (SURVEY Appendix C)
     assert [(lk, (lq, u)) for lk, lq, u in model.last_draw_log] == [tuple(d) for d in gold["draws"]]
     # (a) oracle with the product's selections replayed
     torch.manual_seed(12345)
     orc = O.Routeformer(sd, cfg, spec)
-    Draw = ReplayDraw(tops_for_oracle(model.record_tops, view_order(cfg)))
+    Draw = ReplayDraw(tops_for_oracle(tops, view_order(cfg)))
 
     with torch.no_grad():
         ref = orc.forward(batch, training=False, draw=Draw)
@@ -53,15 +70,38 @@ def test_eval_forward(name):
     assert rel_err(disp, ref_disp) < 1e-2
     if dense is not None:
         assert rel_err(dense.cpu(), ref_dense) < 1e-2
-    bad, total = selection_violations(model.record_tops, orc.tops, view_order(cfg))
-    assert bad == 0, f"{bad} of {total} top-u selections not explained by a near-tie"
-    # (b) raw, against the reference's golden output
-    assert rel_err(wp.cpu(), gold["waypoints"]) < 5e-3
-    # metrics on the device vs the reference's values
-    import routeformer_b200 as R
+    stats = {}
+    bad, total = selection_violations(tops, orc.tops, view_order(cfg), stats=stats)
+    assert bad == 0, f"{bad} of {total} top-u selections not explained by a TF32 near-tie (worst gap {stats['worst_gap']:.2e})"
+    # (b) RAW, no replay, against the reference's golden output.  North-star bound: 1e-3 relative on the waypoints.
+    #   * precise mode (3xTF32 GEMMs, fp32-level): asserted unconditionally, with ADE / FDE of the GPU prediction against the
+    #     reference's own metric values to 4 decimal places;
+    #   * default TF32 mode: asserted at 1e-3 whenever TF32 rounding flipped no top-u query (same selections as the precise run);
+    #     a flipped marginal query changes which rows get real attention -- an O(1) local effect the reference itself shows under
+    #     TF32 emulation -- and is bounded at 5e-3 and logged.
+    wp_p, dense_p, tops_p = _forward(model, dev_batch, precise=True)
     t_wp, _ = targets_for(cfg, gold["B"], gold["dseed"] + 1000)
-    assert abs(R.ade(wp, t_wp.to(DEV)).item() - O.ade(wp.cpu(), t_wp).item()) < 5e-5 + 2e-7 * abs(gold["ade"])
-    assert abs(R.fde(wp, t_wp.to(DEV)).item() - O.fde(wp.cpu(), t_wp).item()) < 5e-5 + 2e-7 * abs(gold["fde_batch"])
+    t_dev = t_wp.to(DEV)
+    raw, raw_p = rel_err(wp.cpu(), gold["waypoints"]), rel_err(wp_p.cpu(), gold["waypoints"])
+    gd = gold["waypoints"] - batch["gps"][:, -1:]
+    raw_disp, raw_disp_p = rel_err(disp, gd), rel_err(wp_p.cpu() - batch["gps"][:, -1:], gd)
+    raw_dense = rel_err(dense.cpu(), gold["dense"]) if dense is not None else float("nan")
+    raw_dense_p = rel_err(dense_p.cpu(), gold["dense"]) if dense_p is not None else float("nan")
+    flips = not same_selections(tops, tops_p)
+    ade_p, fde_b_p, fde_1_p = R.ade(wp_p, t_dev).item(), R.fde(wp_p, t_dev).item(), R.fde(wp_p[-1:], t_dev[-1:]).item()
+    ade_d = R.ade(wp, t_dev).item()
+    log_parity(f"eval {name:30s} raw wp tf32 {raw:.2e} precise {raw_p:.2e} | disp tf32 {raw_disp:.2e} precise {raw_disp_p:.2e} | dense tf32 "
+               f"{raw_dense:.2e} precise {raw_dense_p:.2e} | tf32 flipped a query: {flips} | worst near-tie gap {stats['worst_gap']:.2e} "
+               f"({stats['mismatches']} of {total}) | ADE gold {gold['ade']:.6f} precise {ade_p:.6f} tf32 {ade_d:.6f} | FDE gold "
+               f"{gold['fde_batch']:.6f} precise {fde_b_p:.6f}")
+    assert raw_p < 1e-3, raw_p
+    assert raw < (5e-3 if flips else 1e-3), (raw, flips)
+    assert abs(ade_p - gold["ade"]) < metric_tol(gold["ade"]), (ade_p, gold["ade"])
+    assert abs(fde_b_p - gold["fde_batch"]) < metric_tol(gold["fde_batch"]), (fde_b_p, gold["fde_batch"])
+    assert abs(fde_1_p - gold["fde"]) < metric_tol(gold["fde"]), (fde_1_p, gold["fde"])
+    # the metric kernels themselves, on the product's own prediction
+    assert abs(R.ade(wp, t_dev).item() - O.ade(wp.cpu(), t_wp).item()) < 5e-5 + 2e-7 * abs(gold["ade"])
+    assert abs(R.fde(wp, t_dev).item() - O.fde(wp.cpu(), t_wp).item()) < 5e-5 + 2e-7 * abs(gold["fde_batch"])
 
 
 def _train_step(sd, cfg, spec, batch, t_wp, t_dense):
@@ -135,6 +175,147 @@ def test_train_step_gradients():
     rel.sort(reverse=True)
     assert rel[0][0] < 6e-2, rel[:5]
     assert statistics.median(r for r, _ in rel) < 1.5e-2
+
+
+def _gpu_grads(sd, cfg, spec, batch, t_wp, t_dense, precise: bool, seed: int = 12345):
+    """One training-mode fwd+bwd on the GPU -> (model, loss, {name: grad clone}, recorded selections)."""
+    import routeformer_b200 as R
+    from routeformer_b200 import ops
+
+    model = build_product(cfg, spec).to(DEV).train()
+    model.load_state_dict(sd)
+    model.record_tops = []
+    lossf = R.FutureDiscountedLoss({0: 0.97}, epsilon=1.0, loss_function="smooth_l1")
+    torch.manual_seed(seed)
+    with ops.precise(precise):
+        wp, dense = model(to_device(batch, DEV))
+        loss = lossf(wp, t_wp.to(DEV)) + 0.5 * lossf(dense, t_dense.to(DEV))
+        loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters() if p.grad is not None}
+    return model, loss.item(), grads, model.record_tops
+
+
+@pytest.mark.parametrize("name", ["full_small_train", "full_paper_train"])
+def test_train_step_raw_against_reference(name):
+    """RAW gradient parity at the reference's OWN initialisation (no conditioning of the weights, no replay of selections):
+    in precise mode (3xTF32) loss, every per-parameter gradient norm, the stored gradient tensors and the BatchNorm statistics
+    of the reference's training step (golden generated by the unmodified reference) must be reproduced.  `full_paper_train` is
+    the paper configuration at B = 8 (BASELINE configs[2] shard shape)."""
+    import statistics
+
+    gold = load_golden(name)
+    cfg, spec, sd, batch = case_from_golden(gold)
+    t_wp, t_dense = targets_for(cfg, gold["B"], gold["dseed"] + 1000)
+    model, loss, grads, tops = _gpu_grads(sd, cfg, spec, batch, t_wp, t_dense, precise=True)
+    _, loss_t, grads_t, tops_t = _gpu_grads(sd, cfg, spec, batch, t_wp, t_dense, precise=False)
+    rel_n, rel_t = [], []
+    for k, n in gold["grad_norm"].items():
+        if k.startswith("video_backbone"):
+            continue  # frozen in the product (reference: trained only after epoch 10, TimmBackbone.py:123)
+        assert k in grads, f"missing gradient for {k}"
+        if n > 1e-6:
+            rel_n.append((abs(grads[k].norm().item() - n) / n, k))
+            rel_t.append((abs(grads_t[k].norm().item() - n) / n, k))
+    rel_n.sort(reverse=True)
+    rel_t.sort(reverse=True)
+    full = []
+    for k, g in gold["grad_small"].items():
+        if k.startswith("video_backbone"):
+            continue
+        if g.norm() > 1e-6:
+            full.append((rel_err(grads[k], g), k))
+        else:  # analytically-zero gradients (key biases: softmax shift invariance; biases in front of BatchNorm)
+            assert (grads[k] - g).abs().max() < 1e-4, k
+    full.sort(reverse=True)
+    med = lambda rows: statistics.median(r for r, _ in rows)
+    log_parity(f"train {name:24s} loss gold {gold['loss']:.6f} precise {loss:.6f} tf32 {loss_t:.6f} | grad-norm rel err precise: median "
+               f"{med(rel_n):.2e} max {rel_n[0][0]:.2e} ({rel_n[0][1]}) | tf32: median {med(rel_t):.2e} max {rel_t[0][0]:.2e} | "
+               f"full-tensor rel err precise: median {med(full):.2e} max {full[0][0]:.2e} ({full[0][1]}) | tf32 flipped a query: "
+               f"{not same_selections(tops, tops_t)}")
+    assert abs(loss - gold["loss"]) < 1e-4 * abs(gold["loss"])
+    assert abs(loss_t - gold["loss"]) < 2e-2 * abs(gold["loss"])
+    assert med(rel_n) < 1e-3 and rel_n[0][0] < 5e-2, rel_n[:5]
+    assert med(full) < 2e-3 and full[0][0] < 1e-1, full[:5]
+    new_sd = model.state_dict()
+    for k, v in gold["bn"].items():
+        if "num_batches" in k:
+            assert int(new_sd[k]) == int(v), k
+        else:
+            assert torch.allclose(new_sd[k].cpu(), v, atol=1e-5, rtol=1e-4), k
+
+
+def test_two_shard_data_parallel_equivalence():
+    """the global batch split over two ranks (contiguous shards, identical weights, identical CPU draws, per-shard
+    BatchNorm statistics), gradients summed and scaled by 1/world == the oracle's per-shard autograd averaged the same way.
+    Both "ranks" run through the real model on one GPU; the collective itself is covered by the gloo tests."""
+    from routeformer_b200.parallel import shard_batch
+    from tests.helpers import condition_weights
+
+    gold = load_golden("full_small_train")
+    cfg, spec, sd, _ = case_from_golden(gold)
+    sd = condition_weights(sd)
+    B, world = 4, 2
+    batch = O.synthetic_batch(B, cfg, gold["shapes"], seed=31)
+    t_wp, t_dense = targets_for(cfg, B, 32)
+    gpu_sum, ref_sum, losses = {}, {}, []
+    for rank in range(world):
+        shard = shard_batch(batch, rank, world)
+        tw, td = t_wp[rank * 2:(rank + 1) * 2], t_dense[rank * 2:(rank + 1) * 2]
+        model, loss, grads, tops = _gpu_grads(sd, cfg, spec, shard, tw, td, precise=False)
+        params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and not k.endswith(".pe") and
+                                              not k.startswith("video_backbone")) for k, v in sd.items()}
+        orc = O.Routeformer(params, cfg, spec)
+        torch.manual_seed(12345)
+        rwp, rdense = orc.forward(shard, training=True, draw=ReplayDraw(tops_for_oracle(tops, ["right", "left", "front"])))
+        rloss = O.future_discounted_loss(rwp, tw) + 0.5 * O.future_discounted_loss(rdense, td)
+        rloss.backward()
+        losses.append((loss, rloss.item()))
+        for k, p in params.items():
+            if p.requires_grad:
+                gpu_sum[k] = gpu_sum.get(k, 0) + grads[k] / world
+                ref_sum[k] = ref_sum.get(k, 0) + p.grad / world
+    for l, r in losses:
+        assert abs(l - r) < 1e-3 * abs(r)
+    rel = sorted(((rel_err(gpu_sum[k], ref_sum[k]), k) for k in ref_sum if ref_sum[k].norm() > 1e-6), reverse=True)
+    import statistics
+    log_parity(f"dp2   two-shard averaged gradients vs oracle: median rel err {statistics.median(r for r, _ in rel):.2e} max {rel[0][0]:.2e} ({rel[0][1]})")
+    assert rel[0][0] < 6e-2 and statistics.median(r for r, _ in rel) < 1.5e-2, rel[:5]
+
+
+def test_standalone_perceive_modules():
+    """`PerceiveEncoder(...)(x)` / `PerceiveDecoder(...)(x_enc, x_dec)` used stand-alone, as the baselines of
+    experiments/gimo/adapted_gimo.py:59-67 and experiments/multimodal_transformer do -- same class names and constructor
+    arguments, the module draws its own index tables on the CPU generator (LiveIndexSource).  Against the reference's outputs."""
+    import routeformer_b200 as R
+    from routeformer_b200 import ops
+
+    gold = load_golden("submodules")
+    enc = R.PerceiveEncoder(in_channels=40, out_len=1, out_channels=24, n_heads=8, layers=2, d_ff=64, dropout=0.0).to(DEV).eval()
+    tmpl = {}
+    O._perceive_encoder_keys(tmpl, "e", 40, 24, 128, 2, 64)
+    sd = O.fill_state_dict({k[2:]: v for k, v in tmpl.items()}, 21)
+    assert set(sd) == set(enc.state_dict())
+    enc.load_state_dict(sd)
+    dec = R.PerceiveDecoder(query_channels=16, value_channels=16, out_channels=16, out_len=12, dropout=0.0, d_ff=32, n_heads=4, layers=2,
+                            mix=False).to(DEV).eval()
+    tmpl = {}
+    O._perceive_decoder_keys(tmpl, "d", 16, 16, 16, 2, 32)
+    sd = O.fill_state_dict({k[2:]: v for k, v in tmpl.items()}, 22)
+    assert set(sd) == set(dec.state_dict())
+    dec.load_state_dict(sd)
+    ge, gd = gold["perceive_encoder"], gold["perceive_decoder"]
+    for precise, tol in ((True, 1e-4), (False, 5e-3)):
+        with torch.no_grad(), ops.precise(precise):
+            torch.manual_seed(3)
+            y = enc(ge["x"].to(DEV))
+            torch.manual_seed(4)
+            z = dec(gd["x_enc"].to(DEV), gd["x_dec"].to(DEV))
+        torch.cuda.synchronize()
+        assert y.shape == ge["y"].shape and z.shape == gd["y"].shape
+        e_enc, e_dec = rel_err(y.cpu(), ge["y"]), rel_err(z.cpu(), gd["y"])
+        log_parity(f"perceive stand-alone ({'precise' if precise else 'tf32'}): encoder rel err {e_enc:.2e}, decoder rel err {e_dec:.2e}")
+        assert e_enc < tol and e_dec < tol, (precise, e_enc, e_dec)
 
 
 def test_gaze_centred_fov_and_plugin_api():

@@ -6,7 +6,8 @@ from oracle import routeformer_oracle as O
 from tests.helpers import case_from_golden, load_golden, rel_err, targets_for
 
 EVAL_CASES = ["gps_only_paper", "full_small_eval", "full_paper_eval", "dreyeve_small", "normalized_small",
-              "no_gaze_small", "no_scene_small", "sparse_small", "autoregressive_small", "autoregressive_dreyeve_small"]
+              "no_gaze_small", "no_scene_small", "sparse_small", "autoregressive_small", "autoregressive_dreyeve_small",
+              "dreyeve_paper_eval", "full_paper_b64_eval"]
 
 
 @pytest.mark.parametrize("name", EVAL_CASES)
@@ -41,8 +42,9 @@ def test_autoregressive_gps_only_raises_like_the_reference():
         O.Routeformer(sd, cfg, None).forward(O.synthetic_batch(2, cfg, "tiny", seed=4), training=False)
 
 
-def test_train_step_matches_reference():
-    gold = load_golden("full_small_train")
+@pytest.mark.parametrize("name", ["full_small_train", "full_paper_train"])
+def test_train_step_matches_reference(name):
+    gold = load_golden(name)
     cfg, spec, sd, batch = case_from_golden(gold)
     params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and not k.endswith(".pe"))
               for k, v in sd.items()}
@@ -53,13 +55,16 @@ def test_train_step_matches_reference():
     loss = O.future_discounted_loss(wp, t_wp) + 0.5 * O.future_discounted_loss(dense, t_dense)
     assert abs(loss.item() - gold["loss"]) < 1e-5 * max(1.0, abs(gold["loss"]))
     loss.backward()
+    # paper-size model: fp32 summation order alone (functional oracle vs the reference's module autograd) moves the chaotic first
+    # Informer attention layer by 6e-4 (measured); the small model stays below 2e-4
+    tol = 2e-4 if name == "full_small_train" else 2e-3
     for k, n in gold["grad_norm"].items():
         g = params[k].grad
         assert g is not None, k
-        assert abs(g.norm().item() - n) <= 2e-4 * n + 1e-6, (k, g.norm().item(), n)
+        assert abs(g.norm().item() - n) <= tol * n + (1e-6 if name == "full_small_train" else 1e-5), (k, g.norm().item(), n)
     for k, g in gold["grad_small"].items():
         # key-projection bias grads are analytically 0 (softmax shift invariance): pure rounding noise
-        assert rel_err(params[k].grad, g) < 2e-4 or (params[k].grad - g).abs().max() < 1e-6, k
+        assert rel_err(params[k].grad, g) < tol or (params[k].grad - g).abs().max() < 2e-6, k
     for k, v in gold["bn"].items():
         if "num_batches" in k:
             continue
