@@ -28,32 +28,22 @@ sys.path.insert(0, ROOT)
 
 PAPER = dict(with_video=True, with_gaze=True, dense_prediction=True)  # + OracleConfig defaults = paper configuration
 BACKBONE = dict(image_size=256, patch=32, channels=1024, window=0.5)
+# experiments/full_comparison.py:272-275: the dropouts the paper configuration trains with
+PAPER_DROPOUT = dict(view_dropout=0.6, gaze_dropout=0.2, feature_dropout=0.05)
 
 
-def build_case(B: int, seed: int, fov: str):
-    from oracle import routeformer_oracle as O  # synthetic-batch / config description only (shared with the tests)
+def build_case(B: int, seed: int, shapes: str = "gem"):
+    """Synthetic host batch + targets from the package's own generator (the product arm never touches oracle/)."""
+    from routeformer_b200 import synthetic as S
 
-    cfg = O.OracleConfig(**PAPER)
-    spec = O.BackboneSpec(**BACKBONE)
-    batch = O.synthetic_batch(B, cfg, "gem", seed=seed)
-    g = torch.Generator().manual_seed(seed + 1000)
-    targets = (batch["gps"][:, -1:, :] + torch.cumsum(1.83 + 0.91 * torch.randn(B, cfg.pred_len, 2, generator=g), 1),
-               torch.randn(B, cfg.pred_len, cfg.image_embedding_size, generator=g))
-    return cfg, spec, batch, targets
+    batch = S.synthetic_batch(B, 40, shapes, seed=seed)
+    return batch, S.synthetic_targets(batch, 30, 64, shapes, seed=seed + 1000)
 
 
-def build_model(cfg, spec, fov):
-    import routeformer_b200 as R
+def build_model(fov, shapes: str = "gem", dropout: bool = False):
+    from routeformer_b200 import synthetic as S
 
-    g = R.GPSBackboneConfig(seq_len=cfg.seq_len, label_len=cfg.seq_len, pred_len=cfg.pred_len, factor=cfg.factor, distil=True,
-                            dropout=0.0, activation="relu", d_model=cfg.d_model, n_heads=cfg.n_heads, e_layers=cfg.e_layers,
-                            d_layers=cfg.d_layers, d_ff=cfg.d_ff)
-    vb = R.PatchBackboneConfig(image_size=spec.image_size, patch=spec.patch, channels=spec.channels, fov=fov, window=spec.window)
-    rc = R.RouteformerConfig(gps_backbone_config=g, video_backbone_config=vb, decoder_mode="smart", with_video=True, with_gaze=True,
-                             dense_prediction=True, dense_loss_ratio=0.5, image_embedding_size=64, encoder_hidden_size=64,
-                             encoder_heads=8, encoder_layers=8, encoder_d_ff=256, cross_modal_decoder_heads=8,
-                             cross_modal_decoder_layers=2, view_dropout=0.0, gaze_dropout=0.0, feature_dropout=0.0)
-    return R.Routeformer(rc, gps_backbone=R.Informer, video_backbone=R.PatchEmbedBackbone)
+    return S.paper_model(fov=fov, rotate_motion=shapes == "dreyeve", **(PAPER_DROPOUT if dropout else {}), **BACKBONE)
 
 
 class ClockSampler(threading.Thread):
@@ -96,13 +86,44 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-# ---------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch.distributed as dist
+def measure_tf32_peak(dev, seconds: float = 1.0):
+    """cuBLAS TF32 GEMM 8192^3 timed the way MEASURED_PEAKS.json times bf16: best of 10 (burst) and back to back for
+    `seconds` (sustained, under the power cap).  MEASURED_PEAKS has no TF32 figure, and bf16/2 understates it."""
+    n = 8192
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        sustained = e0.elapsed_time(e1) / reps
+        fl = 2.0 * n ** 3
+        return {"tf32_tflops": round(fl / best / 1e9, 1), "tf32_tflops_sustained": round(fl / sustained / 1e9, 1),
+                "how": f"torch.matmul fp32 {n}^3 with allow_tf32 (cuBLAS): best of 10 and {reps} back to back, CUDA events"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
-    import routeformer_b200 as R
-    from routeformer_b200 import ops
-    from routeformer_b200.parallel import DataParallelTrainer
+
+# ---------------------------------------------------------------------------------------------
+def dist_setup(args):
+    import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -114,10 +135,32 @@ def run_ours(args):
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))  # a stuck collective aborts quickly
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    return dist, world, rank, local, dev, barrier, max_over_ranks
+
+
+def run_train(args):
+    import routeformer_b200 as R
+    from routeformer_b200 import ops
+    from routeformer_b200.parallel import BatchPrefetcher, DataParallelTrainer
+
+    dist, world, rank, local, dev, barrier, max_over_ranks = dist_setup(args)
     B = args.batch_per_gpu
-    cfg, spec, host_batch, host_targets = build_case(B, seed=100 + rank, fov=args.fov)
+    host_batch, host_targets = build_case(B, seed=100 + rank)
     torch.manual_seed(0)
-    model = build_model(cfg, spec, args.fov).to(dev).train()
+    model = build_model(args.fov, dropout=args.paper_dropout).to(dev).train()
     if args.no_branch_overlap:
         R.Routeformer.overlap_branches = False
     lossf = R.FutureDiscountedLoss({0: 0.97}, epsilon=1.0, loss_function="smooth_l1")
@@ -126,7 +169,8 @@ def run_ours(args):
         wp, dense = out
         return lossf(wp, tgt[0]) + 0.5 * lossf(dense, tgt[1])
 
-    trainer = DataParallelTrainer(model, loss_fn, lr=1e-5, weight_decay=1e-4, max_grad_norm=2.5, use_cuda_graph=not args.no_graph,
+    use_graph = not args.no_graph and not args.paper_dropout  # dropout draws data-dependent control flow: eager until it is captured
+    trainer = DataParallelTrainer(model, loss_fn, lr=1e-5, weight_decay=1e-4, max_grad_norm=2.5, use_cuda_graph=use_graph,
                                   overlap_wgrad=not args.no_wgrad_overlap)
     trainer.broadcast_parameters()
     # inputs: pinned host batch in the reference layout; the device batch holds the frames the model consumes (8 of 40 per view)
@@ -136,15 +180,11 @@ def run_ours(args):
     targets = tuple(t.to(dev) for t in host_targets)
     in_bytes = sum(v.numel() * v.element_size() for v in batch.values())
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # ---- device-resident timing -------------------------------------------------------------
     for _ in range(args.warmup):
         trainer.step(batch, targets)
+    if trainer.static_inputs()[0] is not None:  # the captured graph reads its own static buffers: time with the inputs resident THERE
+        batch, targets = trainer.static_inputs()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -156,13 +196,9 @@ def run_ours(args):
         loss = trainer.step(batch, targets)
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     launches = (ops.launch_count - launches0) // max(args.steps, 1) + trainer.graph_launches
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     value = world * B * args.steps / (ms / 1e3)
     if args.profile:
         if rank == 0:
@@ -172,10 +208,8 @@ def run_ours(args):
         return
 
     # ---- end to end through the public API: pinned host batch -> stage -> step -> loss.item() ----
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(20, min(args.steps, 40))
     h2d = in_bytes + sum(t.numel() * t.element_size() for t in pinned_t)
-
-    from routeformer_b200.parallel import BatchPrefetcher
     prefetch = BatchPrefetcher(model, dev, depth=2)
 
     def e2e_step():
@@ -191,7 +225,7 @@ def run_ours(args):
         return loss_t.item()
 
     prefetch.submit(pinned, pinned_t)
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     barrier()
     e0.record()
@@ -199,150 +233,153 @@ def run_ours(args):
         loss_host = e2e_step()
     e1.record()
     barrier()
-    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / (float(ms_e2e.item()) / 1e3)
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMM): one instrumented step, CUDA events per launch ----
-    roofline = cpu_baseline = None
+    roofline = cpu_baseline = eager = None
     kernels = {}
+    peaks, peak_src = measured_peaks()
+    tf32 = measure_tf32_peak(dev)
     # every rank runs the instrumented step (it contains the gradient all-reduce); only rank 0 reports
-    if True:
-        peaks, peak_src = measured_peaks()
-        rec = []
-        orig_gemm, orig_crop, orig_af, orig_ab = ops.gemm, ops.fov_crop, ops.attention_fwd, ops.attention_bwd
+    rec = []
+    orig_gemm, orig_crop, orig_af, orig_ab = ops._gemm, ops.fov_crop, ops.attention_fwd, ops.attention_bwd
+    gemm_calls = []  # (args, kwargs, work) of every GEMM launch of the step, replayed below for clean per-launch timings
 
-        gemm_calls = []  # (args, kwargs, work) of every GEMM launch of the step, replayed below for clean per-launch timings
+    def timed(fn, tag, work):
+        def wrapper(*a, **k):
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            r = fn(*a, **k)
+            e_.record()
+            w = work(*a, **k)
+            rec.append((tag, s_, e_, w))
+            if tag == "gemm":
+                gemm_calls.append((a, k, w))
+            return r
+        return wrapper
 
-        def timed(fn, tag, work):
-            def wrapper(*a, **k):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                r = fn(*a, **k)
-                e.record()
-                w = work(*a, **k)
-                rec.append((tag, s, e, w))
-                if tag == "gemm":
-                    gemm_calls.append((a, k, w))
-                return r
-            return wrapper
+    shapes = {}
 
-        shapes = {}
+    def gemm_work(A, Bm, out, **k):
+        Kd = A.shape[0] if k.get("a_mn") else A.shape[1]
+        Md = A.shape[1] if k.get("a_mn") else A.shape[0]
+        Nd = Bm.shape[1] if k.get("b_mn") else Bm.shape[0]
+        key = (Md, Nd, Kd, bool(k.get("a_mn")), bool(k.get("b_mn")), bool(k.get("accumulate")))
+        shapes.setdefault(key, []).append(len(rec))
+        # algorithmic bytes: both operands once, the output once, plus every [M,N] epilogue operand / second output
+        extra = sum(1 for name in ("residual", "preact", "dact_aux") if k.get(name) is not None) + (1 if k.get("accumulate") else 0)
+        return {"flops": 2.0 * Md * Nd * Kd, "bytes": A.element_size() * (Md * Kd + Nd * Kd) + 4.0 * (1 + extra) * Md * Nd}
 
-        def gemm_work(A, Bm, out, **k):
-            Kd = A.shape[0] if k.get("a_mn") else A.shape[1]
-            Md = A.shape[1] if k.get("a_mn") else A.shape[0]
-            Nd = Bm.shape[1] if k.get("b_mn") else Bm.shape[0]
-            key = (Md, Nd, Kd, bool(k.get("a_mn")), bool(k.get("b_mn")), bool(k.get("accumulate")))
-            shapes.setdefault(key, []).append(len(rec))
-            # algorithmic bytes: both operands once, the output once, plus every [M,N] epilogue operand / second output
-            extra = sum(1 for name in ("residual", "preact", "dact_aux") if k.get(name) is not None) + (1 if k.get("accumulate") else 0)
-            return {"flops": 2.0 * Md * Nd * Kd, "bytes": 4.0 * (Md * Kd + Nd * Kd + (1 + extra) * Md * Nd)}
+    def crop_work(frames, centers, windows, S, mean, std, **k):
+        n = centers.shape[0]
+        H, W = frames.shape[-2:]
+        win = windows[0].tolist()
+        src = 3 * min(H, win[1] * H + 2) * min(W, win[0] * W + 2) * frames.element_size()
+        out_t = k.get("out")
+        return n * (src + 3 * S * S * (out_t.element_size() if out_t is not None else 4))
 
-        def crop_work(frames, centers, windows, S, mean, std, **k):
-            n = centers.shape[0]
-            H, W = frames.shape[-2:]
-            win = windows[0].tolist()
-            src = 3 * min(H, win[1] * H + 2) * min(W, win[0] * W + 2) * frames.element_size()
-            out_t = k.get("out")
-            return n * (src + 3 * S * S * (out_t.element_size() if out_t is not None else 4))
-
-        ops.gemm = timed(orig_gemm, "gemm", gemm_work)
-        ops.fov_crop = timed(orig_crop, "fov_crop", crop_work)
-        ops.attention_fwd = timed(orig_af, "attention", lambda *a, **k: 0.0)
-        ops.attention_bwd = timed(orig_ab, "attention", lambda *a, **k: 0.0)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        graph_mode, trainer.use_cuda_graph = trainer.use_cuda_graph, False  # per-launch events need the eager path
-        trainer.step(batch, targets)
-        trainer.use_cuda_graph = graph_mode
-        ev1.record()
+    ops._gemm = timed(orig_gemm, "gemm", gemm_work)
+    ops.fov_crop = timed(orig_crop, "fov_crop", crop_work)
+    ops.attention_fwd = timed(orig_af, "attention", lambda *a, **k: 0.0)
+    ops.attention_bwd = timed(orig_ab, "attention", lambda *a, **k: 0.0)
+    graph_mode, trainer.use_cuda_graph = trainer.use_cuda_graph, False  # per-launch events need the eager path
+    trainer.step(batch, targets)
+    trainer.use_cuda_graph = graph_mode
+    torch.cuda.synchronize()
+    ops._gemm, ops.fov_crop, ops.attention_fwd, ops.attention_bwd = orig_gemm, orig_crop, orig_af, orig_ab
+    hbm_peak = peaks["hbm_gbs"]
+    tf32_peak = tf32["tf32_tflops_sustained"]
+    for tag in ("fov_crop", "attention"):
+        rows = [(s_.elapsed_time(e_), w) for t_, s_, e_, w in rec if t_ == tag]
+        if rows:
+            # event pairs around eager launches: exact for the long kernels (crop), inflated by host issue time for short ones
+            kernels[tag] = {"launches": len(rows), "ms": round(sum(r[0] for r in rows), 3), "work": sum(r[1] for r in rows)}
+            if tag == "attention":
+                kernels[tag]["ms_note"] = "eager event pairs, includes host launch gaps; see profiles/*ncu_launch_summary* for device times"
+    # GEMM launches, split by the roofline that bounds each one (time at peak: bytes / HBM vs flops / TF32).  The eager step
+    # is host-bound (an event pair then also measures the ~10-20 us the host needs to issue the launch), so the launches that
+    # matter -- at least 8 us at the roofline -- are REPLAYED with their own arguments behind a queue of work that keeps the
+    # host ahead of the device; each one is timed by its own event pair on the launching stream.
+    g_rows = [(s_.elapsed_time(e_), w) for t_, s_, e_, w in rec if t_ == "gemm"]
+    at_peak = lambda w: max(w["bytes"] / (hbm_peak * 1e9), w["flops"] / (tf32_peak * 1e12))
+    replay = [(a_, k_, w) for a_, k_, w in gemm_calls if at_peak(w) >= 8e-6]
+    blocker = torch.empty(256 << 20, device=dev, dtype=torch.float32)
+    timings = []
+    for _ in range(2):  # first pass warms the tensor-map / attribute caches
+        timings.clear()
+        for _ in range(4):
+            blocker.zero_()
+        for a_, k_, w in replay:
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            orig_gemm(*a_, **k_)
+            e_.record()
+            timings.append((s_, e_, w))
         torch.cuda.synchronize()
-        ops.gemm, ops.fov_crop, ops.attention_fwd, ops.attention_bwd = orig_gemm, orig_crop, orig_af, orig_ab
-        step_ms = ev0.elapsed_time(ev1)
-        hbm_peak = peaks["hbm_gbs"]
-        tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0  # kind::tf32 runs at half the bf16 rate
-        for tag in ("fov_crop", "attention"):
-            rows = [(s.elapsed_time(e), w) for t_, s, e, w in rec if t_ == tag]
-            if rows:
-                # event pairs around eager launches: exact for the long kernels (crop), inflated by host issue time for short ones
-                kernels[tag] = {"launches": len(rows), "ms": round(sum(r[0] for r in rows), 3), "work": sum(r[1] for r in rows)}
-                if tag == "attention":
-                    kernels[tag]["ms_note"] = "eager event pairs, includes host launch gaps; see profiles/*ncu_launch_summary* for device times"
-        # GEMM launches, split by the roofline that bounds each one (time at peak: bytes / HBM vs flops / TF32).  The eager step
-        # is host-bound (an event pair then also measures the ~10-20 us the host needs to issue the launch), so the launches that
-        # matter -- at least 8 us at the roofline -- are REPLAYED with their own arguments behind a queue of work that keeps the
-        # host ahead of the device; each one is timed by its own event pair on the launching stream.
-        g_rows = [(s.elapsed_time(e), w) for t_, s, e, w in rec if t_ == "gemm"]
-        at_peak = lambda w: max(w["bytes"] / (hbm_peak * 1e9), w["flops"] / (tf32_peak * 1e12))
-        replay = [(a_, k_, w) for a_, k_, w in gemm_calls if at_peak(w) >= 8e-6]
-        blocker = torch.empty(256 << 20, device=dev, dtype=torch.float32)
-        timings = []
-        for _ in range(2):  # first pass warms the tensor-map / attribute caches
-            timings.clear()
-            for _ in range(4):
-                blocker.zero_()
-            for a_, k_, w in replay:
-                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s_.record()
-                orig_gemm(*a_, **k_)
-                e_.record()
-                timings.append((s_, e_, w))
-            torch.cuda.synchronize()
-        del blocker
-        fam = {"hbm": [0.0, 0.0, 0.0, 0], "tensor": [0.0, 0.0, 0.0, 0]}
-        for s_, e_, w in timings:
-            ms_l = s_.elapsed_time(e_)
-            f = fam["hbm" if w["bytes"] / (hbm_peak * 1e9) >= w["flops"] / (tf32_peak * 1e12) else "tensor"]
-            f[0] += ms_l; f[1] += w["bytes"]; f[2] += w["flops"]; f[3] += 1
-        gemm_calls.clear()
-        kernels["gemm"] = {"launches": len(g_rows), "replayed_for_roofline": len(timings)}
-        for name, (ms_f, by, fl, n) in fam.items():
-            if n:
-                kernels[f"gemm_{name}_bound"] = {"launches": n, "ms": round(ms_f, 3), "achieved_gbs": round(by / ms_f / 1e6, 1),
-                                                 "achieved_tflops": round(fl / ms_f / 1e9, 1), "avg_launch_us": round(1e3 * ms_f / n, 2)}
-        dom = "hbm" if fam["hbm"][0] >= fam["tensor"][0] else "tensor"
-        ms_f, by, fl, n = fam[dom]
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")  # per-launch dram bytes of the same launches (ncu --set full)
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+    del blocker
+    fam = {"hbm": [0.0, 0.0, 0.0, 0], "tensor": [0.0, 0.0, 0.0, 0]}
+    for s_, e_, w in timings:
+        ms_l = s_.elapsed_time(e_)
+        f = fam["hbm" if w["bytes"] / (hbm_peak * 1e9) >= w["flops"] / (tf32_peak * 1e12) else "tensor"]
+        f[0] += ms_l; f[1] += w["bytes"]; f[2] += w["flops"]; f[3] += 1
+    gemm_calls.clear()
+    kernels["gemm"] = {"launches": len(g_rows), "replayed_for_roofline": len(timings)}
+    for name, (ms_f, by, fl, n) in fam.items():
+        if n:
+            kernels[f"gemm_{name}_bound"] = {"launches": n, "ms": round(ms_f, 3), "achieved_gbs": round(by / ms_f / 1e6, 1),
+                                             "achieved_tflops": round(fl / ms_f / 1e9, 1), "avg_launch_us": round(1e3 * ms_f / n, 2)}
+    dom = "hbm" if fam["hbm"][0] >= fam["tensor"][0] else "tensor"
+    ms_f, by, fl, n = fam[dom]
+    traffic = traffic_src = None
+    tpath = os.path.join(ROOT, "profiles", "r2_gemm_dram_traffic.json")  # per-launch dram bytes of the same launches (ncu --set full, this round's build)
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+    if n:
         if dom == "hbm":
             achieved, peak, unit = by / ms_f / 1e6, hbm_peak, "GB/s"
             src = f"{peak_src} HBM copy bandwidth"
         else:
             achieved, peak, unit = fl / ms_f / 1e9, tf32_peak, "TFLOP/s"
-            src = f"{peak_src} bf16 dense sustained / 2 (kind::tf32)"
+            src = "cuBLAS TF32 8192^3 sustained, measured in this run"
         roofline = {"kernel": "gemm_tf32_persistent_kernel / gemm_tf32_kernel (tcgen05.mma kind::tf32): the HBM-bound launches of one step "
                               "(frame-encoder QKV / FFN / projection GEMMs, K = 128..384)" if dom == "hbm" else
                               "gemm_tf32_kernel (tcgen05.mma kind::tf32): the tensor-bound launches of one step",
                     "bound": dom, "achieved": round(achieved, 1), "peak": peak, "unit": unit, "frac": round(achieved / peak, 4),
-                    "traffic": traffic, "peak_source": src, "launches": n, "avg_launch_us": round(1e3 * ms_f / n, 2),
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": src, "launches": n,
+                    "avg_launch_us": round(1e3 * ms_f / n, 2),
                     "algorithmic_bytes_per_launch": round(by / n), "algorithmic_flops_per_launch": round(fl / n),
                     "share_of_step": round(ms_f / (ms / args.steps), 3),  # replayed launch time / timed step (compare with the ncu list)
                     "timing": "the step's own launches (same tensors and arguments), replayed back to back after the step with one CUDA "
                               "event pair per launch on the launching stream; launches below 8 us at the roofline are left out"}
-        if "fov_crop" in kernels:
-            c = kernels["fov_crop"]
-            gbs = c["work"] / (c["ms"] / 1e3) / 1e9
-            kernels["fov_crop"].update({"achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4)})
-        for k in kernels.values():
-            k.pop("work", None)
-        if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
-            with open(os.path.join(ROOT, "gpurun_out", "gemm_shapes.txt"), "w") as f:
-                table = []
-                for key, idxs in shapes.items():
-                    ms_list = [rec[i][1].elapsed_time(rec[i][2]) for i in idxs]
-                    table.append((sum(ms_list), len(idxs), key))
-                for tot, cnt, (Md, Nd, Kd, amn, bmn, accf) in sorted(table, reverse=True):
-                    fl = 2.0 * Md * Nd * Kd
-                    by = 4.0 * (Md * Kd + Nd * Kd + Md * Nd)  # without epilogue operands
-                    f.write(f"{tot:8.3f} ms {cnt:3d} x {1e3 * tot / cnt:8.1f} us  M={Md:6d} N={Nd:5d} K={Kd:6d} a_mn={int(amn)} b_mn={int(bmn)} acc={int(accf)}"
-                            f"  {fl / (tot / cnt) / 1e9:7.1f} TFLOP/s {by / (tot / cnt) / 1e6:7.0f} GB/s\n")
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            cpu_baseline = cpu_reference(cfg, spec, sample_clips=8, steps=2, warmup=1)
+    if "fov_crop" in kernels:
+        c = kernels["fov_crop"]
+        gbs = c["work"] / (c["ms"] / 1e3) / 1e9
+        kernels["fov_crop"].update({"achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4)})
+    for k in kernels.values():
+        k.pop("work", None)
+    if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        with open(os.path.join(ROOT, "gpurun_out", "gemm_shapes.txt"), "w") as f:
+            table = []
+            for key, idxs in shapes.items():
+                ms_list = [rec[i][1].elapsed_time(rec[i][2]) for i in idxs]
+                table.append((sum(ms_list), len(idxs), key))
+            for tot, cnt, (Md, Nd, Kd, amn, bmn, accf) in sorted(table, reverse=True):
+                fl = 2.0 * Md * Nd * Kd
+                by = 4.0 * (Md * Kd + Nd * Kd + Md * Nd)  # without epilogue operands
+                f.write(f"{tot:8.3f} ms {cnt:3d} x {1e3 * tot / cnt:8.1f} us  M={Md:6d} N={Nd:5d} K={Kd:6d} a_mn={int(amn)} b_mn={int(bmn)} acc={int(accf)}"
+                        f"  {fl / (tot / cnt) / 1e9:7.1f} TFLOP/s {by / (tot / cnt) / 1e6:7.0f} GB/s\n")
+    barrier()
+    if rank == 0 and world == 1:
+        # free the product's device memory before the comparators run
+        del trainer, prefetch, batch, targets
+        torch.cuda.empty_cache()
+        if not args.no_eager_baseline:
+            eager = eager_gpu_reference(B, dev, steps=5, warmup=2)
+        if not args.no_cpu_baseline:
+            cpu_baseline = cpu_reference(sample_clips=8, steps=2, warmup=1)
     barrier()
 
     if rank == 0:
@@ -354,13 +391,15 @@ def run_ours(args):
                                    "paper config, random-init patch backbone 256^2/p32/C1024, GEM-shaped clips",
                        "global_batch": world * B, "batch_per_gpu": B, "parallelism": f"dp{world}", "fov": args.fov,
                        "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB of consumed frames + gps + gaze per step per GPU)",
-                       "cuda_graph": bool(trainer.use_cuda_graph),
-                       "dropout": "feature/view/gaze dropout 0 (parity configuration)", "backbone": "frozen (reference: epoch <= 10)"},
+                       "cuda_graph": bool(use_graph),
+                       "dropout": ("paper configuration: view 0.6 / gaze 0.2 / feature 0.05 (full_comparison.py:272-275)" if args.paper_dropout
+                                   else "feature/view/gaze dropout 0 (parity configuration)"),
+                       "backbone": "frozen (reference: epoch <= 10)"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "loss": loss_host},
             "gpu_launches": int(launches),
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "kernels": kernels, "measured_tf32_peak": tf32, "eager_gpu_baseline": eager, "cpu_baseline": cpu_baseline,
             "loss": float(loss.item()),
         }
         print(json.dumps(line), flush=True)
@@ -369,11 +408,72 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference(cfg, spec, sample_clips: int, steps: int, warmup: int):
+def _oracle_trainable(O, sd):
+    return {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and not k.endswith(".pe") and
+                                        not k.startswith("video_backbone")) for k, v in sd.items()}
+
+
+def eager_gpu_reference(B: int, dev, steps: int, warmup: int):
+    """The existing implementation on the same box: the reference's algorithm as a plain
+    PyTorch program (the pinned oracle port -- the reference package itself cannot be imported without lightning / timm /
+    torchcache) moved to the GPU: ATen / cuBLAS / cuDNN kernels launched eagerly, CPU randint draws uploaded inside every
+    attention call exactly as routeformer's ProbAttention does.  Same step as the product arm (fwd + loss + bwd + clip + AdamW)
+    on the same synthetic batch size, timed with CUDA events; both matmul precisions the reference could run at are reported
+    ("medium" is what experiments/full_comparison.py:48 sets).  A comparator, never part of the product path."""
+    try:
+        from oracle import routeformer_oracle as O
+
+        cfg, spec = O.OracleConfig(**PAPER), O.BackboneSpec(**BACKBONE)
+        host = O.synthetic_batch(B, cfg, "gem", seed=5)
+        g = torch.Generator().manual_seed(6)
+        t_wp = (host["gps"][:, -1:, :] + torch.cumsum(1.83 + 0.91 * torch.randn(B, cfg.pred_len, 2, generator=g), 1)).to(dev)
+        t_dense = torch.randn(B, cfg.pred_len, cfg.image_embedding_size, generator=g).to(dev)
+        batch = {k: v.to(dev) for k, v in host.items()}
+        del host
+        sd = {k: v.to(dev) for k, v in O.fill_state_dict(O.state_dict_template(cfg, spec), 0).items()}
+        params = _oracle_trainable(O, sd)
+        train_p = [p for p in params.values() if p.requires_grad]
+        opt = torch.optim.AdamW(train_p, lr=1e-5, weight_decay=1e-4, fused=True)
+        model = O.Routeformer(params, cfg, spec)
+        out = {"unit": "clips/s", "batch": B, "kind": "oracle port of the reference algorithm on cuda:0, eager PyTorch " + torch.__version__,
+               "steps": steps, "warmup": warmup}
+        prev = torch.get_float32_matmul_precision()
+        for precision in ("medium", "highest"):
+            torch.set_float32_matmul_precision(precision)
+            torch.backends.cudnn.allow_tf32 = precision != "highest"
+            times = []
+            for i in range(warmup + steps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                opt.zero_grad(set_to_none=True)
+                model.tops.clear()
+                wp, dense = model.forward(batch, training=True)
+                loss = O.future_discounted_loss(wp, t_wp) + 0.5 * O.future_discounted_loss(dense, t_dense)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(train_p, 2.5)
+                opt.step()
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= warmup:
+                    times.append(e0.elapsed_time(e1))
+            ms = statistics.median(times)
+            out["value" if precision == "medium" else "value_fp32_highest"] = round(B / (ms / 1e3), 2)
+            out["ms_per_step" if precision == "medium" else "ms_per_step_fp32_highest"] = round(ms, 2)
+        torch.set_float32_matmul_precision(prev)
+        out["precision"] = "value: torch.set_float32_matmul_precision('medium') as full_comparison.py:48; value_fp32_highest: fp32"
+        out["peak_mem_gb"] = round(torch.cuda.max_memory_allocated(dev) / 1e9, 1)
+        return out
+    except Exception as exc:  # a comparator must never take the product's line down with it
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(sample_clips: int, steps: int, warmup: int):
     """The reference algorithm's CPU path (oracle port: functional PyTorch restatement pinned against the reference) timed on
     the host cores: fwd + loss + bwd + AdamW on a bounded sample of the same workload."""
     from oracle import routeformer_oracle as O
 
+    cfg, spec = O.OracleConfig(**PAPER), O.BackboneSpec(**BACKBONE)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = O.fill_state_dict(O.state_dict_template(cfg, spec), 0)
@@ -406,13 +506,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import routeformer_oracle as O
-
-    cfg, spec = O.OracleConfig(**PAPER), O.BackboneSpec(**BACKBONE)
     sample = 8
     # K and W are honoured up to a bound that keeps the CPU run within a few minutes (one step of the 8-clip sample takes ~0.7 s)
     steps, warmup = max(1, min(args.steps, 200)), max(1, min(args.warmup, 10))
-    res = cpu_reference(cfg, spec, sample_clips=sample, steps=steps, warmup=warmup)
+    res = cpu_reference(sample_clips=sample, steps=steps, warmup=warmup)
     line = {
         "impl": "reference", "metric": "routeformer_fwd_bwd_clips_per_sec", "value": res["value"], "unit": "clips/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": round(1e3 * res["sec_per_step"], 1), "higher_is_better": True,
@@ -423,6 +520,222 @@ def run_reference(args):
         "e2e": {"value": res["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def _forward_runner(model, dev, use_graph: bool):
+    from routeformer_b200.parallel import GraphedForward
+
+    if use_graph:
+        return GraphedForward(model)
+
+    def eager(batch):
+        with torch.no_grad():
+            return model(batch)
+
+    eager.graph_launches = 0
+    eager.prefetch_draws = lambda: None
+    return eager
+
+
+def _time_forward(run, batch, steps: int, warmup: int):
+    for _ in range(warmup):
+        run(batch)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = run(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), out
+
+
+def run_fwd(args):
+    """BASELINE.json configs[1]: full-modality forward (eval), batch 64, random-init encoders, 1xB200 (N > 1: replicas)."""
+    from routeformer_b200 import ops
+    from routeformer_b200.parallel import BatchPrefetcher
+
+    dist, world, rank, local, dev, barrier, max_over_ranks = dist_setup(args)
+    B = args.batch_per_gpu
+    host_batch, _ = build_case(B, seed=100 + rank)
+    torch.manual_seed(0)
+    model = build_model(args.fov).to(dev).eval()
+    run = _forward_runner(model, dev, not args.no_graph)
+    pinned = {k: v.contiguous().pin_memory() for k, v in host_batch.items()}
+    batch = model.stage_batch(pinned, dev)
+    in_bytes = sum(v.numel() * v.element_size() for v in batch.values())
+    for _ in range(args.warmup):
+        run(batch)
+    if getattr(run, "static_batch", None) is not None:
+        batch = run.static_batch
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = ops.launch_count
+    ms, out = _time_forward(run, batch, args.steps, 0)
+    launches = (ops.launch_count - launches0) // max(args.steps, 1) + run.graph_launches
+    clocks = sampler.stop() if sampler else None
+    ms = max_over_ranks(ms)
+    value = world * B * args.steps / (ms / 1e3)
+    # end to end: pinned host batch -> staged consumed frames -> forward -> waypoints back on the host, every step
+    prefetch = BatchPrefetcher(model, dev, depth=2)
+    e2e_steps = max(20, min(args.steps, 40))
+
+    def e2e_step():
+        b, _t = prefetch.get()
+        wp, dense = run(b)
+        prefetch.release(b)
+        prefetch.submit(pinned, ())
+        run.prefetch_draws()
+        return wp.cpu()
+
+    prefetch.submit(pinned, ())
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        wp_host = e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    if rank == 0:
+        line = {"metric": "routeformer_fwd_clips_per_sec", "mode": "fwd", "value": round(value, 2), "unit": "clips/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate; fp16 patch embedding)", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[1]: Routeformer GPS+scene video+gaze FoV forward (eval), paper config, random-init patch "
+                                       "backbone, GEM-shaped clips", "batch_per_gpu": B, "global_batch": world * B, "fov": args.fov,
+                           "cuda_graph": not args.no_graph, "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB per step per GPU)"},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": round(world * B * e2e_steps / (ms_e2e / 1e3), 2), "unit": "clips/s", "h2d_bytes_per_step": int(in_bytes),
+                        "d2h_bytes_per_step": int(wp_host.numel() * 4), "steps": e2e_steps},
+                "waypoint_checksum": float(wp_host.double().sum())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_dreyeve_sweep(args):
+    """BASELINE.json configs[3]: DR(eye)VE-shaped clips (216x768 / 216x384 roof camera, 240x320 eye-tracker camera, two gaze samples
+    per frame, rotate_motion), full-modality inference, batch 32...1024; plus the longer-video axis (5 fps: 39 frames per view)."""
+    from routeformer_b200 import synthetic as S
+    from routeformer_b200.routeformer import StagedBatch
+
+    dist, world, rank, local, dev, barrier, max_over_ranks = dist_setup(args)
+    rows = []
+    for fps, batches in ((1, (32, 64, 128, 256, 512, 1024)), (5, (32, 128))):
+        torch.manual_seed(0)
+        model = build_model(args.fov, shapes="dreyeve").to(dev).eval()
+        model.configs.video_fps = model.configs.gaze_fps = fps
+        from routeformer_b200.routeformer import frame_indices
+        F_frames = len(frame_indices(40, 5 // fps))
+        for B in batches:
+            g = torch.Generator(device=dev).manual_seed(7 + B)
+            (hl, wl), (hr, wr), (hf, wf), gps_n, mean, std = S.SHAPES["dreyeve"]
+            batch = StagedBatch()
+            batch["gps"] = torch.cumsum(mean + std * torch.randn(B, 40, 2, device=dev, generator=g), 1)
+            for key, (h, w) in (("left_video", (hl, wl)), ("right_video", (hr, wr)), ("front_video", (hf, wf))):
+                batch[key] = torch.rand(B, F_frames, 3, h, w, device=dev, generator=g).to(torch.float16)  # only the consumed frames
+                batch.video_len[key] = 40
+            batch["gaze"] = torch.rand(B, gps_n * 40, 2, device=dev, generator=g)
+            in_bytes = sum(v.numel() * v.element_size() for v in batch.values())
+            run = _forward_runner(model, dev, not args.no_graph)
+            steps = max(3, min(args.steps, int(2048 / B) + 2))
+            ms, out = _time_forward(run, batch, steps, 2)
+            ms = max_over_ranks(ms)
+            rows.append({"batch": B, "video_fps": fps, "frames_per_view": F_frames, "clips_per_s": round(world * B * steps / (ms / 1e3), 1),
+                         "ms_per_batch": round(ms / steps, 3), "steps": steps, "input_mb": round(in_bytes / 1e6),
+                         "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1)})
+            del run, batch, out
+            torch.cuda.empty_cache()
+    if rank == 0:
+        best = max(r["clips_per_s"] for r in rows if r["video_fps"] == 1)
+        print(json.dumps({"metric": "routeformer_fwd_clips_per_sec", "mode": "dreyeve_sweep", "value": best, "unit": "clips/s", "n_gpus": world,
+                          "higher_is_better": True, "data": "synthetic", "dtype": "tf32 / fp16 patch embedding",
+                          "config": {"workload": "BASELINE configs[3]: DR(eye)VE-shaped full-modality inference sweep, inputs resident in HBM "
+                                                 "(consumed frames only), paper config, rotate_motion", "cuda_graph": not args.no_graph},
+                          "sweep": rows}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_crop_micro(args):
+    """BASELINE.json configs[4]: FoV crop + visual-encoder micro-benchmark: 16-frame clips, 224^2 gaze-jittered crops (window 0.5 of
+    the frame), patch-embedding GEMM with p = 28 (8x8 grid); HBM GB/s of the crop and tensor TFLOP/s of the GEMM vs the rooflines."""
+    from routeformer_b200 import ops
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    peaks, peak_src = measured_peaks()
+    S_out, p, C, clips, frames_per_clip = 224, 28, 1024, args.batch_per_gpu, 16
+    n = clips * frames_per_clip
+    g = torch.Generator(device=dev).manual_seed(3)
+    centers = (0.5 + 0.1 * torch.randn(n, 2, device=dev, generator=g)).clamp(0.0, 1.0)
+    windows = torch.full((n, 2), 0.5, device=dev)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.float32)  # 1 GiB > L2
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps
+
+    rows = []
+    for name, (H, W), dtype in (("front 324x326 fp16", (324, 326), torch.float16), ("scene 86x384 fp16", (86, 384), torch.float16),
+                                ("full-res 1080x1088 u8", (1080, 1088), torch.uint8), ("full-res 1080x1088 fp16", (1080, 1088), torch.float16)):
+        n_case = n if H < 1000 else max(64, n // 8)
+        if dtype == torch.uint8:
+            frames = torch.randint(0, 256, (n_case, 3, H, W), device=dev, dtype=torch.uint8, generator=g)
+        else:
+            frames = torch.rand(n_case, 3, H, W, device=dev, generator=g).to(dtype)
+        c_, w_ = centers[:n_case].contiguous(), windows[:n_case].contiguous()
+        for layout, out_dtype in (("planar", torch.bfloat16), ("patch-major", torch.float16)):
+            G = S_out // p
+            out = (torch.empty(n_case, 3, S_out, S_out, device=dev, dtype=out_dtype) if layout == "planar"
+                   else torch.empty(n_case * G * G, 3 * p * p, device=dev, dtype=out_dtype))
+            ms = timed(lambda: ops.fov_crop(frames, c_, w_, S_out, mean, std, patch=0 if layout == "planar" else p, out=out), 10)
+            # algorithmic bytes (SURVEY 8(d)): the source window actually covered, clipped to the frame, + the output patch
+            x0 = (c_[:, 0] - 0.25).clamp(0, 1) * W
+            x1 = (c_[:, 0] + 0.25).clamp(0, 1) * W
+            y0 = (c_[:, 1] - 0.25).clamp(0, 1) * H
+            y1 = (c_[:, 1] + 0.25).clamp(0, 1) * H
+            src_bytes = float((3 * (x1 - x0) * (y1 - y0)).sum()) * frames.element_size()
+            by = src_bytes + out.numel() * out.element_size()
+            rows.append({"case": name, "layout": layout, "out_dtype": str(out_dtype).split(".")[-1], "frames": n_case,
+                         "ms": round(ms, 4), "algorithmic_mb": round(by / 1e6, 1), "gbs": round(by / ms / 1e6, 1),
+                         "frac_of_hbm_peak": round(by / ms / 1e6 / peaks["hbm_gbs"], 4)})
+        del frames
+    # patch embedding: [n*64, 3*28*28] fp16 x [1024, 2352] fp16 -> fp32 tokens (+ bias), tcgen05 kind::f16
+    G = S_out // p
+    patches = torch.randn(n * G * G, 3 * p * p, device=dev, generator=g).to(torch.float16)
+    wmat = (torch.randn(C, 3 * p * p, device=dev, generator=g) / 48.0).to(torch.float16)
+    bias = torch.zeros(C, device=dev)
+    tokens = torch.empty(n * (G * G + 1), C, device=dev)
+    ms = timed(lambda: ops.gemm(patches, wmat, tokens, bias=bias, out_group=(G * G, G * G + 1, 0), round_f16=True), 10)
+    fl = 2.0 * patches.shape[0] * C * patches.shape[1]
+    f16_peak = peaks.get("bf16_tflops", 1590.0)
+    gemm_row = {"M": patches.shape[0], "N": C, "K": patches.shape[1], "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1),
+                "frac_of_bf16_peak": round(fl / ms / 1e9 / f16_peak, 4), "peak": f16_peak}
+    front = next(r for r in rows if r["case"].startswith("front") and r["layout"] == "patch-major")
+    print(json.dumps({"metric": "fov_crop_hbm_gbs", "mode": "crop_micro", "value": front["gbs"], "unit": "GB/s", "n_gpus": 1,
+                      "higher_is_better": True, "data": "synthetic", "dtype": "fp16 / u8 sources, bf16 / fp16 outputs",
+                      "config": {"workload": "BASELINE configs[4]: FoV crop + visual encoder micro-benchmark, 16-frame clips, 224^2 crops, "
+                                             "gaze-jittered (N(0.5, 0.1^2) clipped), window 0.5 of the frame", "clips": clips,
+                                 "l2": "1 GiB flush write between timed launches"},
+                      "roofline": {"bound": "hbm", "achieved": front["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": front["frac_of_hbm_peak"], "traffic": None, "peak_source": f"{peak_src} HBM copy bandwidth"},
+                      "crop": rows, "patch_embed_gemm": gemm_row}), flush=True)
 
 
 def main():
@@ -438,6 +751,11 @@ def main():
     ap.add_argument("--no-wgrad-overlap", action="store_true", help="keep the weight-gradient GEMMs on the main stream")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one captured CUDA graph")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up + --steps steps, no e2e / roofline / CPU legs")
+    ap.add_argument("--mode", default="train", choices=["train", "fwd", "dreyeve_sweep", "crop_micro"],
+                    help="train = the headline metric (BASELINE configs[2], default); fwd = configs[1]; dreyeve_sweep = configs[3]; "
+                         "crop_micro = configs[4]")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU comparator")
+    ap.add_argument("--paper-dropout", action="store_true", help="train with the paper's dropouts (view 0.6 / gaze 0.2 / feature 0.05)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.profile:
         args.warmup = 3
@@ -445,8 +763,14 @@ def main():
         args.warmup = 1
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "fwd":
+        run_fwd(args)
+    elif args.mode == "dreyeve_sweep":
+        run_dreyeve_sweep(args)
+    elif args.mode == "crop_micro":
+        run_crop_micro(args)
     else:
-        run_ours(args)
+        run_train(args)
 
 
 if __name__ == "__main__":

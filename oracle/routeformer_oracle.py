@@ -537,13 +537,13 @@ class Routeformer:
     def _scatter(self, feats: Tensor, idx: Tensor, B: int, T: int) -> Tensor:
         """Zero [B,T,E] with the encoded frames at their time indices (routeformer.py:443-459)."""
         full = torch.zeros(B, T, feats.shape[-1], device=feats.device)
-        return full.index_copy(1, idx, feats.view(B, -1, feats.shape[-1]))
+        return full.index_copy(1, idx.to(feats.device), feats.view(B, -1, feats.shape[-1]))
 
     def _view(self, video: Tensor, rel: int, drop: bool, draw, gaze_xy: Optional[Tensor] = None) -> Tensor:
         B, T = video.shape[:2]
         idx = frame_indices(T, rel)
         if drop:
-            feats = torch.zeros(B * len(idx), self.cfg.image_embedding_size)
+            feats = torch.zeros(B * len(idx), self.cfg.image_embedding_size, device=video.device)
         else:
             centers = None
             if gaze_xy is not None and self.fov == "gaze":
@@ -578,7 +578,7 @@ class Routeformer:
                 drop_g = bool(torch.rand(1) < cfg.gaze_dropout)
             front = batch["front_video"]
             if drop_g:
-                g = torch.zeros(front.shape[0], front.shape[1], cfg.image_embedding_size)
+                g = torch.zeros(front.shape[0], front.shape[1], cfg.image_embedding_size, device=front.device)
             else:
                 gaze = batch["gaze"].to(torch.float32)
                 gaze_ds = median_downsample(gaze, cfg.seq_len)

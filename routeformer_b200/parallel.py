@@ -193,6 +193,68 @@ class DataParallelTrainer:
         return loss
 
 
+class GraphedForward:
+    """Inference at speed: the eval-mode forward (~400 launches, most of them a few microseconds long) captured once into a
+    CUDA graph and replayed per batch.  The CPU random draws of every forward (ProbSparse key sampling, reference order) are
+    still made on the host and reach the graph through the model's persistent pinned index buffer, exactly as in
+    DataParallelTrainer.  Static shapes; not for the autoregressive branch (its window loop re-plans draws per window)."""
+
+    def __init__(self, model):
+        if model.configs.autoregressive:
+            raise ValueError("GraphedForward does not cover the autoregressive branch")
+        self.model = model
+        self._graph = None
+        self.static_batch = None
+        self._out = None
+        self._replayed = None
+        self.graph_launches = 0
+
+    def _capture(self, batch) -> None:
+        m = self.model
+        static = type(batch)() if isinstance(batch, dict) else {}
+        for k, v in batch.items():
+            static[k] = v.clone()
+        if hasattr(batch, "video_len"):
+            static.video_len = dict(batch.video_len)
+        self.static_batch = static
+        rng_state = torch.get_rng_state()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):
+                m(static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        before = ops.launch_count
+        with torch.no_grad(), torch.cuda.graph(self._graph):
+            self._out = m(static)
+        self.graph_launches = ops.launch_count - before
+        torch.set_rng_state(rng_state)
+
+    def __call__(self, batch):
+        if self.model.training:
+            raise RuntimeError("GraphedForward is an inference path: call model.eval() first")
+        if self._graph is None:
+            self._capture(batch)
+        if batch is not self.static_batch:
+            for k, v in batch.items():
+                if v.data_ptr() != self.static_batch[k].data_ptr():
+                    self.static_batch[k].copy_(v, non_blocking=True)
+        if self._replayed is not None:
+            self._replayed.synchronize()  # the previous replay has consumed the pinned index buffer
+        if not self.model.commit_deferred_draws():
+            self.model.prepare_draws(self.static_batch, training=False, refill_only=True)
+        self._graph.replay()
+        self._replayed = torch.cuda.Event()
+        self._replayed.record()
+        return self._out
+
+    def prefetch_draws(self) -> None:
+        if self._graph is not None and not self.model._deferred_tables:
+            self.model.prepare_draws(self.static_batch, training=False, refill_only="defer")
+
+
 class BatchPrefetcher:
     """Stages pinned host batches onto the device on a side stream, `depth` batches ahead of the step that consumes them.
 
