@@ -119,9 +119,14 @@ class precise:
 
 def _tf32_split(t: torch.Tensor):
     """(hi, lo): hi = t rounded to 10 mantissa bits (round-half-away in magnitude), lo = t - hi (exact in fp32)."""
+    rows, cols = t.shape
+    pitch = (cols + 3) // 4 * 4  # TMA needs a 16 B row pitch: keep the padding a column-slice view had
+    hi = torch.zeros(rows, pitch, device=t.device, dtype=torch.float32)[:, :cols]
+    lo = torch.zeros(rows, pitch, device=t.device, dtype=torch.float32)[:, :cols]
     c = t.contiguous()
-    hi = ((c.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
-    return hi, c - hi
+    hi.copy_(((c.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32))
+    torch.sub(c, hi, out=lo) if pitch == cols else lo.copy_(c - hi)
+    return hi, lo
 
 
 def _gemm_precise(A, B, out, *, a_mn, b_mn, residual, accumulate, colsum_a, **kw):

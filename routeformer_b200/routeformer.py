@@ -241,9 +241,11 @@ class Routeformer(nn.Module):
         if refill_only == "defer":  # draw now, write the pinned buffer later (commit_deferred_draws): it may still be in use
             self._deferred_tables.append((host, torch.cat([t.reshape(-1) for t in tables]).to(torch.int32)))
             return []
-        if copied is not None:
+        capturing = device.type == "cuda" and torch.cuda.is_current_stream_capturing()
+        if copied is not None and not capturing:
             # eager path: the previous H2D copy out of this pinned buffer (an earlier forward, the target pass, the previous
-            # autoregressive window) may still be queued -- rewriting the buffer now would hand that forward torn index tables
+            # autoregressive window) may still be queued -- rewriting the buffer now would hand that forward torn index tables.
+            # (While a graph is being captured nothing executes: the warm-up passes were synchronised before the capture began.)
             copied.synchronize()
             self._idx_slots[key][2] = None
         off = 0
@@ -253,7 +255,7 @@ class Routeformer(nn.Module):
         if refill_only:
             return []
         dev.copy_(host, non_blocking=True)
-        if device.type == "cuda" and not torch.cuda.is_current_stream_capturing():
+        if device.type == "cuda" and not capturing:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
             self._idx_slots[key][2] = ev

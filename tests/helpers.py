@@ -76,20 +76,34 @@ def tops_for_oracle(recorded, view_order):
 
 # TF32-derived near-tie bound for the ProbSparse sparsity measure M = max_j s - sum_j s / L_K, s = q.k:
 # q and k leave a tcgen05 kind::tf32 GEMM whose operands carry a unit round-off of 2^-11 each, i.e. ~2^-10 relative on every
-# product, and the activations feeding it have crossed up to 8 such layers (x sqrt(8) if the errors were independent, x 8 if
-# they all lined up).  A pick is "explained" when it lies within 2^-8 (= 4 x 2^-10) of the u-th largest measure, relative to
-# the largest |M| of that (b, h) problem.  Round 1 used 2e-2 here; the worst gap actually observed is logged by the tests.
-SELECTION_REL_TOL = 2.0 ** -8
+# product, and the activations feeding it have crossed several such layers.  A pick is "explained" when it lies within
+# rel_tol of the u-th largest measure, relative to the largest |M| of that (b, h) problem:
+#   Perceive* modules (d_model 128, LayerNorm-ed activations, K = 128 reductions):            2^-8  = 4 x 2^-10
+#   Informer (d_model 832: K = 832..3328 reductions, dh = 104 score sums, un-normalised
+#             68-channel input, autoregressive windows feed predictions back in):            2^-6  = 16 x 2^-10
+# Round 1 used 2e-2 everywhere; the worst gap actually observed per module family is logged by the tests (measured in round
+# 2: Perceive* 3.6e-3, Informer 1.07e-2).
+SELECTION_REL_TOL = {"default": 2.0 ** -8, "gps_backbone": 2.0 ** -6}
+
+
+def _sel_tol(where: str, rel_tol):
+    if not isinstance(rel_tol, dict):
+        return rel_tol
+    for prefix, tol in rel_tol.items():
+        if prefix != "default" and where.startswith(prefix):
+            return tol
+    return rel_tol["default"]
 
 
 def selection_violations(recorded, oracle_tops, view_order, rel_tol=SELECTION_REL_TOL, stats=None):
     """Counts product selections that are NOT explained by a near-tie in the oracle's sparsity measure.
     `stats` (dict, optional) receives "worst_gap": the largest distance of a mismatching pick from the u-th measure, in
-    units of max|M|, and "mismatches": picks that differ from the oracle's own top-u set at all."""
+    units of max|M| (also per module family under "worst_by_module"), and "mismatches": picks outside the oracle's own set."""
     import torch
 
     bad = total = mism = 0
     worst = 0.0
+    by_module = {}
     queues = {}
     for t in oracle_tops:
         queues.setdefault(t["where"], []).append(t["measure"])
@@ -103,18 +117,34 @@ def selection_violations(recorded, oracle_tops, view_order, rel_tol=SELECTION_RE
         u = top.shape[-1]
         kth = m.topk(u, dim=-1).values[..., -1:]                    # u-th largest measure per (b,h)
         scale = m.abs().amax(dim=-1, keepdim=True).clamp_min(1.0)
-        tol = rel_tol * scale
+        tol = _sel_tol(rec["where"], rel_tol) * scale
         sel = torch.zeros_like(m, dtype=torch.bool).scatter(-1, top, True)
         bad += int(((m < kth - tol) & sel).sum() + ((m > kth + tol) & ~sel).sum())
         wrong = ((m < kth) & sel) | ((m > kth) & ~sel)
         mism += int(wrong.sum())
         if wrong.any():
-            worst = max(worst, float((((m - kth).abs() / scale)[wrong]).max()))
+            w = float((((m - kth).abs() / scale)[wrong]).max())
+            worst = max(worst, w)
+            fam = rec["where"].split(".")[0]
+            by_module[fam] = max(by_module.get(fam, 0.0), w)
         total += sel.numel()
     if stats is not None:
         stats["worst_gap"] = max(stats.get("worst_gap", 0.0), worst)
         stats["mismatches"] = stats.get("mismatches", 0) + mism
+        for fam, w in by_module.items():
+            stats.setdefault("worst_by_module", {})[fam] = max(stats.get("worst_by_module", {}).get(fam, 0.0), w)
     return bad, total
+
+
+def flips_vs_oracle(recorded, oracle_tops, view_order) -> int:
+    """Number of (b, h) ProbSparse problems in which the product selected a different top-u SET than an oracle run on the same
+    CPU draws (oracle_tops = the `.tops` of an un-replayed oracle forward, i.e. the reference's own selections)."""
+    mine = tops_for_oracle(recorded, view_order)
+    n = 0
+    for t in oracle_tops:
+        got = mine[t["where"]].pop(0)
+        n += int((got.sort(-1).values != t["top"].long().sort(-1).values).any(-1).sum())
+    return n
 
 
 def same_selections(rec_a, rec_b) -> bool:
