@@ -42,7 +42,7 @@ class LiveIndexSource:
         self.log.append((L_K, L_Q, U))
         return idx.to(torch.int32).unsqueeze(0).to(self.device, non_blocking=True), 0
 
-    def forced_top(self):
+    def forced_top(self, name: str = ""):
         return None
 
 
@@ -50,9 +50,12 @@ class PlannedIndexSource:
     """Replays tables that were drawn up-front in reference order and uploaded with ONE copy (Routeformer.forward)."""
 
     def __init__(self, entries, forced_tops=None):
+        """forced_tops (test hook): a list consumed in call order, or {module path: [top, ...]} consumed per path -- the
+        kernels then use these top-u selections instead of their own (ProbSparse selection is a discontinuous function of the
+        scores; forcing the reference's selections isolates the arithmetic from tie-breaking)."""
         self.entries = list(entries)  # [(key, idx_dev [g,L_Q,U] int32, idx_group)]
         self.pos = 0
-        self.tops = None if forced_tops is None else list(forced_tops)
+        self.tops = forced_tops if (forced_tops is None or isinstance(forced_tops, dict)) else list(forced_tops)
         self.top_pos = 0
 
     def take(self, L_K: int, L_Q: int, U: int):
@@ -62,9 +65,11 @@ class PlannedIndexSource:
             raise RuntimeError(f"index plan out of order: planned {key}, requested {(L_K, L_Q, U)}")
         return idx, group
 
-    def forced_top(self):
+    def forced_top(self, name: str = ""):
         if self.tops is None:
             return None
+        if isinstance(self.tops, dict):
+            return self.tops[name].pop(0)
         t = self.tops[self.top_pos]
         self.top_pos += 1
         return t
@@ -139,7 +144,7 @@ class AttentionLayer(nn.Module):
         if kind != "full":
             meta["U"], meta["u"] = sparse_budget(Lk, factor), sparse_budget(Lq, factor)
             idx, meta["idx_group"] = draw.take(Lk, Lq, meta["U"])
-            meta["forced_top"] = draw.forced_top()
+            meta["forced_top"] = draw.forced_top(name)
         if p_drop > 0.0:
             dev, D = x2.device, self.out_projection.weight.shape[0]
             prob = _site(dev, p_drop, name + ".prob", B * self.n_heads * Lq, Lk) if kind == "full" else None

@@ -91,6 +91,8 @@ class Routeformer(nn.Module):
         self.feature_dropout = c.feature_dropout
         # test hook: when set to a list, every ProbSparse call appends {"where", "top", "measure"} (the oracle replays them)
         self.record_tops: Optional[list] = None
+        # test hook: {module path: [int32 [B,H,u] device tensor per call]} -- ProbSparse selections to use instead of the kernels' own
+        self.forced_tops: Optional[dict] = None
         self.last_draw_log: List[tuple] = []
         self._idx_slots = {}
         self._deferred_tables: list = []
@@ -298,7 +300,7 @@ class Routeformer(nn.Module):
         return plan
 
     def _source(self, keys_tables, groups=0):
-        return PlannedIndexSource([(k, t, groups) for k, t in keys_tables])
+        return PlannedIndexSource([(k, t, groups) for k, t in keys_tables], self.forced_tops)
 
     # ------------------------------------------------------------------------------------------
     # visual streams
@@ -484,7 +486,7 @@ class Routeformer(nn.Module):
                 draws, log = self._plan_backbone(T, gb.pred_len)
                 tables = self._upload(draws, x.device, f"backbone_p{gb.pred_len}")
                 self.last_draw_log += log
-            out = gb.run(x, PlannedIndexSource([(k, t, 0) for k, t in zip(log, tables)]), self.record_tops)
+            out = gb.run(x, PlannedIndexSource([(k, t, 0) for k, t in zip(log, tables)], self.forced_tops), self.record_tops)
         else:  # foreign GPS backbone plugin (routeformer.py:241)
             out = gb(x[:, :, :enc_in])
         if c.decoder_mode == "recursive":

@@ -188,7 +188,8 @@ def test_gemm_dact_and_accumulate(ops):
 
 
 # ------------------------------------------------------------------------------------------------ FoV crop
-@pytest.mark.parametrize("H,W,S,patch", [(324, 326, 224, 28), (86, 384, 256, 32), (36, 34, 32, 8), (240, 320, 64, 0)])
+@pytest.mark.parametrize("H,W,S,patch", [(324, 326, 224, 28), (86, 384, 256, 32), (36, 34, 32, 8), (240, 320, 64, 0), (37, 35, 32, 8),
+                                         (216, 768, 256, 32), (64, 1088, 224, 28)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.uint8])
 def test_fov_crop(ops, H, W, S, patch, dtype):
     gen = g(H + W)
@@ -220,6 +221,25 @@ def test_fov_crop(ops, H, W, S, patch, dtype):
     hf = ops.fov_crop(frames.to(DEV), centers.to(DEV), windows.to(DEV), S, spec.mean, spec.std, patch=patch, frame_ids=ids.to(DEV),
                       out_dtype=torch.float16)
     assert torch.equal(hf.cpu(), got.half())  # same values, rounded to fp16 (the A operand of the fp16 patch GEMM)
+
+
+def test_fov_crop_mirrored_and_offscreen(ops):
+    """Windows the tiled kernel special-cases: mirrored (fw < 0: direct gather path), entirely outside the frame (constant
+    tile), touching the left / right / top / bottom border (clamped taps with zero weight)."""
+    gen = g(77)
+    H, W, S = 48, 50, 32
+    frames = torch.rand(6, 3, H, W, generator=gen).half()
+    centers = torch.tensor([[0.5, 0.5], [3.0, 0.5], [0.0, 0.0], [1.0, 1.0], [0.5, -2.0], [0.02, 0.98]])
+    windows = torch.tensor([[-0.6, 0.8], [0.5, 0.5], [0.5, 0.5], [0.4, 0.4], [0.5, 0.5], [0.1, 0.1]])
+    spec = O.BackboneSpec()
+    ref = O.fov_crop(frames.float(), centers, windows, S, spec.mean, spec.std)
+    for patch in (0, 8):
+        out = ops.fov_crop(frames.to(DEV), centers.to(DEV), windows.to(DEV), S, spec.mean, spec.std, patch=patch).cpu()
+        want = ref
+        if patch:
+            G = S // patch
+            want = ref.view(6, 3, G, patch, G, patch).permute(0, 2, 4, 1, 3, 5).reshape(6 * G * G, 3 * patch * patch)
+        assert (out - want).abs().max() < 1e-3, patch
 
 
 # ------------------------------------------------------------------------------------------------ circular conv
