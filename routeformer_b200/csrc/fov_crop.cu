@@ -340,9 +340,11 @@ __global__ void __launch_bounds__(TILE_THREADS) fov_crop_tiled_kernel(const Tile
   }
 }
 
+// RF_CROP_TILED=1 selects the tiled kernel (read per call so tests can toggle it).  Off by default: its first version is
+// latency-bound in pass V and measured 2.6x slower than the direct gather (profiles/r2_bench_crop_micro_v1_tiled_kernel.json).
 static bool tiled_enabled() {
-  static const bool on = [] { const char* e = getenv("RF_CROP_TILED"); return !(e && e[0] == '0'); }();
-  return on;
+  const char* e = getenv("RF_CROP_TILED");
+  return e && e[0] == '1';
 }
 
 template <typename TS, typename TD>

@@ -191,7 +191,9 @@ def test_gemm_dact_and_accumulate(ops):
 @pytest.mark.parametrize("H,W,S,patch", [(324, 326, 224, 28), (86, 384, 256, 32), (36, 34, 32, 8), (240, 320, 64, 0), (37, 35, 32, 8),
                                          (216, 768, 256, 32), (64, 1088, 224, 28)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.uint8])
-def test_fov_crop(ops, H, W, S, patch, dtype):
+@pytest.mark.parametrize("tiled", ["0", "1"])  # direct 4-tap gather (default) / separable shared-memory-staged kernel
+def test_fov_crop(ops, monkeypatch, H, W, S, patch, dtype, tiled):
+    monkeypatch.setenv("RF_CROP_TILED", tiled)
     gen = g(H + W)
     n = 5
     if dtype == torch.uint8:
@@ -214,7 +216,7 @@ def test_fov_crop(ops, H, W, S, patch, dtype):
         ref = ref.view(n, 3, G, patch, G, patch).permute(0, 2, 4, 1, 3, 5).reshape(n * G * G, 3 * patch * patch)
     # white-noise frames are the worst case: |dI/dx| ~ 1/std per pixel, so a 1e-4 px difference in the fp32
     # sample position (ATen builds the grid with linspace + matmul) moves the value by ~5e-4
-    assert (got - ref).abs().max() < 1e-3 and (got - ref).abs().mean() < 2e-5
+    assert (got - ref).abs().max() < 1e-3 and (got - ref).abs().mean() < 2.5e-5
     bf = ops.fov_crop(frames.to(DEV), centers.to(DEV), windows.to(DEV), S, spec.mean, spec.std, patch=patch, frame_ids=ids.to(DEV),
                       out_dtype=torch.bfloat16)
     assert (bf.float().cpu() - ref).abs().max() < 3e-2
@@ -223,9 +225,11 @@ def test_fov_crop(ops, H, W, S, patch, dtype):
     assert torch.equal(hf.cpu(), got.half())  # same values, rounded to fp16 (the A operand of the fp16 patch GEMM)
 
 
-def test_fov_crop_mirrored_and_offscreen(ops):
+@pytest.mark.parametrize("tiled", ["0", "1"])
+def test_fov_crop_mirrored_and_offscreen(ops, monkeypatch, tiled):
     """Windows the tiled kernel special-cases: mirrored (fw < 0: direct gather path), entirely outside the frame (constant
     tile), touching the left / right / top / bottom border (clamped taps with zero weight)."""
+    monkeypatch.setenv("RF_CROP_TILED", tiled)
     gen = g(77)
     H, W, S = 48, 50, 32
     frames = torch.rand(6, 3, H, W, generator=gen).half()
@@ -353,6 +357,22 @@ def test_attention_forward_backward(ops, B, H, Lq, Lk, dh, factor, mode, layout)
     assert rel_err(dqkv_q.cpu()[:, :D].reshape(B, Lq, H, dh), q.grad) < 2e-5
     assert rel_err(dqkv_k.cpu()[:, D:2 * D].reshape(B, Lk, H, dh), k.grad) < 2e-5
     assert rel_err(dqkv_k.cpu()[:, 2 * D:].reshape(B, Lk, H, dh), v.grad) < 2e-5
+    if mode != "full":
+        # forced selection in ARBITRARY order (torch.topk(sorted=False) gives no order; Routeformer.forced_tops feeds the reference's
+        # picks straight in): forward and backward must not depend on the order of the u indices
+        forced = tops.gather(-1, torch.argsort(torch.rand(tops.shape, generator=gen), -1)).to(torch.int32).to(DEV)
+        out2 = torch.full(ref.shape, float("nan"), device=DEV)
+        top2 = torch.zeros_like(top)
+        ops.attention_fwd(qa, ka, va, B, H, Lq, Lk, dh, code, lay, idx_d, B // groups if groups > 1 else 0, U, u, out2, top2, forced_top=forced)
+        assert torch.equal(top2, forced)
+        assert rel_err(out2.cpu(), ref.detach()) < 1e-5
+        g_q = torch.zeros_like(qd)
+        g_k = g_q if qkv_k is qkv_q else torch.zeros_like(kd)
+        ops.attention_bwd(qa, ka, va, B, H, Lq, Lk, dh, code, lay, U, u, top2, dout.to(DEV), g_q, g_k[:, D:], g_k[:, 2 * D:])
+        torch.cuda.synchronize()
+        assert rel_err(g_q.cpu()[:, :D].reshape(B, Lq, H, dh), q.grad) < 2e-5
+        assert rel_err(g_k.cpu()[:, D:2 * D].reshape(B, Lk, H, dh), k.grad) < 2e-5
+        assert rel_err(g_k.cpu()[:, 2 * D:].reshape(B, Lk, H, dh), v.grad) < 2e-5
 
 
 @pytest.mark.parametrize("B,H,L,dh", [(6, 8, 65, 16), (4, 4, 40, 8), (3, 2, 20, 16)])
