@@ -22,6 +22,10 @@
 #include "common.cuh"
 
 namespace rf {
+// tensor-core forward for the small unmasked ProbSparse problems (attention_tc.cu)
+bool attention_tc_fwd_eligible(const RfAttnParams* p);
+int attention_tc_fwd(const RfAttnParams* p, cudaStream_t stream);
+
 namespace attn {
 
 constexpr int THREADS = 128;
@@ -1117,6 +1121,7 @@ extern "C" int rf_attention_fwd(const RfAttnParams* p, void* stream) {
   int rc = attn::validate(p, "rf_attention_fwd", true);
   if (rc != RF_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (attention_tc_fwd_eligible(p)) return attention_tc_fwd(p, s);
   if (attn::small_path(p)) {
     const size_t smem = attn::small_fwd_smem(p);
     RF_ATTN_SMALL_DISPATCH(attention_small_fwd_kernel, *p, p->dh, attn::small_nt(p->Lk), p->B * p->H, smem, s)

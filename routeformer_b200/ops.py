@@ -110,11 +110,20 @@ class precise:
     def __enter__(self):
         global PRECISE
         self.prev, PRECISE = PRECISE, self.on
+        # the tensor-core attention forward rounds P and V to tf32: precise mode takes the fp32 FMA kernels instead
+        self.prev_tc = _os.environ.get("RF_ATTN_TC")
+        if self.on:
+            _os.environ["RF_ATTN_TC"] = "0"
         return self
 
     def __exit__(self, *exc):
         global PRECISE
         PRECISE = self.prev
+        if self.on:
+            if self.prev_tc is None:
+                _os.environ.pop("RF_ATTN_TC", None)
+            else:
+                _os.environ["RF_ATTN_TC"] = self.prev_tc
 
 
 def _tf32_split(t: torch.Tensor):
