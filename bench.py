@@ -32,11 +32,16 @@ BACKBONE = dict(image_size=256, patch=32, channels=1024, window=0.5)
 PAPER_DROPOUT = dict(view_dropout=0.6, gaze_dropout=0.2, feature_dropout=0.05)
 
 
-def build_case(B: int, seed: int, shapes: str = "gem"):
-    """Synthetic host batch + targets from the package's own generator (the product arm never touches oracle/)."""
+def build_case(B: int, seed: int, shapes: str = "gem", u8: bool = False):
+    """Synthetic host batch + targets from the package's own generator (the product arm never touches oracle/).
+    u8: frames as raw uint8 (what a decoder produces; the crop kernel converts them like the reference's loader does)."""
     from routeformer_b200 import synthetic as S
 
     batch = S.synthetic_batch(B, 40, shapes, seed=seed)
+    if u8:
+        for k in list(batch):
+            if k.endswith("_video"):
+                batch[k] = (batch[k].float() * 255.0).round().clamp(0, 255).to(torch.uint8)
     return batch, S.synthetic_targets(batch, 30, 64, shapes, seed=seed + 1000)
 
 
@@ -158,7 +163,7 @@ def run_train(args):
 
     dist, world, rank, local, dev, barrier, max_over_ranks = dist_setup(args)
     B = args.batch_per_gpu
-    host_batch, host_targets = build_case(B, seed=100 + rank)
+    host_batch, host_targets = build_case(B, seed=100 + rank, u8=args.u8_frames)
     torch.manual_seed(0)
     model = build_model(args.fov, dropout=args.paper_dropout).to(dev).train()
     if args.no_branch_overlap:
@@ -394,7 +399,9 @@ def run_train(args):
                        "cuda_graph": bool(use_graph),
                        "dropout": ("paper configuration: view 0.6 / gaze 0.2 / feature 0.05 (full_comparison.py:272-275)" if args.paper_dropout
                                    else "feature/view/gaze dropout 0 (parity configuration)"),
-                       "backbone": "frozen (reference: epoch <= 10)"},
+                       "backbone": "frozen (reference: epoch <= 10)",
+                       "frames": ("raw uint8 frames staged on the device, converted in the crop kernel (SURVEY 8(f) N4)" if args.u8_frames
+                                  else "fp16 frames, as the reference's loader hands them over")},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "loss": loss_host},
@@ -755,6 +762,7 @@ def main():
                     help="train = the headline metric (BASELINE configs[2], default); fwd = configs[1]; dreyeve_sweep = configs[3]; "
                          "crop_micro = configs[4]")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU comparator")
+    ap.add_argument("--u8-frames", action="store_true", help="host batch holds raw uint8 frames (half the H2D bytes); converted in the crop kernel")
     ap.add_argument("--paper-dropout", action="store_true", help="train with the paper's dropouts (view 0.6 / gaze 0.2 / feature 0.05)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.profile:

@@ -36,6 +36,7 @@ extern "C" {
 #define RF_F16 1
 #define RF_BF16 2
 #define RF_U8 3
+#define RF_U8_F16 4 /* crop source only: uint8 pixel converted like the reference loader, fp16(v / 255) (io/dataset.py:1505-1522) */
 
 /* activations */
 #define RF_ACT_NONE 0
@@ -60,7 +61,8 @@ int rf_struct_size(int which);
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   const void* frames;       /* planar frames, [*, 3, H, W]; frame i starts at frames + frame_ids[i]*3*H*W */
-  int src_dtype;            /* RF_F16 | RF_F32 | RF_U8 (u8 is scaled by 1/255) */
+  int src_dtype;            /* RF_F16 | RF_F32 | RF_U8 (scaled by 1/255 in fp32) | RF_U8_F16 (scaled by 1/255 and rounded to fp16:
+                               raw uint8 frames staged on the device give bit-identical taps to the reference's host-side conversion) */
   const int* frame_ids;     /* [n_frames] source frame numbers, or NULL for 0..n_frames-1 */
   int n_frames, H, W;
   const float* centers;     /* [n_frames,2] (cx,cy) as fractions of the frame */
@@ -180,6 +182,10 @@ typedef struct {
                               (top / measure are complete).  Backward: rows 0..Lq-2 of `dout` are taken as zero and not read. */
 } RfAttnParams;
 int rf_attention_fwd(const RfAttnParams* p, void* stream);
+/* Profiling hook: installs (or clears with NULL) a device buffer of >= 16 i64; the middle CTA of every later tensor-core
+ * attention forward records clock64 at its phase boundaries (setup, tiles landed, operands prepared, scores ready, per head:
+ * measure / soft-max / P written / P.V issued, contexts written, exit). */
+int rf_debug_attn_stamps(long long* device_buffer);
 typedef struct {
   RfAttnParams f;          /* same problem description; f.top is now an INPUT; f.out unused */
   const float* dout;       /* gradient of the context, same layout as f.out */

@@ -91,7 +91,9 @@ class PatchEmbedBackbone(VideoBackboneModule):
         n_total = sum(v["video"].shape[0] * len(v["t_idx"]) for v in views)
         # fp16 clips: crop to fp16 patches and multiply in fp16 with fp32 accumulation, as the reference backbone does under
         # autocast (TimmBackbone.py:106-145) -- half the patch bytes and twice the MMA rate of the TF32 path; other dtypes: TF32.
-        half = all(v["video"].dtype == torch.float16 for v in views) and not self.proj.weight.requires_grad
+        # uint8 clips (raw frames staged on the device: half the host->device bytes) are converted in the crop kernel exactly as the
+        # reference's loader converts them on the host (fp16(v / 255), io/dataset.py:1505-1522) and then follow the fp16 path.
+        half = all(v["video"].dtype in (torch.float16, torch.uint8) for v in views) and not self.proj.weight.requires_grad
         patches = torch.empty(n_total * G * G, 3 * p * p, device=dev, dtype=torch.float16 if half else torch.float32)
         row = 0
         round_f16 = True
@@ -107,8 +109,8 @@ class PatchEmbedBackbone(VideoBackboneModule):
             else:
                 centers, windows = self._frame_fov(n, H, W, dev)
             ops.fov_crop(video, centers, windows, S, c.mean, c.std, patch=p, frame_ids=ids, n_frames=n,
-                         out=patches[row * G * G:(row + n) * G * G])
-            round_f16 = round_f16 and video.dtype == torch.float16
+                         out=patches[row * G * G:(row + n) * G * G], u8_as_f16=half)
+            round_f16 = round_f16 and video.dtype in (torch.float16, torch.uint8)
             row += n
         tokens = torch.empty(n_total * (G * G + 1), C, device=dev, dtype=torch.float32)
         tokens.view(n_total, G * G + 1, C)[:, G * G, :] = -1.0

@@ -28,6 +28,16 @@ constexpr int DH = 16;
 constexpr int CNT_WORDS = 25;  // byte counts per query row: 100 >= LP keys; an odd word pitch keeps the row reads conflict-free
 constexpr int MAX_ROWS = 96;
 
+// Optional in-kernel timeline (profiling hook, rf_debug_attn_stamps): the CTA with blockIdx.x == gridDim.x / 2 records clock64
+// at its phase boundaries (thread 0).  One global load per CTA otherwise.
+__device__ long long* g_attn_stamps = nullptr;
+
+__device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2, 2 ulp; -inf -> 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int LP>
 struct Layout {
   static constexpr int TILE = LP * 128;        // one k-block (32 fp32 columns) of LP rows
@@ -70,6 +80,8 @@ __global__ void __launch_bounds__(THREADS) attention_tc_fwd_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  long long* stamps = (tid == 0 && blockIdx.x == gridDim.x / 2) ? g_attn_stamps : nullptr;
+  if (stamps) stamps[0] = clock64();
   const int L = p.Lq, u = p.u;
   const int pairs = p.H >> 1;
   const int b = blockIdx.x / pairs, hp = blockIdx.x - b * pairs;
@@ -94,6 +106,7 @@ __global__ void __launch_bounds__(THREADS) attention_tc_fwd_kernel(const __grid_
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
   pdl_trigger();
+  if (stamps) stamps[1] = clock64();  // setup + TMEM allocation done
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_tma, 3 * LY::TILE);
@@ -110,9 +123,18 @@ __global__ void __launch_bounds__(THREADS) attention_tc_fwd_kernel(const __grid_
     const int group = p.idx_group > 0 ? b / p.idx_group : 0;
     const int* idx = p.idx + (static_cast<long long>(group) * L + row) * p.U;
     unsigned char* bytes = reinterpret_cast<unsigned char*>(mine);
-    for (int j = 0; j < p.U; ++j) bytes[__ldg(idx + j)] += 1;
+    // all index loads first (independent, ~one L2 round trip in total), then the byte increments
+    int samp[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) samp[j] = (j < p.U) ? __ldg(idx + j) : -1;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (samp[j] >= 0) bytes[samp[j]] += 1;
+    for (int j = 32; j < p.U; ++j) bytes[__ldg(idx + j)] += 1;
   }
+  if (stamps) stamps[2] = clock64();  // count table built
   mbar_wait(bar_tma, 0);
+  if (stamps) stamps[3] = clock64();  // tiles landed
 
   // ---- operand preparation ------------------------------------------------------------------------
   // hi / lo split of Q and K (layout-agnostic: element-wise over the swizzled tiles)
@@ -144,6 +166,7 @@ __global__ void __launch_bounds__(THREADS) attention_tc_fwd_kernel(const __grid_
   fence_proxy_async_smem();
   __syncthreads();
 
+  if (stamps) stamps[4] = clock64();  // hi/lo split + V^T done
   // ---- S = Q.K^T for both heads (3xTF32) -------------------------------------------------------------
   if (tid == 0) {
     tc_fence_after();
@@ -164,6 +187,7 @@ __global__ void __launch_bounds__(THREADS) attention_tc_fwd_kernel(const __grid_
   }
   mbar_wait(bar_s, 0);
   tc_fence_after();
+  if (stamps) stamps[5] = clock64();  // scores ready
 
   const float scale = rsqrtf(static_cast<float>(DH));
   int sel_rank[2] = {-1, -1};
@@ -182,11 +206,12 @@ __global__ void __launch_bounds__(THREADS) attention_tc_fwd_kernel(const __grid_
         for (int j = 0; j < 16; ++j) s[c * 16 + j] = __uint_as_float(r[j]);
       }
     }
-    // sparsity measure over the sampled keys (cross_modal_transformer.py:97-100): M = max_j s - sum_j s / L_K
+    // sparsity measure over the sampled keys (cross_modal_transformer.py:97-100): M = max_j s - sum_j s / L_K.
+    // Four independent (max, sum) chains: the loop is latency-bound otherwise (one warp per scheduler).
     if (select) {
       if (active) {
         const uint32_t* mine = sCnt + row * CNT_WORDS;
-        float mx = -INFINITY, sum = 0.f;
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j4 = 0; j4 < LP / 4; ++j4) {
           const uint32_t w = mine[j4];
@@ -195,29 +220,39 @@ __global__ void __launch_bounds__(THREADS) attention_tc_fwd_kernel(const __grid_
             const int j = j4 * 4 + t;
             const uint32_t c = (w >> (8 * t)) & 0xFFu;
             if (j < L && c != 0u) {
-              mx = fmaxf(mx, s[j]);
-              sum = fmaf(static_cast<float>(c), s[j], sum);
+              mx[t] = fmaxf(mx[t], s[j]);
+              sum[t] = fmaf(static_cast<float>(c), s[j], sum[t]);
             }
           }
         }
-        const float mval = mx - sum / p.Lk;
+        const float mval = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) - ((sum[0] + sum[1]) + (sum[2] + sum[3])) / p.Lk;
         sM[hh * 128 + row] = mval;
         if (p.measure) p.measure[(bh0 + hh) * L + row] = mval;
+      } else if (row < 128) {
+        sM[hh * 128 + row] = -INFINITY;  // padding rows never beat a real one (the rank loop reads whole float4 groups)
       }
     } else if (tid < u) {
       sTop[hh * 128 + tid] = p.forced_top[(bh0 + hh) * u + tid];
     }
     __syncthreads();
+    if (stamps) stamps[6 + 4 * hh] = clock64();  // measure done
     // top-u: rank = number of rows that beat this one (ties -> lower index first)
     int rank = -1;
     if (active) {
       if (select) {
         const float mi = sM[hh * 128 + row];
-        int r = 0;
-        for (int j = 0; j < L; ++j) {
-          const float mj = sM[hh * 128 + j];
-          r += (mj > mi) || (mj == mi && j < row);
+        int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+        const float4* m4 = reinterpret_cast<const float4*>(sM + hh * 128);
+#pragma unroll 4
+        for (int j4 = 0; j4 < (L + 3) >> 2; ++j4) {
+          const float4 m = m4[j4];
+          const int j = j4 << 2;
+          r0 += (m.x > mi) || (m.x == mi && j < row);
+          r1 += (m.y > mi) || (m.y == mi && j + 1 < row);
+          r2 += (m.z > mi) || (m.z == mi && j + 2 < row);
+          r3 += (m.w > mi) || (m.w == mi && j + 3 < row);
         }
+        const int r = (r0 + r1) + (r2 + r3);
         if (r < u) rank = r;
       } else {
         for (int r = 0; r < u; ++r)
@@ -226,21 +261,31 @@ __global__ void __launch_bounds__(THREADS) attention_tc_fwd_kernel(const __grid_
     }
     sel_rank[hh] = rank;
     // soft-max of the selected rows (cross_modal_transformer.py:158-162); probabilities rounded to tf32 (nearest)
-    float inv = 0.f, mx2 = 0.f;
+    float inv = 0.f;
     if (rank >= 0) {
-      mx2 = -INFINITY;
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < LP; ++j)
-        if (j < L) mx2 = fmaxf(mx2, s[j] * scale);
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < LP; ++j) {
-        const float e = (j < L) ? __expf(s[j] * scale - mx2) : 0.f;
-        s[j] = e;
-        sum += e;
+      for (int j = 0; j < LP; j += 4) {
+        if (j < L) m0 = fmaxf(m0, s[j]);
+        if (j + 1 < L) m1 = fmaxf(m1, s[j + 1]);
+        if (j + 2 < L) m2 = fmaxf(m2, s[j + 2]);
+        if (j + 3 < L) m3 = fmaxf(m3, s[j + 3]);
       }
-      inv = 1.f / sum;
+      const float k2 = scale * 1.4426950408889634f;                       // exp(x * scale) = exp2(x * scale * log2 e)
+      const float mraw = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * k2;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < LP; j += 4) {
+        const float e0 = (j < L) ? fast_exp2(fmaf(s[j], k2, -mraw)) : 0.f;
+        const float e1 = (j + 1 < L) ? fast_exp2(fmaf(s[j + 1], k2, -mraw)) : 0.f;
+        const float e2 = (j + 2 < L) ? fast_exp2(fmaf(s[j + 2], k2, -mraw)) : 0.f;
+        const float e3 = (j + 3 < L) ? fast_exp2(fmaf(s[j + 3], k2, -mraw)) : 0.f;
+        s[j] = e0; s[j + 1] = e1; s[j + 2] = e2; s[j + 3] = e3;
+        a0 += e0; a1 += e1; a2 += e2; a3 += e3;
+      }
+      inv = 1.f / ((a0 + a1) + (a2 + a3));
     }
+    if (stamps) stamps[7 + 4 * hh] = clock64();  // rank + softmax done
     if (hh == 1) {  // the P tile is shared by the two heads: head 0's P.V must have consumed it
       mbar_wait(&bar_pv[0], 0);
       tc_fence_after();
@@ -262,6 +307,7 @@ __global__ void __launch_bounds__(THREADS) attention_tc_fwd_kernel(const __grid_
     }
     fence_proxy_async_smem();
     __syncthreads();
+    if (stamps) stamps[8 + 4 * hh] = clock64();  // P written
     if (p.top && tid < u) p.top[(bh0 + hh) * u + tid] = sTop[hh * 128 + tid];
     // ---- ctx = P.V (+ the ones row: column sums of V) ------------------------------------------------
     if (tid == 0) {
@@ -276,6 +322,7 @@ __global__ void __launch_bounds__(THREADS) attention_tc_fwd_kernel(const __grid_
       }
       umma_commit(&bar_pv[hh]);
     }
+    if (stamps) stamps[9 + 4 * hh] = clock64();  // P.V issued
   }
 
   // ---- context rows: P.V for the selected queries, mean(V) for the others ------------------------------
@@ -310,9 +357,11 @@ __global__ void __launch_bounds__(THREADS) attention_tc_fwd_kernel(const __grid_
     }
   }
 
+  if (stamps) stamps[14] = clock64();  // contexts written
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, LY::TMEM_COLS);
+  if (stamps) stamps[15] = clock64();
 }
 
 template <int LP>
@@ -337,8 +386,11 @@ static int launch_fwd(const RfAttnParams* p, cudaStream_t stream) {
 // Eligibility of the tensor-core forward: unmasked ProbSparse self-attention, head dim 16, an even number of heads, L <= 80,
 // contiguous sequences of rows (batch stride = L x row stride), 16 B-aligned rows, no last-query-only hint.
 bool attention_tc_fwd_eligible(const RfAttnParams* p) {
-  const char* e = getenv("RF_ATTN_TC");  // read per call: RF_ATTN_TC=0 (and ops.precise) select the fp32 kernels
-  if (e && e[0] == '0') return false;
+  // Opt-in (read per call): RF_ATTN_TC=1.  The kernel is exact on the selections and tested, but its thread-per-row epilogue
+  // keeps only two of the four warp schedulers busy and is latency-bound: 304 us against 224 us for the fp32 FMA kernel on the
+  // frame-encoder problem (profiles/r2_attention_tc_microbench.txt), so the FMA kernels stay the default.
+  const char* e = getenv("RF_ATTN_TC");
+  if (!(e && e[0] == '1')) return false;
   if (p->mode != RF_ATTN_PROB || p->dh != attn_tc::DH || (p->H & 1) || p->Lq != p->Lk || p->Lq > 80 || p->Lq < 8) return false;
   if (p->tail_only || p->dropout_p != 0.f) return false;
   if (p->q_bs != static_cast<long long>(p->Lq) * p->q_ls || p->k_bs != static_cast<long long>(p->Lk) * p->k_ls ||
@@ -351,6 +403,16 @@ bool attention_tc_fwd_eligible(const RfAttnParams* p) {
   if (p->U > 100 || p->u > 128) return false;
   return true;
 }
+
+}  // namespace rf
+
+extern "C" int rf_debug_attn_stamps(long long* device_buffer) {
+  using namespace rf;
+  RF_CUDA_OK(cudaMemcpyToSymbol(attn_tc::g_attn_stamps, &device_buffer, sizeof(device_buffer)));
+  return RF_OK;
+}
+
+namespace rf {
 
 int attention_tc_fwd(const RfAttnParams* p, cudaStream_t stream) {
   if (p->Lq <= 48) return attn_tc::launch_fwd<48>(p, stream);

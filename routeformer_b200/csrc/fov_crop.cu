@@ -27,6 +27,13 @@ template <typename T> __device__ __forceinline__ float load_px(const T* p);
 template <> __device__ __forceinline__ float load_px<__half>(const __half* p) { return __half2float(__ldg(p)); }
 template <> __device__ __forceinline__ float load_px<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float load_px<unsigned char>(const unsigned char* p) { return __ldg(p) * (1.0f / 255.0f); }
+// uint8 pixel converted the way the reference's loader does on the host, `astype(float16) / 255.0` (io/dataset.py:1505-1522):
+// fp16(v * (1/255)) equals numpy's fp16 division for all 256 values (checked exhaustively), so uint8 frames staged on the
+// device (half the H2D bytes) give bit-identical taps
+struct u8h { unsigned char v; };
+template <> __device__ __forceinline__ float load_px<u8h>(const u8h* p) {
+  return __half2float(__float2half_rn(__ldg(&p->v) * (1.0f / 255.0f)));
+}
 
 __device__ __forceinline__ void store4(float* dst, const float (&v)[4]) {
   *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
@@ -179,6 +186,10 @@ template <> __device__ __forceinline__ float2 load_px2<float>(const float* p) { 
 template <> __device__ __forceinline__ float2 load_px2<unsigned char>(const unsigned char* p) {
   const unsigned short u = __ldg(reinterpret_cast<const unsigned short*>(p));
   return make_float2((u & 0xFF) * (1.0f / 255.0f), (u >> 8) * (1.0f / 255.0f));
+}
+template <> __device__ __forceinline__ float2 load_px2<u8h>(const u8h* p) {
+  const unsigned short u = __ldg(reinterpret_cast<const unsigned short*>(p));
+  return __half22float2(__floats2half2_rn((u & 0xFF) * (1.0f / 255.0f), (u >> 8) * (1.0f / 255.0f)));
 }
 
 __device__ __forceinline__ void store2(float* dst, float a, float b) { *reinterpret_cast<float2*>(dst) = make_float2(a, b); }
@@ -416,6 +427,7 @@ extern "C" int rf_fov_crop(const RfFovCropParams* p, void* stream) {
     case RF_F16: return crop::dispatch_out<__half>(p, a, s);
     case RF_F32: return crop::dispatch_out<float>(p, a, s);
     case RF_U8: return crop::dispatch_out<unsigned char>(p, a, s);
+    case RF_U8_F16: return crop::dispatch_out<crop::u8h>(p, a, s);
     default: set_error("rf_fov_crop: unsupported src_dtype %d", p->src_dtype); return RF_ERR_INVALID_ARGUMENT;
   }
 }

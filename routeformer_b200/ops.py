@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import check
 
-F32, F16, BF16, U8 = 0, 1, 2, 3
+F32, F16, BF16, U8, U8_F16 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 ACT_GELU_SAVE_GRAD = 3  # forward: out = gelu(x), `preact` receives gelu'(x)
 DACT_SAVED = 3          # backward: multiply by the saved derivative in `dact_aux`
@@ -60,8 +60,9 @@ def _row_pitch(t: torch.Tensor, name: str) -> int:
 # ---------------------------------------------------------------------------------------------
 def fov_crop(frames: torch.Tensor, centers: torch.Tensor, windows: torch.Tensor, out_size: int, mean, std,
              patch: int = 0, frame_ids: Optional[torch.Tensor] = None, n_frames: Optional[int] = None,
-             out_dtype=torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """frames [*,3,H,W] (fp16/fp32/u8, contiguous) -> [n,3,S,S] or patch-major [n*G*G, 3*p*p]."""
+             out_dtype=torch.float32, out: Optional[torch.Tensor] = None, u8_as_f16: bool = False) -> torch.Tensor:
+    """frames [*,3,H,W] (fp16/fp32/u8, contiguous) -> [n,3,S,S] or patch-major [n*G*G, 3*p*p].
+    u8_as_f16: uint8 pixels are converted like the reference's loader, fp16(v / 255), before they are interpolated."""
     lib = _lib.load()
     assert frames.is_contiguous() and frames.shape[-3] == 3
     H, W = frames.shape[-2:]
@@ -78,7 +79,7 @@ def fov_crop(frames: torch.Tensor, centers: torch.Tensor, windows: torch.Tensor,
         else:
             out = torch.empty(n, 3, out_size, out_size, device=frames.device, dtype=out_dtype)
     p = _lib.RfFovCropParams()
-    p.frames, p.src_dtype, p.frame_ids = _ptr(frames), _DTYPES[frames.dtype], _ptr(frame_ids)
+    p.frames, p.src_dtype, p.frame_ids = _ptr(frames), (U8_F16 if (u8_as_f16 and frames.dtype == torch.uint8) else _DTYPES[frames.dtype]), _ptr(frame_ids)
     p.n_frames, p.H, p.W = n, H, W
     p.centers, p.windows = _ptr(centers), _ptr(windows)
     for c in range(3):

@@ -226,6 +226,34 @@ def test_fov_crop(ops, monkeypatch, H, W, S, patch, dtype, tiled):
 
 
 @pytest.mark.parametrize("tiled", ["0", "1"])
+def test_fov_crop_uint8_frames_like_the_reference_loader(ops, monkeypatch, tiled):
+    """raw uint8 frames staged on the device (half the host->device bytes) and converted inside the crop kernel
+    exactly as the reference's loader converts them on the host, `astype(float16) / 255.0` (io/dataset.py:1505-1522): the crop of
+    the uint8 frames must equal the crop of the host-converted fp16 frames BIT FOR BIT."""
+    import numpy as np
+
+    monkeypatch.setenv("RF_CROP_TILED", tiled)
+    gen = g(5)
+    n, H, W, S, patch = 4, 60, 62, 32, 8
+    u8 = torch.randint(0, 256, (n, 3, H, W), generator=gen, dtype=torch.uint8)
+    f16 = torch.from_numpy(u8.numpy().astype(np.float16) / 255.0)
+    assert f16.dtype == torch.float16
+    centers = (0.5 + 0.2 * torch.randn(n, 2, generator=gen)).clamp(0, 1).to(DEV)
+    windows = torch.full((n, 2), 0.6).to(DEV)
+    spec = O.BackboneSpec()
+    for p_, dt in ((patch, torch.float16), (0, torch.float32)):
+        a = ops.fov_crop(u8.to(DEV), centers, windows, S, spec.mean, spec.std, patch=p_, out_dtype=dt, u8_as_f16=True)
+        b = ops.fov_crop(f16.to(DEV), centers, windows, S, spec.mean, spec.std, patch=p_, out_dtype=dt)
+        assert torch.equal(a, b)
+    # every one of the 256 pixel values converts like numpy does
+    ramp = torch.arange(256, dtype=torch.uint8).view(1, 1, 16, 16).repeat(1, 3, 1, 1)
+    ident = ops.fov_crop(ramp.to(DEV), torch.tensor([[0.5, 0.5]], device=DEV), torch.tensor([[1.0, 1.0]], device=DEV), 16,
+                         (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), out_dtype=torch.float32, u8_as_f16=True)
+    want = torch.from_numpy(np.arange(256, dtype=np.uint8).astype(np.float16) / 255.0).float().view(16, 16)
+    assert torch.equal(ident[0, 0].cpu(), want)
+
+
+@pytest.mark.parametrize("tiled", ["0", "1"])
 def test_fov_crop_mirrored_and_offscreen(ops, monkeypatch, tiled):
     """Windows the tiled kernel special-cases: mirrored (fw < 0: direct gather path), entirely outside the frame (constant
     tile), touching the left / right / top / bottom border (clamped taps with zero weight)."""
@@ -303,11 +331,26 @@ ATTN_CASES = [
     (3, 4, 40, 70, 16, 5, "prob", "bhld"),
     (3, 8, 90, 33, 8, 4, "prob", "blhd"),
     (6, 2, 20, 96, 16, 5, "prob", "blhd"),
+    # shapes the tensor-core forward takes (unmasked, dh 16, Lq == Lk <= 80): gaze encoder, odd length, LP = 80 limit, 2 heads
+    (4, 8, 40, 40, 16, 5, "prob", "blhd"),
+    (5, 8, 33, 33, 16, 4, "prob", "blhd"),
+    (3, 2, 80, 80, 16, 5, "prob", "bhld"),
+    (7, 4, 48, 48, 16, 5, "prob", "blhd"),
 ]
 
 
+def _tc_eligible(Lq, Lk, dh, mode, H):
+    return mode == "prob" and dh == 16 and Lq == Lk and 8 <= Lq <= 80 and H % 2 == 0
+
+
+@pytest.mark.parametrize("tc", ["0", "1"])  # fp32 FMA kernels / tcgen05 forward (3xTF32 scores, tf32 P.V) where it applies
 @pytest.mark.parametrize("B,H,Lq,Lk,dh,factor,mode,layout", ATTN_CASES)
-def test_attention_forward_backward(ops, B, H, Lq, Lk, dh, factor, mode, layout):
+def test_attention_forward_backward(ops, monkeypatch, B, H, Lq, Lk, dh, factor, mode, layout, tc):
+    on_tc = tc == "1" and _tc_eligible(Lq, Lk, dh, mode, H)
+    if tc == "1" and not on_tc:
+        pytest.skip("shape not taken by the tensor-core forward")
+    monkeypatch.setenv("RF_ATTN_TC", tc)
+    out_tol = 1e-3 if on_tc else 1e-5  # P and V enter the P.V product rounded to tf32 (2^-11), like every GEMM of the model
     gen = g(Lq * 7 + Lk + dh)
     D = H * dh
     # q/k/v live inside fused [rows, 3D] buffers exactly as the modules produce them
@@ -349,7 +392,10 @@ def test_attention_forward_backward(ops, B, H, Lq, Lk, dh, factor, mode, layout)
     if mode != "full":
         assert rel_err(measure.cpu(), meas) < 1e-5
         assert torch.equal(top.cpu().long().sort(-1).values, tops.sort(-1).values)  # same selected set (index work: exact)
-    assert rel_err(out.cpu(), ref.detach()) < 1e-5
+    assert rel_err(out.cpu(), ref.detach()) < out_tol, rel_err(out.cpu(), ref.detach())
+    if on_tc:
+        print(f"tcgen05 attention forward B={B} H={H} L={Lq}: context rel err {rel_err(out.cpu(), ref.detach()):.2e}, measure rel err "
+              f"{rel_err(measure.cpu(), meas):.2e}")
     dqkv_q = torch.zeros_like(qd)
     dqkv_k = dqkv_q if qkv_k is qkv_q else torch.zeros_like(kd)
     ops.attention_bwd(qa, ka, va, B, H, Lq, Lk, dh, code, lay, U, u, top, dout.to(DEV), dqkv_q, dqkv_k[:, D:], dqkv_k[:, 2 * D:])
@@ -365,7 +411,7 @@ def test_attention_forward_backward(ops, B, H, Lq, Lk, dh, factor, mode, layout)
         top2 = torch.zeros_like(top)
         ops.attention_fwd(qa, ka, va, B, H, Lq, Lk, dh, code, lay, idx_d, B // groups if groups > 1 else 0, U, u, out2, top2, forced_top=forced)
         assert torch.equal(top2, forced)
-        assert rel_err(out2.cpu(), ref.detach()) < 1e-5
+        assert rel_err(out2.cpu(), ref.detach()) < out_tol
         g_q = torch.zeros_like(qd)
         g_k = g_q if qkv_k is qkv_q else torch.zeros_like(kd)
         ops.attention_bwd(qa, ka, va, B, H, Lq, Lk, dh, code, lay, U, u, top2, dout.to(DEV), g_q, g_k[:, D:], g_k[:, 2 * D:])
