@@ -383,7 +383,7 @@ static int launch_fwd(const RfAttnParams* p, cudaStream_t stream) {
 
 }  // namespace attn_tc
 
-// Eligibility of the tensor-core forward: unmasked ProbSparse self-attention, head dim 16, an even number of heads, L <= 80,
+// Eligibility of the tensor-core forward: unmasked ProbSparse self-attention, head dim 16, an even number of heads, L <= 79,
 // contiguous sequences of rows (batch stride = L x row stride), 16 B-aligned rows, no last-query-only hint.
 bool attention_tc_fwd_eligible(const RfAttnParams* p) {
   // Opt-in (read per call): RF_ATTN_TC=1.  The kernel is exact on the selections and tested, but its thread-per-row epilogue
@@ -391,7 +391,7 @@ bool attention_tc_fwd_eligible(const RfAttnParams* p) {
   // frame-encoder problem (profiles/r2_attention_tc_microbench.txt), so the FMA kernels stay the default.
   const char* e = getenv("RF_ATTN_TC");
   if (!(e && e[0] == '1')) return false;
-  if (p->mode != RF_ATTN_PROB || p->dh != attn_tc::DH || (p->H & 1) || p->Lq != p->Lk || p->Lq > 80 || p->Lq < 8) return false;
+  if (p->mode != RF_ATTN_PROB || p->dh != attn_tc::DH || (p->H & 1) || p->Lq != p->Lk || p->Lq > 79 || p->Lq < 8) return false;  // L + 1 rows (the ones row) must fit the LP-row P tile
   if (p->tail_only || p->dropout_p != 0.f) return false;
   if (p->q_bs != static_cast<long long>(p->Lq) * p->q_ls || p->k_bs != static_cast<long long>(p->Lk) * p->k_ls ||
       p->v_bs != static_cast<long long>(p->Lk) * p->v_ls)
@@ -415,7 +415,7 @@ extern "C" int rf_debug_attn_stamps(long long* device_buffer) {
 namespace rf {
 
 int attention_tc_fwd(const RfAttnParams* p, cudaStream_t stream) {
-  if (p->Lq <= 48) return attn_tc::launch_fwd<48>(p, stream);
+  if (p->Lq < 48) return attn_tc::launch_fwd<48>(p, stream);
   return attn_tc::launch_fwd<80>(p, stream);
 }
 

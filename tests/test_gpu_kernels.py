@@ -331,16 +331,16 @@ ATTN_CASES = [
     (3, 4, 40, 70, 16, 5, "prob", "bhld"),
     (3, 8, 90, 33, 8, 4, "prob", "blhd"),
     (6, 2, 20, 96, 16, 5, "prob", "blhd"),
-    # shapes the tensor-core forward takes (unmasked, dh 16, Lq == Lk <= 80): gaze encoder, odd length, LP = 80 limit, 2 heads
+    # shapes the tensor-core forward takes (unmasked, dh 16, Lq == Lk <= 79): gaze encoder, odd length, LP = 80 limit, 2 heads
     (4, 8, 40, 40, 16, 5, "prob", "blhd"),
     (5, 8, 33, 33, 16, 4, "prob", "blhd"),
-    (3, 2, 80, 80, 16, 5, "prob", "bhld"),
+    (3, 2, 79, 79, 16, 5, "prob", "bhld"),
     (7, 4, 48, 48, 16, 5, "prob", "blhd"),
 ]
 
 
 def _tc_eligible(Lq, Lk, dh, mode, H):
-    return mode == "prob" and dh == 16 and Lq == Lk and 8 <= Lq <= 80 and H % 2 == 0
+    return mode == "prob" and dh == 16 and Lq == Lk and 8 <= Lq <= 79 and H % 2 == 0
 
 
 @pytest.mark.parametrize("tc", ["0", "1"])  # fp32 FMA kernels / tcgen05 forward (3xTF32 scores, tf32 P.V) where it applies
