@@ -174,7 +174,7 @@ def run_train(args):
         wp, dense = out
         return lossf(wp, tgt[0]) + 0.5 * lossf(dense, tgt[1])
 
-    use_graph = not args.no_graph and not args.paper_dropout  # dropout draws data-dependent control flow: eager until it is captured
+    use_graph = not args.no_graph
     trainer = DataParallelTrainer(model, loss_fn, lr=1e-5, weight_decay=1e-4, max_grad_norm=2.5, use_cuda_graph=use_graph,
                                   overlap_wgrad=not args.no_wgrad_overlap)
     trainer.broadcast_parameters()
@@ -186,6 +186,8 @@ def run_train(args):
     in_bytes = sum(v.numel() * v.element_size() for v in batch.values())
 
     # ---- device-resident timing -------------------------------------------------------------
+    if use_graph:
+        trainer.capture_patterns(batch, targets)  # one graph per view / gaze drop pattern (6 with the paper's dropouts, else 1)
     for _ in range(args.warmup):
         trainer.step(batch, targets)
     if trainer.static_inputs()[0] is not None:  # the captured graph reads its own static buffers: time with the inputs resident THERE
@@ -205,6 +207,7 @@ def run_train(args):
     launches = (ops.launch_count - launches0) // max(args.steps, 1) + trainer.graph_launches
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (ms / 1e3)
+    patterns_timed = {"".join("LRG"[i] for i in range(3) if p[i]) or "none": n for p, n in trainer.pattern_counts.items()}
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_run": True, "value": round(value, 2), "ms_per_step": round(ms / args.steps, 3), "gpu_launches": int(launches)}))
@@ -397,8 +400,10 @@ def run_train(args):
                        "global_batch": world * B, "batch_per_gpu": B, "parallelism": f"dp{world}", "fov": args.fov,
                        "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB of consumed frames + gps + gaze per step per GPU)",
                        "cuda_graph": bool(use_graph),
-                       "dropout": ("paper configuration: view 0.6 / gaze 0.2 / feature 0.05 (full_comparison.py:272-275)" if args.paper_dropout
+                       "dropout": ("paper configuration: view 0.6 / gaze 0.2 / feature 0.05 (full_comparison.py:272-275); dropped views skip "
+                                   "their frame-encoder pass as in the reference, so step time depends on the drawn pattern" if args.paper_dropout
                                    else "feature/view/gaze dropout 0 (parity configuration)"),
+                       "dropped_views_of_all_steps_so_far": patterns_timed,
                        "backbone": "frozen (reference: epoch <= 10)",
                        "frames": ("raw uint8 frames staged on the device, converted in the crop kernel (SURVEY 8(f) N4)" if args.u8_frames
                                   else "fp16 frames, as the reference's loader hands them over")},

@@ -177,6 +177,7 @@ typedef struct {
   const int* forced_top;   /* optional in [B,H,u]: use this selection instead (test hook) */
   float dropout_p;         /* RF_ATTN_FULL only: dropout on the softmax probabilities (cross_modal_transformer.py:63), 0 = off */
   unsigned long long dropout_seed, dropout_offset; /* mask = rf_dropout's for a [B*H*Lq, Lk] tensor with the same seed / offset */
+  const unsigned long long* dropout_offset_base;   /* optional DEVICE scalar added to dropout_offset (see rf_dropout) */
   int tail_only;           /* hint: the caller consumes only the context of the LAST query of every sequence (PerceiveEncoder with
                               out_len = 1, cross_modal_transformer.py:433).  Forward: rows 0..Lq-2 of `out` may be left unwritten
                               (top / measure are complete).  Backward: rows 0..Lq-2 of `dout` are taken as zero and not read. */
@@ -274,7 +275,10 @@ int rf_ade_fde(const float* pred, const float* truth, int B, int T, float* resul
  * x); residual optional.  The same call with x = dy and residual = NULL is the backward pass (the mask is a function of
  * seed / offset / logical element index only). */
 int rf_dropout(const float* x, long long ldx, const float* residual, long long ldr, float* out, long long ldo, int M, int N,
-               float p, unsigned long long seed, unsigned long long offset, void* stream);
+               float p, unsigned long long seed, unsigned long long offset, const unsigned long long* offset_base, void* stream);
+/* offset_base (optional): DEVICE scalar added to `offset` when the kernel runs.  A training step captured in a CUDA graph bakes
+ * `offset` (the call site) into the launch; the per-step part of the Philox counter lives in device memory and is advanced by
+ * the graph itself, so every replay draws fresh masks. */
 /* replaces: experiments/full_comparison.py:654-679 (_eval_step): mean of S stochastic forwards, then per clip the
  * FutureDiscountedLoss, ADE and "FDE" of the [1,T,2] slices.  preds [S,B,T,2] (sample-major), truth [B,T,2];
  * mean_pred (optional, [B,T,2]) = stack(preds).mean(0); per_clip [B,3] = (loss, ade, fde).  kind / gamma / epsilon as below. */

@@ -67,7 +67,7 @@ class RfAttnParams(C.Structure):
         ("mode", C.c_int), ("out_layout", C.c_int),
         ("idx", c_fp), ("idx_group", C.c_int), ("U", C.c_int), ("u", C.c_int),
         ("out", c_fp), ("top", c_fp), ("measure", c_fp), ("forced_top", c_fp),
-        ("dropout_p", C.c_float), ("dropout_seed", C.c_ulonglong), ("dropout_offset", C.c_ulonglong),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_ulonglong), ("dropout_offset", C.c_ulonglong), ("dropout_offset_base", c_fp),
         ("tail_only", C.c_int),
     ]
 
@@ -122,7 +122,7 @@ SIGNATURES = {
     "rf_decode_waypoints_bwd": [_P, _P, _P, _L, _I, _I, _I, _I, _F, _P],
     "rf_median_downsample": [_P, _P, _I, _I, _I, _I, _P],
     "rf_ade_fde": [_P, _P, _I, _I, _P, _P, _P],
-    "rf_dropout": [_P, _L, _P, _L, _P, _L, _I, _I, _F, C.c_ulonglong, C.c_ulonglong, _P],
+    "rf_dropout": [_P, _L, _P, _L, _P, _L, _I, _I, _F, C.c_ulonglong, C.c_ulonglong, _P, _P],
     "rf_eval_samples": [_P, _P, _I, _I, _I, _F, _F, _I, _P, _P, _P],
     "rf_discounted_loss_fwd": [_P, _L, _P, _L, _I, _I, _I, _F, _F, _I, _P, _P],
     "rf_discounted_loss_bwd": [_P, _L, _P, _L, _I, _I, _I, _F, _F, _I, _P, _F, _P, _L, _I, _P],

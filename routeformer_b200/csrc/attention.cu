@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(THREADS) attention_fwd_kernel(const RfAttnPara
     const uint32_t thr = dropout_threshold(p.dropout_p);
     const float keep_scale = 1.f / (1.f - p.dropout_p);
     const unsigned long long base = static_cast<unsigned long long>(bh) * Lq * Lk;
-    for (int i = threadIdx.x; i < Lq * Lk; i += THREADS) sm.s[i] *= dropout_factor(p.dropout_seed, p.dropout_offset, base + i, thr, keep_scale);
+    for (int i = threadIdx.x; i < Lq * Lk; i += THREADS) sm.s[i] *= dropout_factor(p.dropout_seed, p.dropout_offset + (p.dropout_offset_base ? __ldg(p.dropout_offset_base) : 0ull), base + i, thr, keep_scale);
     __syncthreads();
   }
 
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
       float v = 0.f;
       if (j < Lk) {
         v = dot4(d, dorow, sm.v + j * pitch);
-        if (drop) v *= dropout_factor(p.dropout_seed, p.dropout_offset, drop_base + static_cast<unsigned long long>(r) * Lk + j, drop_thr, drop_scale);
+        if (drop) v *= dropout_factor(p.dropout_seed, p.dropout_offset + (p.dropout_offset_base ? __ldg(p.dropout_offset_base) : 0ull), drop_base + static_cast<unsigned long long>(r) * Lk + j, drop_thr, drop_scale);
         acc = fmaf(sm.s[r * Lk + j], v, acc);
       }
       dp[t] = v;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(THREADS) attention_bwd_kernel(const RfAttnBwdP
       const int qi = sm.top[r];
       acck.fma(s_ds[r * Lk + j], sm.q + qi * pitch + 4 * c);
       float wp = sm.s[r * Lk + j];
-      if (drop) wp *= dropout_factor(p.dropout_seed, p.dropout_offset, drop_base + static_cast<unsigned long long>(r) * Lk + j, drop_thr, drop_scale);
+      if (drop) wp *= dropout_factor(p.dropout_seed, p.dropout_offset + (p.dropout_offset_base ? __ldg(p.dropout_offset_base) : 0ull), drop_base + static_cast<unsigned long long>(r) * Lk + j, drop_thr, drop_scale);
       accv.fma(wp, s_do + qi * pitch + 4 * c);
     }
     float4 ak = acck.get(), av = accv.get();

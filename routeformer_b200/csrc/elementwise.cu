@@ -630,12 +630,29 @@ extern "C" int rf_ade_fde(const float* pred, const float* truth, int B, int T, f
 
 __global__ void dropout_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ residual, long long ldr,
                                float* __restrict__ out, long long ldo, int M, int N, uint32_t threshold, float scale,
-                               unsigned long long seed, unsigned long long offset) {
+                               unsigned long long seed, unsigned long long offset, const unsigned long long* __restrict__ offset_base) {
   // one thread per group of 4 consecutive LOGICAL elements (row-major over [M,N]): one Philox call, 4 keep decisions
+  if (offset_base) offset += __ldg(offset_base);
   const long long total = static_cast<long long>(M) * N;
   const long long groups = (total + 3) >> 2;
+  const bool vec = (N & 3) == 0 && ((ldx | ldo | ldr) & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual)) & 15) == 0;
+  const int n4 = N >> 2;
   for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < groups; g += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 r = philox4x32_10(seed, static_cast<unsigned long long>(g), offset);
+    if (vec) {  // the 4 elements of a group share a row: one 16 B load / store per operand
+      const long long row = g / n4;
+      const int col = static_cast<int>(g - row * n4) << 2;
+      const float4 v = *reinterpret_cast<const float4*>(x + row * ldx + col);
+      float4 o = make_float4(r.x >= threshold ? v.x * scale : 0.0f, r.y >= threshold ? v.y * scale : 0.0f,
+                             r.z >= threshold ? v.z * scale : 0.0f, r.w >= threshold ? v.w * scale : 0.0f);
+      if (residual) {
+        const float4 q = *reinterpret_cast<const float4*>(residual + row * ldr + col);
+        o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+      }
+      *reinterpret_cast<float4*>(out + row * ldo + col) = o;
+      continue;
+    }
     const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -652,12 +669,12 @@ __global__ void dropout_kernel(const float* __restrict__ x, long long ldx, const
 }
 
 extern "C" int rf_dropout(const float* x, long long ldx, const float* residual, long long ldr, float* out, long long ldo, int M, int N, float p,
-                          unsigned long long seed, unsigned long long offset, void* stream) {
+                          unsigned long long seed, unsigned long long offset, const unsigned long long* offset_base, void* stream) {
   RF_CHECK_ARG(x && out && M > 0 && N > 0 && ldx >= N && ldo >= N, "rf_dropout: bad arguments");
   RF_CHECK_ARG(p >= 0.0f && p < 1.0f, "rf_dropout: p=%f must be in [0, 1)", p);
   const long long groups = (static_cast<long long>(M) * N + 3) / 4;
   dropout_kernel<<<blocks_for(groups, TPB, 148 * 16), TPB, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, ldx, residual, ldr, out, ldo, M, N, dropout_threshold(p), 1.0f / (1.0f - p), seed, offset);
+      x, ldx, residual, ldr, out, ldo, M, N, dropout_threshold(p), 1.0f / (1.0f - p), seed, offset, offset_base);
   RF_LAUNCH_OK();
   return RF_OK;
 }

@@ -61,6 +61,28 @@ class ParallelTrainerSteps:
         metrics["train_fde"] = fde(future_gps, target_gps)
         return loss, metrics
 
+    # -- the same step under DataParallelTrainer (CUDA graph, fused AdamW, gradient all-reduce) -------------------
+    def graph_hooks(self, current_epoch: int = 0):
+        """(step_fn, draw_fn) for `DataParallelTrainer(model, None, step_fn=..., draw_fn=...)`: the whole `training_step`
+        (forward, eval-mode target pass, both losses, detached dense re-weighting) becomes ONE captured graph per drop pattern.
+        Batches are {"train": {...}, "target": {...}}; set `trainer.graph_tag = current_epoch >= 10` when the epoch crosses the
+        point where the dense loss switches on (full_comparison.py:503-506).  The logged metrics of the last step are in
+        `self.last_metrics` (static tensors of the captured graph)."""
+        model = self.model
+
+        def step_fn(batch, _targets):
+            loss, self.last_metrics = self.training_step(batch, current_epoch)
+            return loss
+
+        def draw_fn(batch, refill_only):
+            model.prepare_draws(batch["train"], training=True, refill_only=refill_only)
+            pattern = model.last_pattern
+            if model.configs.dense_prediction and model.with_video:  # the target pass draws only what preprocess_batch draws
+                model.prepare_draws(batch["target"], training=False, refill_only=refill_only, backbone=False)
+            return pattern
+
+        return step_fn, draw_fn
+
     # -- full_comparison.py:654-679 ----------------------------------------------------------------
     @torch.no_grad()
     def eval_step(self, batch: Dict[str, Dict[str, torch.Tensor]]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:

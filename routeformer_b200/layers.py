@@ -283,6 +283,8 @@ class PerceiveEncoder(nn.Module):
     def forward(self, x_enc: torch.Tensor, draw=None) -> torch.Tensor:
         n, L, C = x_enc.shape
         draw = draw or LiveIndexSource(x_enc.device)
+        if self.training and any(layer.p_drop > 0.0 for layer in self.encoder.attn_layers):
+            ops.DropoutStream.begin_step(x_enc.device)
         x2 = _pad_channels(x_enc.to(torch.float32).reshape(n * L, C))
         out = self.encode(x2, n, L, draw)
         return out.view(n, min(L, self.pred_len), -1)
@@ -320,6 +322,8 @@ class PerceiveDecoder(nn.Module):
         n, S, Cv = x_enc.shape
         _, L, Cq = x_dec.shape
         draw = draw or LiveIndexSource(x_dec.device)
+        if self.training and any(layer.p_drop > 0.0 for layer in self.decoder.layers):
+            ops.DropoutStream.begin_step(x_dec.device)
         enc2 = x_enc.to(torch.float32).reshape(n * S, Cv)
         dec2 = _pad_channels(x_dec.to(torch.float32).reshape(n * L, Cq))
         out = self.decode(enc2, dec2, n, S, L, draw)

@@ -283,8 +283,11 @@ def _attn_params(q, k, v, B, H, Lq, Lk, dh, mode, layout, idx, idx_group, U, u, 
 
 
 def _set_attn_dropout(p, dropout):
+    """dropout = (p, seed, offset[, base]): base = device scalar added to the offset when the kernel runs (CUDA-graph replays)."""
     if dropout is not None and dropout[0] > 0.0:
         p.dropout_p, p.dropout_seed, p.dropout_offset = float(dropout[0]), int(dropout[1]), int(dropout[2])
+        if len(dropout) > 3 and dropout[3] is not None:
+            p.dropout_offset_base = _ptr(dropout[3])
 
 
 def attention_fwd(q, k, v, B, H, Lq, Lk, dh, mode, layout, idx, idx_group, U, u, out, top, measure=None, forced_top=None, dropout=None,
@@ -310,31 +313,76 @@ def attention_bwd(q, k, v, B, H, Lq, Lk, dh, mode, layout, U, u, top, dout, dq, 
     _count()
 
 
-def dropout(x: torch.Tensor, out: torch.Tensor, p: float, seed: int, offset: int, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = residual + keep * x / (1 - p) over a 2-D fp32 view (out may alias x).  The mask is a pure function of (seed, offset,
-    logical element index): calling it again on a gradient is the backward pass."""
+def dropout(x: torch.Tensor, out: torch.Tensor, p: float, seed: int, offset: int, base: Optional[torch.Tensor] = None,
+            residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = residual + keep * x / (1 - p) over a 2-D fp32 view (out may alias x).  The mask is a pure function of (seed, offset
+    [+ *base], logical element index): calling it again on a gradient is the backward pass.  `base` is an optional int64 device
+    scalar added to `offset` on the device -- the per-step part of the Philox counter of a CUDA-graph-captured step."""
     M, N = x.shape
     _f32(x, "x"), _f32(out, "out")
     check(_lib.load().rf_dropout(_ptr(x), _row_pitch(x, "x"), _ptr(residual), _row_pitch(residual, "residual") if residual is not None else 0,
-                                 _ptr(out), _row_pitch(out, "out"), M, N, float(p), int(seed), int(offset), _stream()), "rf_dropout")
+                                 _ptr(out), _row_pitch(out, "out"), M, N, float(p), int(seed), int(offset), _ptr(base), _stream()), "rf_dropout")
     _count()
     return out
 
 
 class DropoutStream:
-    """Hands out (seed, offset) pairs for dropout call sites.  seed = the CUDA generator's seed (torch.manual_seed sets it without
-    touching the CPU stream that feeds the ProbSparse index draws); offset = a process-wide call counter, so every site of every
-    step gets its own Philox sub-stream."""
-    counter = 0
-    log = None  # tests: list that receives (where, seed, offset, rows, cols)
+    """Hands out (seed, offset, base) triples for dropout call sites.
+
+    seed   = the CUDA generator's seed (torch.manual_seed sets it without touching the CPU stream that feeds the ProbSparse draws);
+    offset = index of the call site within the current step (host side, baked into a captured launch);
+    base   = int64 device scalar, advanced by STEP at the start of every training forward (`begin_step`, a device-side add that
+             is captured with the step) -- so every step, and every replay of a captured step, draws fresh masks.
+    The Philox counter a kernel uses is offset + *base; `log` (tests) records that effective value."""
+    STEP = 1 << 20
+    site = 0
+    _base = {}       # device index -> int64 device scalar
+    _base_host = {}  # device index -> host mirror of the value the NEXT kernels will read
+    log = None       # tests: list that receives (where, seed, effective offset, rows, cols)
+
+    @classmethod
+    def _dev(cls, device) -> int:
+        return device.index if device.index is not None else torch.cuda.current_device()
+
+    @classmethod
+    def base(cls, device) -> torch.Tensor:
+        d = cls._dev(device)
+        if d not in cls._base:
+            cls._base[d] = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", d))
+            cls._base_host[d] = 0
+        return cls._base[d]
+
+    @classmethod
+    def begin_step(cls, device) -> None:
+        """Start of a training forward: new per-step base (device-side add: capturable), call-site counter back to 0."""
+        cls.base(device).add_(cls.STEP)
+        if not torch.cuda.is_current_stream_capturing():  # a captured add runs at replay time (note_replay), not now
+            cls._base_host[cls._dev(device)] += cls.STEP
+        cls.site = 0
+
+    @classmethod
+    def snapshot(cls, device):
+        return cls.base(device).clone(), cls._base_host[cls._dev(device)]
+
+    @classmethod
+    def restore(cls, device, snap) -> None:
+        """Undo the advances of forwards that do not count as steps (the warm-up passes of a CUDA-graph capture)."""
+        cls.base(device).copy_(snap[0])
+        cls._base_host[cls._dev(device)] = snap[1]
+
+    @classmethod
+    def note_replay(cls, device) -> None:
+        """A captured step (which contains the device-side add of `begin_step`) has been replayed: advance the host mirror."""
+        cls._base_host[cls._dev(device)] += cls.STEP
 
     @classmethod
     def next(cls, device, where: str = "", rows: int = 0, cols: int = 0):
-        seed = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()].initial_seed()
-        cls.counter += 1
+        seed = torch.cuda.default_generators[cls._dev(device)].initial_seed()
+        base = cls.base(device)
+        cls.site += 1
         if cls.log is not None:
-            cls.log.append((where, seed, cls.counter, rows, cols))
-        return seed, cls.counter
+            cls.log.append((where, seed, cls._base_host[cls._dev(device)] + cls.site, rows, cols))
+        return seed, cls.site, base
 
 
 def layernorm_fwd(x, gamma, beta, y, mean, rstd):

@@ -32,6 +32,34 @@ def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[s
     return out
 
 
+def _clone_tree(x):
+    """Deep copy of a (possibly nested) dict / tuple / list of tensors, keeping StagedBatch's `video_len`."""
+    if isinstance(x, torch.Tensor):
+        return x.clone()
+    if isinstance(x, dict):
+        out = type(x)()
+        for k, v in x.items():
+            out[k] = _clone_tree(v)
+        if hasattr(x, "video_len"):
+            out.video_len = dict(x.video_len)
+        return out
+    if isinstance(x, (tuple, list)):
+        return type(x)(_clone_tree(v) for v in x)
+    return x
+
+
+def _copy_tree(dst, src) -> None:
+    if isinstance(dst, torch.Tensor):
+        if src.data_ptr() != dst.data_ptr():
+            dst.copy_(src, non_blocking=True)
+    elif isinstance(dst, dict):
+        for k in dst:
+            _copy_tree(dst[k], src[k])
+    elif isinstance(dst, (tuple, list)):
+        for d, s_ in zip(dst, src):
+            _copy_tree(d, s_)
+
+
 def bucket_bounds(n: int, n_buckets: int, align: int = 1024) -> List[Tuple[int, int]]:
     """Splits [0, n) into <= n_buckets aligned ranges, last bucket first (reverse execution order: the Informer decoder's
     gradients, which autograd produces first, sit at the end of the arena)."""
@@ -58,9 +86,16 @@ class DataParallelTrainer:
 
     def __init__(self, model, loss_fn: Callable, lr: float = 1e-5, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  max_grad_norm: float = 2.5, group=None, n_buckets: int = 4, use_cuda_graph: bool = False,
-                 overlap_wgrad: bool = True):
+                 overlap_wgrad: bool = True, step_fn: Optional[Callable] = None, draw_fn: Optional[Callable] = None):
+        """step_fn(batch, targets) -> loss (optional) replaces `loss_fn(model(batch), targets)`: e.g. the reference's whole
+        `training_step` (forward + eval-mode target pass + both losses, `ParallelTrainerSteps.graph_hooks`).  draw_fn(batch,
+        refill_only) -> drop pattern must then make ALL CPU random draws of that step, in order (used to refresh the pinned index
+        buffers before a replay).  `graph_tag` (any hashable) is part of the graph cache key: set it when the step function
+        changes (e.g. the dense-loss weight switching on after epoch 10)."""
         self.model = model
         self.loss_fn = loss_fn
+        self.step_fn, self.draw_fn = step_fn, draw_fn
+        self.graph_tag = None
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.lr, self.wd, self.betas, self.eps, self.max_grad_norm = lr, weight_decay, betas, eps, max_grad_norm
@@ -74,10 +109,13 @@ class DataParallelTrainer:
         self.step_count = 0
         self.use_cuda_graph = use_cuda_graph
         self.wgrad_stream = torch.cuda.Stream(dev) if (overlap_wgrad and dev.type == "cuda") else None
-        self._graph = None
+        self._graph = None       # most recently captured graph (None until the first graph step)
+        self._graphs = {}        # drop pattern -> (graph, static loss tensor, launches)
+        self._pool = None
+        self._next_pattern = (False, False, False)
+        self.pattern_counts = {}
         self.static_batch = None
         self.static_targets = None
-        self._static_loss = None
         self._replayed = None
         self.graph_launches = 0
 
@@ -86,8 +124,11 @@ class DataParallelTrainer:
         from . import functional as Fn
 
         self.arena.zero_grad()
-        out = self.model(batch)
-        loss = self.loss_fn(out, targets)
+        if self.step_fn is not None:
+            loss = self.step_fn(batch, targets)
+        else:
+            out = self.model(batch)
+            loss = self.loss_fn(out, targets)
         if self.wgrad_stream is None:
             loss.backward()
             return loss
@@ -102,71 +143,113 @@ class DataParallelTrainer:
             main.wait_stream(self.wgrad_stream)
         return loss
 
-    def _capture(self, batch, targets) -> None:
-        m = self.model
-        if m.training and (m.view_dropout > 0 or m.gaze_dropout > 0 or m.feature_dropout > 0 or m.motion_noise > 0):
-            raise ValueError("CUDA-graph capture needs a static step: view/gaze/feature dropout and motion noise must be 0")
-        # Dedicated static input buffers: the graph never reads a tensor somebody else owns (e.g. a BatchPrefetcher ring slot
+    def _ensure_static(self, batch, targets) -> None:
+        if self.static_batch is not None:
+            return
+        # Dedicated static input buffers: the graphs never read a tensor somebody else owns (e.g. a BatchPrefetcher ring slot
         # that the side-stream staging of a later step overwrites while a replay is reading it).  `static_inputs()` hands them
         # out for callers that want to fill them in place and skip the per-step device copy.
-        static = type(batch)() if isinstance(batch, dict) else {}
-        for k, v in batch.items():
-            static[k] = v.clone()
-        if hasattr(batch, "video_len"):
-            static.video_len = dict(batch.video_len)
-        self.static_batch, self.static_targets = static, tuple(t.clone() for t in targets)
+        self.static_batch, self.static_targets = _clone_tree(batch), _clone_tree(tuple(targets))
+
+    def _draw(self, refill_only):
+        """All CPU random draws of one step (reference order) -> drop pattern of the training forward."""
+        if self.draw_fn is not None:
+            return self.draw_fn(self.static_batch, refill_only)
+        self.model.prepare_draws(self.static_batch, refill_only=refill_only)
+        return self.model.last_pattern
+
+    def _capture(self, batch, targets, pattern=None) -> None:
+        """Captures zero-grad + forward + loss + backward for one view/gaze drop pattern (routeformer.py:299-310,405-408: dropped
+        views skip their whole frame-encoder pass, so every pattern is a different launch sequence).  pattern = (drop_left,
+        drop_right, drop_gaze); None = whatever the model draws (dropouts off: always (False, False, False))."""
+        m = self.model
+        if m.training and m.motion_noise > 0:
+            raise ValueError("CUDA-graph capture needs a static step: motion noise must be 0")
+        self._ensure_static(batch, targets)
         batch, targets = self.static_batch, self.static_targets
         # The two eager warm-up passes and the capture pass are real training forwards without an optimiser step: without the
         # snapshot below they would leave three momentum updates in the BatchNorm running statistics and advance the CPU RNG
         # stream by three draw plans, so the graph path would diverge from the eager / reference path from step 1.
         rng_state = torch.get_rng_state()
         buffers = {name: b.clone() for name, b in m.named_buffers() if "running_" in name or name.endswith("num_batches_tracked")}
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                self._fwd_bwd(batch, targets)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
-        before = ops.launch_count
-        with torch.cuda.graph(self._graph):
-            self._static_loss = self._fwd_bwd(batch, targets)
-        self.graph_launches = ops.launch_count - before  # kernels of this library inside the captured step
+        drop_state = ops.DropoutStream.snapshot(self.arena.device)  # the warm-up forwards advance the dropout step counter
+        deferred, m._deferred_tables = m._deferred_tables, []  # this step's own draws, made before the capture was found necessary
+        key = (pattern if pattern is not None else (False, False, False), self.graph_tag)
+        m.forced_pattern = pattern
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._fwd_bwd(batch, targets)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            before = ops.launch_count
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(graph, pool=self._pool):
+                loss = self._fwd_bwd(batch, targets)
+            self._graphs[key] = (graph, loss, ops.launch_count - before)
+            self.graph_launches = ops.launch_count - before  # kernels of this library inside the captured step
+        finally:
+            m.forced_pattern = None
+            m._deferred_tables = deferred
         with torch.no_grad():
             for name, b in m.named_buffers():
                 if name in buffers:
                     b.copy_(buffers[name])
         torch.set_rng_state(rng_state)
+        ops.DropoutStream.restore(self.arena.device, drop_state)
         torch.cuda.synchronize()
+        self._graph = graph
+
+    def capture_patterns(self, batch, targets, patterns=None) -> None:
+        """Captures the graphs of the given drop patterns up front (default: every pattern the configured dropouts can produce),
+        so that no capture falls into a timed region."""
+        m = self.model
+        if patterns is None:
+            views = [(False, False)] + ([(True, False), (False, True)] if (m.training and m.view_dropout > 0 and m.with_scene) else [])
+            gazes = [False] + ([True] if (m.training and m.gaze_dropout > 0 and m.with_gaze) else [])
+            patterns = [(dl, dr, dg) for dl, dr in views for dg in gazes]
+        for pat in patterns:
+            if (pat, self.graph_tag) not in self._graphs:
+                self._capture(batch, targets, pat)
 
     def static_inputs(self):
-        """(batch, targets) the captured graph reads (None before the first graph step): fill them in place to avoid the copy."""
+        """(batch, targets) the captured graphs read (None before the first graph step): fill them in place to avoid the copy."""
         return self.static_batch, self.static_targets
 
     def _replay(self, batch, targets) -> torch.Tensor:
+        self._ensure_static(batch, targets)
         if batch is not self.static_batch:
-            for k, v in batch.items():
-                if v.data_ptr() != self.static_batch[k].data_ptr():
-                    self.static_batch[k].copy_(v, non_blocking=True)
+            _copy_tree(self.static_batch, batch)
         if targets is not self.static_targets:
-            for dst, src in zip(self.static_targets, targets):
-                if src.data_ptr() != dst.data_ptr():
-                    dst.copy_(src, non_blocking=True)
+            _copy_tree(self.static_targets, tuple(targets))
+        m = self.model
+        if not m._deferred_tables:  # draws not made ahead of time by prefetch_draws(): make them now (CPU RNG, reference order)
+            self._next_pattern = self._draw("defer")
+        pattern = self._next_pattern
+        if (pattern, self.graph_tag) not in self._graphs:
+            self._capture(self.static_batch, self.static_targets, pattern)
         if self._replayed is not None:
-            self._replayed.synchronize()  # the previous replay has consumed the pinned index buffer
-        if not self.model.commit_deferred_draws():  # draws made ahead of time by prefetch_draws(), else made now
-            self.model.prepare_draws(self.static_batch, refill_only=True)  # host only: this step's CPU random draws
-        self._graph.replay()
+            self._replayed.synchronize()  # the previous replay has consumed the pinned index buffers
+        m.commit_deferred_draws()
+        graph, loss, launches = self._graphs[(pattern, self.graph_tag)]
+        self.graph_launches = launches
+        graph.replay()
+        if m.training and m.feature_dropout > 0.0:
+            ops.DropoutStream.note_replay(self.arena.device)
         self._replayed = torch.cuda.Event()
         self._replayed.record()
-        return self._static_loss
+        self.pattern_counts[pattern] = self.pattern_counts.get(pattern, 0) + 1
+        return loss
 
     def prefetch_draws(self) -> None:
         """Optional: makes the NEXT step's CPU random draws now (same order of the CPU RNG stream), while the current replay is
         still running on the device, so that the next `step` only has to copy them into the pinned buffer and launch."""
-        if self._graph is not None and not self.model._deferred_tables:
-            self.model.prepare_draws(self.static_batch, refill_only="defer")
+        if self._graphs and not self.model._deferred_tables:
+            self._next_pattern = self._draw("defer")
 
     def broadcast_parameters(self, src: int = 0) -> None:
         if self.world > 1:
@@ -180,8 +263,6 @@ class DataParallelTrainer:
         if not self.use_cuda_graph:
             loss = self._fwd_bwd(batch, targets)
         else:
-            if self._graph is None:
-                self._capture(batch, targets)
             loss = self._replay(batch, targets)
         for w in allreduce_flat(arena.grad, self.group, self.n_buckets):
             w.wait()

@@ -97,6 +97,10 @@ class Routeformer(nn.Module):
         self._idx_slots = {}
         self._deferred_tables: list = []
         self._pending_plan = None
+        # (drop_left, drop_right, drop_gaze) of the most recent draw plan; `forced_pattern` makes the next plans use a given
+        # pattern WITHOUT drawing torch.rand (CUDA-graph capture of one graph per drop pattern, parallel.DataParallelTrainer)
+        self.last_pattern = (False, False, False)
+        self.forced_pattern = None
 
     @property
     def device(self):
@@ -173,7 +177,9 @@ class Routeformer(nn.Module):
             left = batch["left_video"]
             has_right = "right_video" in batch
             drop_left = drop_right = False
-            if self.view_dropout > 0.0 and training:  # routeformer.py:405-410
+            if self.forced_pattern is not None and training:
+                drop_left, drop_right = self.forced_pattern[0], self.forced_pattern[1] or not has_right
+            elif self.view_dropout > 0.0 and training:  # routeformer.py:405-410
                 one = bool(torch.rand(1) < self.view_dropout)
                 drop_left = one and bool(torch.rand(1) < 0.5)
                 drop_right = (one and not drop_left) or not has_right
@@ -187,7 +193,9 @@ class Routeformer(nn.Module):
             T_vid = self._video_len(batch, "left_video")
             n_streams += 2
         if self.with_gaze:
-            if self.gaze_dropout > 0.0 and training:  # routeformer.py:300-301
+            if self.forced_pattern is not None and training:
+                plan["drop_gaze"] = bool(self.forced_pattern[2])
+            elif self.gaze_dropout > 0.0 and training:  # routeformer.py:300-301
                 plan["drop_gaze"] = bool(torch.rand(1) < self.gaze_dropout)
             T_vid = self._video_len(batch, "front_video")
             n_streams += 1
@@ -288,9 +296,12 @@ class Routeformer(nn.Module):
         log: List[tuple] = []
         if self.with_video:
             pv = self._plan_visual(batch, training)
-            pv["tables"] = self._upload(pv["draws"], dev, "visual", refill_only)
+            # the training forward and the eval-mode target pass of one step (full_comparison.py:481-482) get separate staging
+            # buffers: both uploads of a captured step read theirs at replay time
+            pv["tables"] = self._upload(pv["draws"], dev, "visual" if training else "visual_eval", refill_only)
             plan["visual"] = pv
             log += pv["log"]
+            self.last_pattern = (bool(pv["drop_left"]), bool(pv["drop_right"]), bool(pv["drop_gaze"]))
         if backbone and isinstance(self.gps_backbone, Informer) and not (not self.training and self.configs.autoregressive):
             draws, blog = self._plan_backbone(batch["gps"].shape[1], self.gps_backbone.pred_len)
             plan["backbone"] = (blog, self._upload(draws, dev, "backbone", refill_only))
@@ -512,6 +523,8 @@ class Routeformer(nn.Module):
 
     def forward(self, batch, target_batch=None):
         c = self.configs
+        if self.training and self.feature_dropout > 0.0:
+            ops.DropoutStream.begin_step(batch["gps"].device)  # fresh Philox sub-streams for this step's dropout sites
         if self._pending_plan is None:
             self.prepare_draws(batch)
         motion, visual = self.preprocess_batch(batch)

@@ -460,6 +460,76 @@ def test_cuda_graph_step_matches_eager():
     assert eager[0][0] != eager[1][0]  # different draws every step
 
 
+def test_cuda_graph_with_paper_dropouts():
+    """The paper configuration trains with view / gaze / feature dropout (full_comparison.py:272-275).  Under CUDA graphs:
+    one graph per (left, right, gaze) drop pattern, chosen per step by the same CPU torch.rand draws the reference makes;
+    feature-dropout masks come from a device-resident step counter the graph itself advances.  The graph path must follow the
+    eager path step for step: same patterns, same draws, same losses, same gradients."""
+    import dataclasses
+
+    import routeformer_b200 as R
+    from routeformer_b200.parallel import DataParallelTrainer
+
+    gold = load_golden("full_small_train")
+    cfg, spec, sd, batch = case_from_golden(gold)
+    cfg = dataclasses.replace(cfg, view_dropout=0.6, gaze_dropout=0.4)
+    t_wp, t_dense = targets_for(cfg, gold["B"], gold["dseed"] + 1000)
+    lossf = R.FutureDiscountedLoss({0: 0.97}, epsilon=1.0, loss_function="smooth_l1")
+    runs = []
+    for graph in (False, True):
+        from routeformer_b200 import ops
+        ops.DropoutStream._base.clear()
+        ops.DropoutStream._base_host.clear()
+        model = build_product(cfg, spec, feature_dropout=0.1).to(DEV).train()
+        model.load_state_dict(sd)
+        trainer = DataParallelTrainer(model, lambda out, tgt: lossf(out[0], tgt[0]) + 0.5 * lossf(out[1], tgt[1]), use_cuda_graph=graph)
+        dev_batch, tgt = to_device(batch, DEV), (t_wp.to(DEV), t_dense.to(DEV))
+        torch.manual_seed(4242)
+        steps = []
+        for _ in range(10):
+            loss = trainer._replay(dev_batch, tgt) if graph else trainer._fwd_bwd(dev_batch, tgt)
+            torch.cuda.synchronize()
+            steps.append((model.last_pattern if not graph else trainer._next_pattern, loss.item(), trainer.arena.grad.clone(),
+                          list(model.last_draw_log)))
+        runs.append((steps, trainer))
+    (eager, _), (graphed, trainer) = runs
+    assert len(trainer._graphs) > 1, "the seeds must exercise more than one drop pattern"
+    assert len({p for p, *_ in eager}) == len(trainer._graphs)
+    for (p0, l0, g0, d0), (p1, l1, g1, d1) in zip(eager, graphed):
+        assert p0 == p1 and d0 == d1
+        assert abs(l0 - l1) < 1e-5 * abs(l0), (l0, l1)
+        assert rel_err(g1.cpu(), g0.cpu()) < 1e-3
+    assert len({round(l, 6) for _, l, _, _ in graphed}) == len(graphed)  # fresh masks / draws every replay
+
+
+def test_training_step_under_cuda_graph():
+    """SURVEY 8(f) N1 at speed: the reference's whole training_step (forward + eval-mode target pass + both losses + detached
+    dense re-weighting, full_comparison.py:470-532) captured as one graph through DataParallelTrainer(step_fn, draw_fn)."""
+    import routeformer_b200 as R
+    from routeformer_b200.parallel import DataParallelTrainer
+
+    results = []
+    for graph in (False, True):
+        gold, cfg, spec, sd, batch, model, dev_batch = _steps_case()
+        model.train()
+        steps = R.ParallelTrainerSteps(model)
+        step_fn, draw_fn = steps.graph_hooks(current_epoch=10)
+        trainer = DataParallelTrainer(model, None, use_cuda_graph=graph, step_fn=step_fn, draw_fn=draw_fn)
+        trainer.graph_tag = True
+        torch.manual_seed(12345)
+        out = []
+        for _ in range(3):
+            loss = trainer._replay(dev_batch, ()) if graph else trainer._fwd_bwd(dev_batch, ())
+            torch.cuda.synchronize()
+            out.append((loss.item(), steps.last_metrics["train_ade"].item(), trainer.arena.grad.clone()))
+        results.append(out)
+    g = gold["train_epoch10"]
+    assert abs(results[0][0][0] - g["loss"]) < 2e-2 * abs(g["loss"])  # first eager step = the reference's golden step
+    for (l0, a0, g0), (l1, a1, g1) in zip(*results):
+        assert abs(l0 - l1) < 1e-5 * abs(l0) and abs(a0 - a1) < 1e-5 * abs(a0)
+        assert rel_err(g1.cpu(), g0.cpu()) < 1e-3
+
+
 def _steps_case():
     gold = load_golden("steps_small")
     cfg, spec = O.OracleConfig(**gold["cfg"]), O.BackboneSpec(**gold["spec"])
