@@ -86,7 +86,8 @@ class DataParallelTrainer:
 
     def __init__(self, model, loss_fn: Callable, lr: float = 1e-5, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  max_grad_norm: float = 2.5, group=None, n_buckets: int = 4, use_cuda_graph: bool = False,
-                 overlap_wgrad: bool = True, step_fn: Optional[Callable] = None, draw_fn: Optional[Callable] = None):
+                 overlap_wgrad: bool = True, step_fn: Optional[Callable] = None, draw_fn: Optional[Callable] = None,
+                 overlap_allreduce: bool = True):
         """step_fn(batch, targets) -> loss (optional) replaces `loss_fn(model(batch), targets)`: e.g. the reference's whole
         `training_step` (forward + eval-mode target pass + both losses, `ParallelTrainerSteps.graph_hooks`).  draw_fn(batch,
         refill_only) -> drop pattern must then make ALL CPU random draws of that step, in order (used to refresh the pinned index
@@ -109,6 +110,12 @@ class DataParallelTrainer:
         self.step_count = 0
         self.use_cuda_graph = use_cuda_graph
         self.wgrad_stream = torch.cuda.Stream(dev) if (overlap_wgrad and dev.type == "cuda") else None
+        # Early all-reduce (the reference's DDP buckets overlap with backward, full_comparison.py:794): the GPS backbone holds
+        # 78 % of the gradient bytes and finishes its backward pass first, so its slices of the arena are all-reduced on a side
+        # stream -- inside the captured step -- while the visual encoders' backward pass is still running.
+        self.comm_stream = torch.cuda.Stream(dev) if (overlap_allreduce and self.world > 1 and dev.type == "cuda") else None
+        self.early_ranges, self.late_ranges = self._split_ranges("gps_backbone.") if self.comm_stream is not None else ([], [])
+        self._early_work = []
         self._graph = None       # most recently captured graph (None until the first graph step)
         self._graphs = {}        # drop pattern -> (graph, static loss tensor, launches)
         self._pool = None
@@ -119,28 +126,72 @@ class DataParallelTrainer:
         self._replayed = None
         self.graph_launches = 0
 
+    def _split_ranges(self, prefix: str):
+        """(ranges of the gradient arena holding the parameters named `prefix*`, the complementary ranges), merged and sorted."""
+        arena = self.arena
+        spans = sorted((arena.offsets[id(p)], arena.offsets[id(p)] + p.numel()) for n, p in self.model.named_parameters()
+                       if p.requires_grad and n.startswith(prefix))
+        early = []
+        for lo, hi in spans:
+            if early and lo - early[-1][1] < 2 * 64:  # alignment padding between groups (always zero): keep the range whole
+                early[-1][1] = hi
+            else:
+                early.append([lo, hi])
+        late, pos = [], 0
+        for lo, hi in early:
+            if lo > pos:
+                late.append((pos, lo))
+            pos = hi
+        if pos < arena.n_trainable:
+            late.append((pos, arena.n_trainable))
+        return [tuple(r) for r in early], late
+
+    def _early_allreduce(self) -> None:
+        """Backward hook: the GPS backbone's gradients are complete (their kernels are enqueued on the main / wgrad streams)."""
+        main = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(main)
+        if self.wgrad_stream is not None:
+            self.comm_stream.wait_stream(self.wgrad_stream)
+        with torch.cuda.stream(self.comm_stream):
+            for lo, hi in self.early_ranges:
+                self._early_work.append(dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
     # -- forward + backward ----------------------------------------------------------------------
     def _fwd_bwd(self, batch, targets) -> torch.Tensor:
         from . import functional as Fn
 
         self.arena.zero_grad()
-        if self.step_fn is not None:
-            loss = self.step_fn(batch, targets)
-        else:
-            out = self.model(batch)
-            loss = self.loss_fn(out, targets)
-        if self.wgrad_stream is None:
-            loss.backward()
-            return loss
-        # weight-gradient GEMMs on a side stream, concurrent with the dgrad chain; joined before anyone reads the gradients
-        main = torch.cuda.current_stream()
-        self.wgrad_stream.wait_stream(main)  # the zero-fill of the gradient arena precedes the first accumulation
-        Fn.WgradStream.stream = self.wgrad_stream
+        early = self.comm_stream is not None
+        self.model.backbone_grads_ready_hook = self._early_allreduce if early else None
+        self._early_work = []
         try:
-            loss.backward()
+            if self.step_fn is not None:
+                loss = self.step_fn(batch, targets)
+            else:
+                out = self.model(batch)
+                loss = self.loss_fn(out, targets)
+            main = torch.cuda.current_stream()
+            if self.wgrad_stream is None:
+                loss.backward()
+            else:
+                # weight-gradient GEMMs on a side stream, concurrent with the dgrad chain; joined before anyone reads the gradients
+                self.wgrad_stream.wait_stream(main)  # the zero-fill of the gradient arena precedes the first accumulation
+                Fn.WgradStream.stream = self.wgrad_stream
+                try:
+                    loss.backward()
+                finally:
+                    Fn.WgradStream.stream = None
+                    main.wait_stream(self.wgrad_stream)
         finally:
-            Fn.WgradStream.stream = None
-            main.wait_stream(self.wgrad_stream)
+            self.model.backbone_grads_ready_hook = None
+        if early:
+            if not self._early_work:
+                raise RuntimeError("the early all-reduce did not fire: the GPS backbone's input carried no gradient")
+            with torch.cuda.stream(self.comm_stream):
+                for w in self._early_work:
+                    w.wait()
+            main.wait_stream(self.comm_stream)
+            self._early_work = []
         return loss
 
     def _ensure_static(self, batch, targets) -> None:
@@ -231,6 +282,10 @@ class DataParallelTrainer:
             self._next_pattern = self._draw("defer")
         pattern = self._next_pattern
         if (pattern, self.graph_tag) not in self._graphs:
+            if self.comm_stream is not None and self._graphs:
+                # a capture runs two eager warm-up steps whose collectives the other ranks would not match
+                raise RuntimeError("with the overlapped all-reduce every drop pattern must be captured up front, on all ranks in the "
+                                   "same order: call capture_patterns(batch, targets) before the first step")
             self._capture(self.static_batch, self.static_targets, pattern)
         if self._replayed is not None:
             self._replayed.synchronize()  # the previous replay has consumed the pinned index buffers
@@ -264,7 +319,11 @@ class DataParallelTrainer:
             loss = self._fwd_bwd(batch, targets)
         else:
             loss = self._replay(batch, targets)
-        for w in allreduce_flat(arena.grad, self.group, self.n_buckets):
+        if self.comm_stream is not None:  # the backbone's slices were all-reduced inside the step, overlapped with backward
+            work = [dist.all_reduce(arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True) for lo, hi in self.late_ranges]
+        else:
+            work = allreduce_flat(arena.grad, self.group, self.n_buckets)
+        for w in work:
             w.wait()
         self.step_count += 1
         self.gnorm_sq.zero_()

@@ -101,6 +101,9 @@ class Routeformer(nn.Module):
         # pattern WITHOUT drawing torch.rand (CUDA-graph capture of one graph per drop pattern, parallel.DataParallelTrainer)
         self.last_pattern = (False, False, False)
         self.forced_pattern = None
+        # called (no arguments) in the backward pass as soon as the gradient w.r.t. the GPS backbone's input is complete, i.e.
+        # when every gradient of the backbone's own parameters has been enqueued (data-parallel trainer: early all-reduce)
+        self.backbone_grads_ready_hook = None
 
     @property
     def device(self):
@@ -489,6 +492,9 @@ class Routeformer(nn.Module):
         ld = (enc_in + 3) // 4 * 4
         x, origin = Fn.MotionFeatures.apply(motion_dynamics.contiguous(), visual_features if has_vis else None, E, ld, c.rotate_motion,
                                             False, 0.0, 1.0, bool(c._only_motion) or not has_vis, True)
+        if self.backbone_grads_ready_hook is not None and x.requires_grad:
+            hook = self.backbone_grads_ready_hook
+            x.register_hook(lambda g: (hook(), None)[1])
         if isinstance(gb, Informer):
             if getattr(self, "_backbone_plan", None) is not None:
                 log, tables = self._backbone_plan

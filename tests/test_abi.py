@@ -68,3 +68,35 @@ def test_build_stamp_is_location_independent(tmp_path):
     assert B._digest(src) == B._digest([str(c) for c in copies])
     (copy_dir / os.path.basename(src[0])).write_text("// changed")
     assert B._digest(src) != B._digest([str(c) for c in copies])
+
+
+def test_patch_reference_rebinds_the_path_symbols():
+    """routeformer_b200.compat.patch_reference(): the experiment's own import lines then resolve to the CUDA implementations."""
+    import sys
+    import types
+
+    import routeformer_b200 as R
+    from routeformer_b200.compat import patch_reference
+
+    saved = {k: v for k, v in sys.modules.items() if k == "routeformer" or k.startswith("routeformer.")}
+    try:
+        for name in ("routeformer", "routeformer.models", "routeformer.models.gps_backbone", "routeformer.score",
+                     "routeformer.losses", "routeformer.losses.future_discounted_mse"):
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+        sys.modules["routeformer.models.gps_backbone"].Transformer = "reference class, outside the path"
+        done = patch_reference()
+        from routeformer import Routeformer  # noqa: I001
+        from routeformer.losses.future_discounted_mse import FutureDiscountedLoss
+        from routeformer.models import RouteformerConfig
+        from routeformer.models.gps_backbone import GPSBackboneConfig, Informer, Transformer
+        from routeformer.score import ade, fde
+        assert Routeformer is R.Routeformer and RouteformerConfig is R.RouteformerConfig and Informer is R.Informer
+        assert GPSBackboneConfig is R.GPSBackboneConfig and FutureDiscountedLoss is R.FutureDiscountedLoss
+        assert ade is R.ade and fde is R.fde and Transformer == "reference class, outside the path"
+        assert "routeformer.models.cross_modal_transformer" not in done  # not importable here: skipped, not an error
+    finally:
+        for k in [k for k in sys.modules if k == "routeformer" or k.startswith("routeformer.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

@@ -119,3 +119,28 @@ def test_deferred_draws_fill_the_same_pinned_tables():
     assert all(bool((v[0] == 0).all()) for v in model._idx_slots.values())
     assert model.commit_deferred_draws() and not model.commit_deferred_draws()
     assert ref and all(torch.equal(ref[k], v[0]) for k, v in model._idx_slots.items())
+
+
+def test_early_allreduce_ranges_partition_the_gradient_arena():
+    """The overlapped all-reduce sends the GPS backbone's slices of the flat gradient arena early and the rest after backward:
+    the two range lists must partition [0, n_trainable) and the early one must hold exactly the backbone's parameters."""
+    from oracle import routeformer_oracle as O
+    from routeformer_b200.parallel import DataParallelTrainer
+    from tests.helpers import build_product
+
+    cfg = O.OracleConfig(d_model=64, n_heads=4, e_layers=3, d_ff=128, with_video=True, with_gaze=True, dense_prediction=True,
+                         encoder_layers=2, encoder_d_ff=64, image_embedding_size=32, encoder_hidden_size=32)
+    model = build_product(cfg, O.BackboneSpec(image_size=32, patch=8, channels=48))
+    trainer = DataParallelTrainer(model, None)
+    early, late = trainer._split_ranges("gps_backbone.")
+    arena = trainer.arena
+    covered = sorted(early + late)
+    assert covered[0][0] == 0 and covered[-1][1] == arena.n_trainable
+    assert all(a[1] == b[0] for a, b in zip(covered[:-1], covered[1:]))
+    assert len(early) <= 3  # the q/k/v groups and the remaining parameters of the backbone: a few large contiguous slices
+    inside = lambda o: any(lo <= o < hi for lo, hi in early)
+    for name, p in model.named_parameters():
+        if p.requires_grad:
+            assert inside(arena.offsets[id(p)]) == name.startswith("gps_backbone."), name
+    n_early = sum(hi - lo for lo, hi in early)
+    assert n_early >= sum(p.numel() for n, p in model.named_parameters() if n.startswith("gps_backbone.") and p.requires_grad)
