@@ -71,7 +71,10 @@ class ParallelTrainerSteps:
         model = self.model
 
         def step_fn(batch, _targets):
-            loss, self.last_metrics = self.training_step(batch, current_epoch)
+            loss, metrics = self.training_step(batch, current_epoch)
+            # detached: a metric that kept its autograd graph would keep the previous (warm-up) step's saved tensors alive until
+            # the next call replaces it -- i.e. free them in the middle of a graph capture
+            self.last_metrics = {k: v.detach() for k, v in metrics.items()}
             return loss
 
         def draw_fn(batch, refill_only):
