@@ -176,7 +176,8 @@ def run_train(args):
 
     use_graph = not args.no_graph
     trainer = DataParallelTrainer(model, loss_fn, lr=1e-5, weight_decay=1e-4, max_grad_norm=2.5, use_cuda_graph=use_graph,
-                                  overlap_wgrad=not args.no_wgrad_overlap)
+                                  overlap_wgrad=not args.no_wgrad_overlap,
+                                  overlap_allreduce=os.environ.get("RF_NO_EARLY_ALLREDUCE", "0") != "1")
     trainer.broadcast_parameters()
     # inputs: pinned host batch in the reference layout; the device batch holds the frames the model consumes (8 of 40 per view)
     pinned = {k: v.contiguous().pin_memory() for k, v in host_batch.items()}
