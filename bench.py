@@ -156,6 +156,19 @@ def dist_setup(args):
     return dist, world, rank, local, dev, barrier, max_over_ranks
 
 
+def finish(dist, world) -> None:
+    """End of a multi-rank run.  Captured graphs that contain NCCL collectives keep communicator resources alive, and
+    `destroy_process_group()` was observed to hang behind them (N = 2, overlapped all-reduce): all ranks synchronise, flush and
+    leave without tearing the communicator down."""
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def run_train(args):
     import routeformer_b200 as R
     from routeformer_b200 import ops
@@ -212,8 +225,7 @@ def run_train(args):
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_run": True, "value": round(value, 2), "ms_per_step": round(ms / args.steps, 3), "gpu_launches": int(launches)}))
-        if world > 1:
-            dist.destroy_process_group()
+        finish(dist, world)
         return
 
     # ---- end to end through the public API: pinned host batch -> stage -> step -> loss.item() ----
@@ -416,8 +428,7 @@ def run_train(args):
             "loss": float(loss.item()),
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(dist, world)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -626,8 +637,7 @@ def run_fwd(args):
                         "d2h_bytes_per_step": int(wp_host.numel() * 4), "steps": e2e_steps},
                 "waypoint_checksum": float(wp_host.double().sum())}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(dist, world)
 
 
 def run_dreyeve_sweep(args):
@@ -670,8 +680,7 @@ def run_dreyeve_sweep(args):
                           "config": {"workload": "BASELINE configs[3]: DR(eye)VE-shaped full-modality inference sweep, inputs resident in HBM "
                                                  "(consumed frames only), paper config, rotate_motion", "cuda_graph": not args.no_graph},
                           "sweep": rows}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(dist, world)
 
 
 def run_crop_micro(args):
