@@ -173,8 +173,10 @@ __global__ void __launch_bounds__(256) fov_crop_kernel(const Args a) {
   }
 }
 
-// ---- tiled, separable kernel -------------------------------------------------------------------
+// ---- strip kernel: shared-memory staged source window, separable blend, register reuse down the rows -------------
 constexpr int TILE_THREADS = 256;
+constexpr int STRIP_ROWS = 32;        // output rows per CTA
+constexpr int STAGE_FLOATS = 15872;   // 62 KiB staging buffer (3 channels x rows x pitch floats)
 
 // two adjacent source elements (element offset even, pointer 2-element aligned) -> float2
 template <typename T> __device__ __forceinline__ float2 load_px2(const T* p);
@@ -200,8 +202,7 @@ __device__ __forceinline__ void store2(__nv_bfloat16* dst, float a, float b) {
 
 struct TiledArgs {
   Args a;
-  int pitch;   // floats per (channel, row) line of the staging buffer: >= W + 2, even
-  int vec2;    // 1: W even and the frame base 2-element aligned -> 2-element vector loads in pass V
+  int vec2;    // 1: W even and the frame base 2-element aligned -> 2-element vector loads while staging
 };
 
 // one bilinear sample with zero padding, taps in ATen's order (mirrored windows only: rare, slow, correct)
@@ -218,13 +219,99 @@ __device__ __forceinline__ float direct_sample(const TS* pl, float sx, float sy,
   return v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
 }
 
-template <typename TS, typename TD, int ROWS>
-__global__ void __launch_bounds__(TILE_THREADS) fov_crop_tiled_kernel(const TiledArgs ta) {
-  extern __shared__ float tmp[];  // [3][ROWS][pitch]
+// The four staged floats [e, e+3] of one line, e even: two 8 B shared loads
+struct Win4 { float f[4]; };
+__device__ __forceinline__ Win4 load_win(const float* line, int e) {
+  const float2 lo = *reinterpret_cast<const float2*>(line + e), hi = *reinterpret_cast<const float2*>(line + e + 2);
+  Win4 w;
+  w.f[0] = lo.x; w.f[1] = lo.y; w.f[2] = hi.x; w.f[3] = hi.y;
+  return w;
+}
+
+// packed fp32 pairs (Blackwell FFMA2 / FMUL2: two IEEE fp32 operations per issue slot)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float2 upk(f32x2 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+// the four staged floats [e, e+3] of one line (e even) as two packed pairs: two 8 B shared loads
+struct Win { f32x2 lo, hi; };
+__device__ __forceinline__ Win load_w(const float* line) {
+  Win w;
+  w.lo = *reinterpret_cast<const f32x2*>(line);
+  w.hi = *reinterpret_cast<const f32x2*>(line + 2);
+  return w;
+}
+
+struct RowInfo {  // per output row of a chunk, written once per CTA
+  int ia, ib;      // float offsets of the staged lines of source rows y0 / y0+1 (channel 0)
+  float wy0, wy1;  // their weights (0 outside the frame)
+  long long o;     // output offset of (row, this thread's columns excluded, channel 0)
+  int y0, pad;
+};
+
+__device__ __forceinline__ void store1(float* dst, float a) { *dst = a; }
+__device__ __forceinline__ void store1(__half* dst, float a) { *dst = __float2half_rn(a); }
+__device__ __forceinline__ void store1(__nv_bfloat16* dst, float a) { *dst = __float2bfloat16_rn(a); }
+
+// Rows [my_a, my_b) of the chunk for one thread.  PAIR: the thread's two adjacent output pixels read the same 4-float window
+// (<= 1 source column per output column) and leave as one packed store; otherwise the routine is called once per pixel.
+// The source rows of the previous output row stay in registers; all control flow is CTA-uniform.
+template <bool PAIR, typename TD>
+__device__ __forceinline__ void strip_rows(const float* __restrict__ stage, const RowInfo* __restrict__ rows, int my_a, int my_b, int pitch,
+                                           int e0, const float (&wa)[4], const float (&wb)[4], long long col_off, long long ch_stride,
+                                           const float (&mean)[3], const float (&inv_std)[3], TD* __restrict__ out) {
+  Win A[3], B[3];
+  const f32x2 walo = pk(wa[0], wa[1]), wahi = pk(wa[2], wa[3]);
+  const f32x2 wblo = pk(wb[0], wb[1]), wbhi = pk(wb[2], wb[3]);
+  int cur_y = -(1 << 30);
+  for (int r = my_a; r < my_b; ++r) {
+    const RowInfo ri = rows[r];
+    if (ri.y0 != cur_y) {
+      const bool shift = ri.y0 == cur_y + 1;
+      const float* la = stage + ri.ia + e0;
+      const float* lb = stage + ri.ib + e0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (shift) A[c] = B[c];
+        else A[c] = load_w(la + c * pitch);
+        B[c] = load_w(lb + c * pitch);
+      }
+      cur_y = ri.y0;
+    }
+    const f32x2 wy0 = pk(ri.wy0, ri.wy0), wy1 = pk(ri.wy1, ri.wy1);
+    TD* dst = out + ri.o + col_off;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      // vertical blend of the window, then the horizontal 4-tap dot product(s)
+      const f32x2 tlo = fma2(B[c].lo, wy1, mul2(A[c].lo, wy0)), thi = fma2(B[c].hi, wy1, mul2(A[c].hi, wy0));
+      const float2 p0 = upk(fma2(thi, wahi, mul2(tlo, walo)));
+      if (PAIR) {
+        const float2 p1 = upk(fma2(thi, wbhi, mul2(tlo, wblo)));
+        store2(dst + c * ch_stride, ((p0.x + p0.y) - mean[c]) * inv_std[c], ((p1.x + p1.y) - mean[c]) * inv_std[c]);
+      } else {
+        store1(dst + c * ch_stride, ((p0.x + p0.y) - mean[c]) * inv_std[c]);
+      }
+    }
+  }
+}
+
+// A CTA owns STRIP_ROWS output rows of one frame and works through them in chunks whose source rows fit the staging buffer:
+//   stage  : the source rows x columns the chunk touches, converted to fp32, loaded with independent coalesced vector loads
+//            (every thread issues its whole share before the first use: the pass is bandwidth-, not latency-bound);
+//   compute: a thread owns two adjacent output columns and walks DOWN its rows; the column taps are a 4-float window of the
+//            staged line with a fixed 4-vector of weights (no indexing in the loop), the two source rows of the previous
+//            output row stay in registers (an up-sampling crop needs a new source row for ~2 of 3 output rows), the vertical
+//            blend is shared by the two pixels.  ~10 instructions per output element against ~35 for the direct gather.
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(TILE_THREADS, 2) fov_crop_tiled_kernel(const TiledArgs ta) {
+  extern __shared__ __align__(16) float stage[];  // [rows][3][pitch]
+  __shared__ RowInfo s_rows[STRIP_ROWS];
   const Args& a = ta.a;
   const int n = blockIdx.y;
-  const int r0 = blockIdx.x * ROWS;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = blockIdx.x * STRIP_ROWS;
+  const int tid = threadIdx.x;
   const int S = a.S, H = a.H, W = a.W;
 
   const float cx = __ldg(a.centers + 2 * n), cy = __ldg(a.centers + 2 * n + 1);
@@ -239,84 +326,17 @@ __global__ void __launch_bounds__(TILE_THREADS) fov_crop_tiled_kernel(const Tile
   auto sample_x = [&](int ox) { return ((fw * ((2 * ox + 1) * inv_s - 1.0f) + (2.0f * cx - 1.0f) + 1.0f) * W - 1.0f) * 0.5f; };
   auto sample_y = [&](int oy) { return ((fh * ((2 * oy + 1) * inv_s - 1.0f) + (2.0f * cy - 1.0f) + 1.0f) * H - 1.0f) * 0.5f; };
 
-  // ---- this thread's two output columns (pass H) ------------------------------------------------
   const int pairs = S >> 1;
   const int groups = TILE_THREADS / pairs;            // row groups that fit the CTA (S = 256 -> 2, 224 -> 2, 64 -> 8)
   const int pg = tid / pairs, pp = tid - pg * pairs;  // one integer division per thread
   const int ox = pp << 1;
-  const bool mirrored = !(fw > 0.0f);                 // CTA-uniform; sx then does not grow with ox: direct gather below
-  // Source-column span the window covers, clipped to the frame; the first column is rounded down to an even one (vector
-  // loads).  sx grows with ox, so every in-frame tap of every output column lies in [j_lo, j_hi].
-  const int j_lo = max(static_cast<int>(floorf(sample_x(0))), 0) & ~1;
-  const int j_hi = min(static_cast<int>(floorf(sample_x(S - 1))) + 1, W - 1);
-  const int span = j_hi - j_lo + 1;                   // <= 0: the window misses the frame horizontally
-  // Column taps: slots (xi, xi + 1) of the staged line with weights (wa, wb).  Slot `span` is zero-filled by pass V, so an
-  // in-frame tap a at the last column can read its (out-of-frame, weight 0) neighbour safely.
-  int xi[2];
-  float wa[2], wb[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float sx = sample_x(ox + i);
-    const float fx0 = floorf(sx);
-    const int x0 = static_cast<int>(fx0);
-    const float w1 = sx - fx0, w0 = 1.0f - w1;
-    const bool a_in = x0 >= 0 && x0 < W, b_in = x0 + 1 >= 0 && x0 + 1 < W;
-    if (a_in) { xi[i] = x0 - j_lo; wa[i] = w0; wb[i] = b_in ? w1 : 0.0f; }
-    else if (b_in) { xi[i] = 0; wa[i] = w1; wb[i] = 0.0f; }   // x0 == -1: column 0 is slot 0 (j_lo == 0)
-    else { xi[i] = 0; wa[i] = 0.0f; wb[i] = 0.0f; }
-  }
+  const bool worker = pg < groups;
+  const bool mirrored = !(fw > 0.0f) || !(fh > 0.0f);  // CTA-uniform; sample positions then do not grow with the index
+  const int r_end = min(r0 + STRIP_ROWS, S);
 
-  // ---- rows of this tile (out-of-frame rows: weight 0, row index clamped into the frame) -------
-  int yar[ROWS], ybr[ROWS];
-  float wy0r[ROWS], wy1r[ROWS];
-  bool any_row = false;
-#pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    const float sy = sample_y(min(r0 + r, S - 1));
-    const float fy0 = floorf(sy);
-    const int y0 = static_cast<int>(fy0);
-    const float w1 = sy - fy0;
-    const bool a_in = y0 >= 0 && y0 < H, b_in = y0 + 1 >= 0 && y0 + 1 < H;
-    yar[r] = min(max(y0, 0), H - 1);
-    ybr[r] = min(max(y0 + 1, 0), H - 1);
-    wy0r[r] = a_in ? 1.0f - w1 : 0.0f;
-    wy1r[r] = b_in ? w1 : 0.0f;
-    any_row = any_row || a_in || b_in;
-  }
-  const bool constant_tile = !mirrored && (!any_row || span <= 0);  // CTA-uniform: the whole tile samples the zero padding
-
-  // ---- pass V: vertical blend of the window's source columns into shared memory ------------------
-  if (!constant_tile && !mirrored) {
-    const int npairs = (span + 1) >> 1;
-    const int half = (npairs + 1) >> 1;
-    for (int item = warp; item < 3 * ROWS * 2; item += TILE_THREADS / 32) {  // (channel, row, half line) per warp
-      const int rc = item >> 1, hsel = item & 1;
-      const int c = rc / ROWS, r = rc - c * ROWS;
-      float* line = tmp + rc * ta.pitch;
-      const float w0 = wy0r[r], w1 = wy1r[r];
-      const TS* rowa = src + c * plane + static_cast<long long>(yar[r]) * W + j_lo;
-      const TS* rowb = src + c * plane + static_cast<long long>(ybr[r]) * W + j_lo;
-      const int p_begin = hsel * half, p_end = min(npairs, p_begin + half);
-      if (ta.vec2) {
-        for (int jp = p_begin + lane; jp < p_end; jp += 32) {
-          const int j = jp << 1;
-          float2 va, vb;
-          if (j + 1 < span) { va = load_px2<TS>(rowa + j); vb = load_px2<TS>(rowb + j); }
-          else { va = make_float2(load_px<TS>(rowa + j), 0.0f); vb = make_float2(load_px<TS>(rowb + j), 0.0f); }
-          *reinterpret_cast<float2*>(line + j) = make_float2(va.x * w0 + vb.x * w1, va.y * w0 + vb.y * w1);
-        }
-      } else {
-        for (int j = 2 * p_begin + lane; j < min(span, 2 * p_end); j += 32) line[j] = load_px<TS>(rowa + j) * w0 + load_px<TS>(rowb + j) * w1;
-      }
-      if (hsel == 1 && lane == 0) line[span] = 0.0f;  // (an odd span has already written this slot with the same 0)
-    }
-  }
-  __syncthreads();
-  if (pg >= groups) return;
-
-  // ---- pass H: horizontal blend, normalise, store -----------------------------------------------
+  // output addressing
   long long obase, row_stride, ch_stride;
-  int patch_rows_left = 1 << 30;  // patch-major: rows until the tile crosses into the next row of patches
+  int patch_rows_left = 1 << 30;  // patch-major: rows until the strip crosses into the next row of patches
   if (a.patch > 0) {
     const int px = fast_div(ox, a.patch_magic), ix = ox - px * a.patch;
     const int py = fast_div(r0, a.patch_magic), iy = r0 - py * a.patch;
@@ -329,25 +349,155 @@ __global__ void __launch_bounds__(TILE_THREADS) fov_crop_tiled_kernel(const Tile
     row_stride = S;
     ch_stride = static_cast<long long>(S) * S;
   }
-  for (int r = pg; r < ROWS; r += groups) {
-    if (r0 + r >= S) break;
+  auto out_offset = [&](int r) {  // r = row inside the strip
     long long o = obase + r * row_stride;
-    if (r >= patch_rows_left)  // next row of patches: + G patches, back to row (r - patch_rows_left) of that patch
+    int left = patch_rows_left, rr = r;
+    while (rr >= left) {  // next row(s) of patches: + G patches, back to the first row of that patch
       o += static_cast<long long>(a.G) * a.out_ld - static_cast<long long>(a.patch) * a.patch;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float v0 = 0.0f, v1 = 0.0f;
-      if (mirrored) {
-        const float sy = sample_y(r0 + r);
-        v0 = direct_sample<TS>(src + c * plane, sample_x(ox), sy, H, W);
-        v1 = direct_sample<TS>(src + c * plane, sample_x(ox + 1), sy, H, W);
-      } else if (!constant_tile) {
-        const float* line = tmp + (c * ROWS + r) * ta.pitch;
-        v0 = line[xi[0]] * wa[0] + line[xi[0] + 1] * wb[0];
-        v1 = line[xi[1]] * wa[1] + line[xi[1] + 1] * wb[1];
-      }
-      store2(out + o + c * ch_stride, (v0 - a.mean[c]) * a.inv_std[c], (v1 - a.mean[c]) * a.inv_std[c]);
+      rr -= a.patch;
     }
+    return o;
+  };
+
+  if (mirrored) {  // direct gather, any orientation
+    if (worker)
+      for (int r = r0 + pg; r < r_end; r += groups) {
+        const float sy = sample_y(r);
+        const long long o = out_offset(r - r0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float v0 = direct_sample<TS>(src + c * plane, sample_x(ox), sy, H, W);
+          const float v1 = direct_sample<TS>(src + c * plane, sample_x(ox + 1), sy, H, W);
+          store2(out + o + c * ch_stride, (v0 - a.mean[c]) * a.inv_std[c], (v1 - a.mean[c]) * a.inv_std[c]);
+        }
+      }
+    return;
+  }
+
+  // Source-column span the window covers, clipped to the frame, first column rounded down to an even one.  sx grows with ox,
+  // so every in-frame tap of every output column lies in [j_lo, j_hi].
+  const int j_lo = max(static_cast<int>(floorf(sample_x(0))), 0) & ~1;
+  const int j_hi = min(static_cast<int>(floorf(sample_x(S - 1))) + 1, W - 1);
+  const int span = j_hi - j_lo + 1;                       // <= 0: the window misses the frame horizontally
+  const int pitch = ((max(span, 0) + 1) & ~1) + 4;        // even, >= span + 4: the 4-float windows never leave the line
+  const int max_rows = max(span > 0 ? STAGE_FLOATS / (3 * pitch) : 0, 0);
+
+  // Column taps of the two pixels: window start e (even) and a 4-vector of weights over slots e..e+3 of the staged line.
+  // narrow (<= 1 source column per output column): both pixels share the window of pixel 0.
+  const bool narrow = fw * W <= 0.999f * static_cast<float>(S);  // (margin: the two floors must never differ by 2)
+  int e[2];
+  float wgt[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float sx = sample_x(ox + i);
+    const float fx0 = floorf(sx);
+    const int x0 = static_cast<int>(fx0);
+    const float w1 = sx - fx0, w0 = 1.0f - w1;
+    const int rel = x0 - j_lo;
+    const int start = (i == 1 && narrow) ? e[0] : min(max(rel, 0) & ~1, max(pitch - 4, 0));
+    e[i] = start;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int col = j_lo + start + k;
+      float w = 0.0f;
+      if (col >= 0 && col < W) {
+        if (col == x0) w = w0;
+        else if (col == x0 + 1) w = w1;
+      }
+      wgt[i][k] = w;
+    }
+  }
+
+  int ra = r0;
+  while (ra < r_end) {  // chunks of rows whose source rows fit the staging buffer (CTA-uniform control flow)
+    // rows of the chunk: [ra, rb); source rows [y_lo, y_hi] clipped to the frame
+    const int ya0 = static_cast<int>(floorf(sample_y(ra)));
+    int rb = ra + 1;
+    int y_last = ya0;
+    if (max_rows >= 2) {
+      // sy grows with the row: extend the chunk while its last source row still fits
+      while (rb < r_end) {
+        const int yn = static_cast<int>(floorf(sample_y(rb)));
+        if (min(yn + 1, H - 1) - max(ya0, 0) + 1 > max_rows) break;
+        y_last = yn;
+        ++rb;
+      }
+    }
+    const int y_lo = min(max(ya0, 0), H - 1), y_hi = min(max(y_last + 1, 0), H - 1);
+    const bool rows_out = (y_last + 1 < 0) || (ya0 >= H);  // every tap row of the chunk is outside the frame
+    const bool constant = rows_out || span <= 0 || max_rows < 2;
+    const bool fits = max_rows >= 2 || rows_out || span <= 0;
+    const int n_rows = y_hi - y_lo + 1;
+
+    if (!constant) {
+      // ---- stage: n_rows x 3 lines of `pitch` floats (tail zero-filled) --------------------------------------
+      const int npairs = pitch >> 1;
+      const int lane = tid & 31, warp = tid >> 5;
+      for (int line_id = warp; line_id < n_rows * 3; line_id += TILE_THREADS / 32) {  // one (row, channel) line per warp pass
+        const int yr = line_id / 3, c = line_id - yr * 3;
+        const TS* row = src + c * plane + static_cast<long long>(y_lo + yr) * W + j_lo;
+        float* line = stage + line_id * pitch;
+#pragma unroll 4
+        for (int jp = lane; jp < npairs; jp += 32) {  // independent loads: the compiler batches four of them per lane
+          const int j = jp << 1;
+          float2 v = make_float2(0.0f, 0.0f);
+          if (j + 1 < span) v = ta.vec2 ? load_px2<TS>(row + j) : make_float2(load_px<TS>(row + j), load_px<TS>(row + j + 1));
+          else if (j < span) v.x = load_px<TS>(row + j);
+          *reinterpret_cast<float2*>(line + j) = v;
+        }
+      }
+    }
+    if (!constant && tid < rb - ra) {  // per-row constants of the chunk, once per CTA
+      const int r = ra + tid;
+      const float sy = sample_y(r);
+      const float fy0 = floorf(sy);
+      const int y0 = static_cast<int>(fy0);
+      const float w1 = sy - fy0;
+      RowInfo ri;
+      ri.y0 = y0;
+      ri.pad = 0;
+      ri.wy0 = (y0 >= 0 && y0 < H) ? 1.0f - w1 : 0.0f;
+      ri.wy1 = (y0 + 1 >= 0 && y0 + 1 < H) ? w1 : 0.0f;
+      ri.ia = (min(max(y0, y_lo), y_hi) - y_lo) * 3 * pitch;
+      ri.ib = (min(max(y0 + 1, y_lo), y_hi) - y_lo) * 3 * pitch;
+      ri.o = out_offset(r - r0) - obase;
+      s_rows[tid] = ri;
+    }
+    __syncthreads();
+
+    if (worker) {
+      const int per = (rb - ra + groups - 1) / groups;
+      const int my_a = ra + pg * per, my_b = min(my_a + per, rb);
+      if (!fits) {  // frame too wide for even two staged rows: direct gather for this chunk
+        for (int r = my_a; r < my_b; ++r) {
+          const float sy = sample_y(r);
+          const long long o = out_offset(r - r0);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float v0 = direct_sample<TS>(src + c * plane, sample_x(ox), sy, H, W);
+            const float v1 = direct_sample<TS>(src + c * plane, sample_x(ox + 1), sy, H, W);
+            store2(out + o + c * ch_stride, (v0 - a.mean[c]) * a.inv_std[c], (v1 - a.mean[c]) * a.inv_std[c]);
+          }
+        }
+      } else if (constant) {
+        for (int r = my_a; r < my_b; ++r) {
+          const long long o = out_offset(r - r0);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) store2(out + o + c * ch_stride, (0.0f - a.mean[c]) * a.inv_std[c], (0.0f - a.mean[c]) * a.inv_std[c]);
+        }
+      } else {
+        // ---- compute: walk down the rows, the two source rows of the previous output row stay in registers ----
+        const long long col_off = obase;  // (row / patch-row part comes from RowInfo.o, measured from the strip's first row)
+        if (narrow) {
+          strip_rows<true, TD>(stage, s_rows, my_a - ra, my_b - ra, pitch, e[0], wgt[0], wgt[1], col_off, ch_stride, a.mean, a.inv_std, out);
+        } else {  // > 1 source column per output column: each pixel has its own window; one pass per pixel, scalar stores
+          strip_rows<false, TD>(stage, s_rows, my_a - ra, my_b - ra, pitch, e[0], wgt[0], wgt[0], col_off, ch_stride, a.mean, a.inv_std, out);
+          strip_rows<false, TD>(stage, s_rows, my_a - ra, my_b - ra, pitch, e[1], wgt[1], wgt[1], col_off + 1, ch_stride, a.mean, a.inv_std, out);
+        }
+      }
+    }
+    __syncthreads();  // the staging buffer is reused by the next chunk
+    ra = rb;
   }
 }
 
@@ -362,29 +512,18 @@ template <typename TS, typename TD>
 static int launch_tiled(const RfFovCropParams* p, const Args& a, cudaStream_t s) {
   TiledArgs ta;
   ta.a = a;
-  ta.pitch = (p->W + 2 + 1) & ~1;
   ta.vec2 = (p->W % 2 == 0) && (reinterpret_cast<uintptr_t>(p->frames) % (2 * sizeof(TS)) == 0);
-  // 8 output rows per tile while the staging lines stay small (more outputs per thread for the same tap setup); wide frames
-  // (DR(eye)VE 768, full-resolution 1088) use 4 rows to keep several tiles resident per SM
-  if (p->W <= 512) {
-    const size_t smem = sizeof(float) * 3 * 8 * ta.pitch;
-    RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(fov_crop_tiled_kernel<TS, TD, 8>), smem));
-    fov_crop_tiled_kernel<TS, TD, 8><<<dim3(ceil_div(p->out_size, 8), p->n_frames), TILE_THREADS, smem, s>>>(ta);
-  } else {
-    const size_t smem = sizeof(float) * 3 * 4 * ta.pitch;
-    RF_CHECK_ARG(smem <= 200 * 1024, "rf_fov_crop: frames of width %d need %zu B of staging memory", p->W, smem);
-    RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(fov_crop_tiled_kernel<TS, TD, 4>), smem));
-    fov_crop_tiled_kernel<TS, TD, 4><<<dim3(ceil_div(p->out_size, 4), p->n_frames), TILE_THREADS, smem, s>>>(ta);
-  }
+  const size_t smem = sizeof(float) * STAGE_FLOATS;
+  RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(fov_crop_tiled_kernel<TS, TD>), smem));
+  fov_crop_tiled_kernel<TS, TD><<<dim3(ceil_div(p->out_size, STRIP_ROWS), p->n_frames), TILE_THREADS, smem, s>>>(ta);
   RF_LAUNCH_OK();
   return RF_OK;
 }
 
 template <typename TS>
 static int dispatch_out(const RfFovCropParams* p, const Args& a, cudaStream_t s) {
-  // tiled kernel: 2 px per thread -> even S with at least one pair row per CTA; a patch no shorter than a tile (one patch-row
-  // crossing per tile at most)
-  if (tiled_enabled() && p->out_size >= 8 && (p->patch == 0 || p->patch >= 8)) {
+  // strip kernel: 2 px per thread -> even S, at most 256 threads per output row
+  if (tiled_enabled() && p->out_size >= 8 && p->out_size <= 2 * TILE_THREADS) {
     if (p->out_dtype == RF_F32) return launch_tiled<TS, float>(p, a, s);
     if (p->out_dtype == RF_F16) return launch_tiled<TS, __half>(p, a, s);
     return launch_tiled<TS, __nv_bfloat16>(p, a, s);
