@@ -42,7 +42,8 @@ def _digest(paths) -> str:
 
 def build(force: bool = False, verbose: bool = True) -> str:
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    headers = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "routeformer_b200.h")]
+    headers = (sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(CSRC, "*.inc"))) +
+               [os.path.join(HERE, "..", "include", "routeformer_b200.h")])
     os.makedirs(os.path.join(OUT_DIR, "obj"), exist_ok=True)
     stamp = os.path.join(OUT_DIR, "build.sha256")
     digest = _digest(sources + headers)
