@@ -212,11 +212,15 @@ def run_train(args):
         sampler.start()
     launches0 = ops.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile:
+        torch.cuda.nvtx.range_push("timed_step")  # ncu --nvtx --nvtx-include "timed_step/" captures exactly the timed launches
     e0.record()
     for _ in range(args.steps):
         loss = trainer.step(batch, targets)
     e1.record()
     barrier()
+    if args.profile:
+        torch.cuda.nvtx.range_pop()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = (ops.launch_count - launches0) // max(args.steps, 1) + trainer.graph_launches
     clocks = sampler.stop() if sampler else None

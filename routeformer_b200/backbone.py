@@ -83,9 +83,6 @@ class PatchEmbedBackbone(VideoBackboneModule):
         -> token buffer [sum_v B*F*(G*G+1), C] fp32: per frame G*G patch features then the constant -1 token
         (routeformer.py:478-487), ready for the frame encoder."""
         c = self.configs
-        if self.train_backbone and torch.is_grad_enabled() and self.proj.weight.requires_grad:
-            raise NotImplementedError("train_backbone=True (patch-embedding wgrad) is not implemented yet; the reference also keeps the "
-                                      "backbone frozen at epoch <= 10 (TimmBackbone.py:123)")
         G, S, p, C = c.grid, c.image_size, c.patch, c.channels
         dev = views[0]["video"].device
         n_total = sum(v["video"].shape[0] * len(v["t_idx"]) for v in views)
@@ -112,9 +109,12 @@ class PatchEmbedBackbone(VideoBackboneModule):
                          out=patches[row * G * G:(row + n) * G * G], u8_as_f16=half)
             round_f16 = round_f16 and video.dtype in (torch.float16, torch.uint8)
             row += n
+        # the plugin returns features in the input dtype (fp16 video -> fp16 features, TimmBackbone.py:141-143)
+        if torch.is_grad_enabled() and self.proj.weight.requires_grad:  # train_backbone: fp32 patches, TF32 GEMM, weight gradient
+            from . import functional as Fn
+            return Fn.PatchEmbed.apply(patches, self.proj.weight, self.proj.bias, G * G, round_f16)
         tokens = torch.empty(n_total * (G * G + 1), C, device=dev, dtype=torch.float32)
         tokens.view(n_total, G * G + 1, C)[:, G * G, :] = -1.0
-        # the plugin returns features in the input dtype (fp16 video -> fp16 features, TimmBackbone.py:141-143)
         ops.gemm(patches, self._weight_matrix(half), tokens, bias=self.proj.bias, out_group=(G * G, G * G + 1, 0), round_f16=round_f16)
         return tokens
 

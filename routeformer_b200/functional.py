@@ -428,6 +428,39 @@ class CircularConv3(Function):
         return dx, None, None, None, None, None, None, None
 
 
+class PatchEmbed(Function):
+    """tokens[n*(GG+1), C] = patch rows (GG per frame) x W^T + b, plus the constant -1 token row per frame -- with a gradient for
+    the projection (train_backbone: the reference un-freezes its backbone after epoch 10, TimmBackbone.py:123).
+    The patches (the FoV-crop output) carry no gradient: the crop has no trainable input."""
+
+    @staticmethod
+    def forward(ctx, patches, w, b, GG, round_f16):
+        C = w.shape[0]
+        n = patches.shape[0] // GG
+        tokens = torch.empty(n * (GG + 1), C, device=patches.device, dtype=torch.float32)
+        tokens.view(n, GG + 1, C)[:, GG, :] = -1.0
+        ops.gemm(patches, w.view(C, -1), tokens, bias=b, out_group=(GG, GG + 1, 0), round_f16=round_f16)
+        ctx.dims = (n, GG, C)
+        ctx.params = (w, b)
+        ctx.save_for_backward(patches)
+        return tokens
+
+    @staticmethod
+    def backward(ctx, dtokens):
+        (patches,) = ctx.saved_tensors
+        n, GG, C = ctx.dims
+        w, b = ctx.params
+        # gradient rows of the patch tokens only (the -1 token is a constant); the fp16 rounding of the features is a straight-through
+        dy = dtokens.view(n, GG + 1, C)[:, :GG, :].reshape(n * GG, C)
+        g = grad_buffer(w)
+        if g is not None:
+            wgrad(dy, patches, g.view(C, -1))
+        gb = grad_buffer(b)
+        if gb is not None:
+            ops.colsum_accumulate(dy, gb)
+        return None, None, None, None, None
+
+
 class DistilTail(Function):
     """BatchNorm1d (batch statistics when training; running statistics updated in place) -> ELU -> MaxPool1d(3,2,1)."""
 

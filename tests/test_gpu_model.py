@@ -298,6 +298,46 @@ def test_train_step_raw_against_reference(name):
             assert torch.allclose(new_sd[k].cpu(), v, atol=1e-5, rtol=1e-4), k
 
 
+def test_train_backbone_gradients():
+    """train_backbone (the reference un-freezes its visual backbone after epoch 10, TimmBackbone.py:123): the patch-embedding
+    projection receives its weight / bias gradient through the wgrad GEMM.  Against the reference's own training-step golden
+    (whose backbone stub is trainable), precise mode with the reference's selections forced."""
+    import routeformer_b200 as R
+    from routeformer_b200 import ops
+
+    gold = load_golden("full_small_train")
+    cfg, spec, sd, batch = case_from_golden(gold)
+    t_wp, t_dense = targets_for(cfg, gold["B"], gold["dseed"] + 1000)
+    orc_raw = O.Routeformer({k: v.clone() for k, v in sd.items()}, cfg, spec)
+    torch.manual_seed(12345)
+    with torch.no_grad():
+        orc_raw.forward(batch, training=True)
+    model = build_product(cfg, spec)
+    model.video_backbone.proj.requires_grad_(True)
+    model = model.to(DEV).train()
+    model.load_state_dict(sd)
+    model.forced_tops = tops_for_product(orc_raw.tops, ["right", "left", "front"])
+    lossf = R.FutureDiscountedLoss({0: 0.97}, epsilon=1.0, loss_function="smooth_l1")
+    torch.manual_seed(12345)
+    with ops.precise(True):
+        wp, dense = model(to_device(batch, DEV))
+        loss = lossf(wp, t_wp.to(DEV)) + 0.5 * lossf(dense, t_dense.to(DEV))
+        loss.backward()
+    torch.cuda.synchronize()
+    model.forced_tops = None
+    # with a trainable backbone the fp16 clips take the TF32 patch GEMM instead of the fp16 one: same loss to TF32 accuracy
+    assert abs(loss.item() - gold["loss"]) < 1e-3 * abs(gold["loss"])
+    gw, gb = model.video_backbone.proj.weight.grad, model.video_backbone.proj.bias.grad
+    assert gw is not None and gb is not None
+    nw, nb = gold["grad_norm"]["video_backbone.proj.weight"], gold["grad_norm"]["video_backbone.proj.bias"]
+    e_w, e_b = abs(gw.norm().item() - nw) / nw, abs(gb.norm().item() - nb) / nb
+    e_full = rel_err(gb.cpu(), gold["grad_small"]["video_backbone.proj.bias"])
+    log_parity(f"train_backbone: patch-embedding gradient norms vs reference: weight rel err {e_w:.2e}, bias {e_b:.2e}; bias tensor rel err {e_full:.2e}")
+    assert e_w < 2e-2 and e_b < 2e-2 and e_full < 5e-2
+    # every other gradient is still there
+    assert all(p.grad is not None for n, p in model.named_parameters() if p.requires_grad)
+
+
 def test_two_shard_data_parallel_equivalence():
     """the global batch split over two ranks (contiguous shards, identical weights, identical CPU draws, per-shard
     BatchNorm statistics), gradients summed and scaled by 1/world == the oracle's per-shard autograd averaged the same way.

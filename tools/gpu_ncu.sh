@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 CMD="python bench.py --profile --steps 1 --no-graph"
 $CMD > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1000 -c 1300 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+ncu --nvtx --nvtx-include "timed_step/" --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"
 $CMD > gpurun_out/plain2.log 2>&1 && \
 ncu --set full --clock-control none -k regex:"gemm_tf32_persistent" -s 340 -c 20 -f -o /tmp/prof_gemm $CMD > gpurun_out/ncu_full_gemm.log 2>&1
