@@ -240,19 +240,22 @@ def prob_attention(
 # come from a caller-installed hook `fn(x, where) -> dropped x` (tests replay the CUDA path's Philox masks through it); without a
 # hook dropout is the identity, i.e. the parity configuration feature_dropout = 0.
 _DROPOUT_HOOK: Optional[Callable] = None
+_DROPOUT_INFORMER = False  # hook also applied at the Informer's dropout sites (GPSBackboneConfig.dropout > 0; paper config: 0.0)
 
 
 class dropout_hook:
-    def __init__(self, fn: Optional[Callable]):
-        self.fn = fn
+    def __init__(self, fn: Optional[Callable], informer: bool = False):
+        self.fn, self.informer = fn, informer
 
     def __enter__(self):
-        global _DROPOUT_HOOK
+        global _DROPOUT_HOOK, _DROPOUT_INFORMER
         self.prev, _DROPOUT_HOOK = _DROPOUT_HOOK, self.fn
+        self.prev_inf, _DROPOUT_INFORMER = _DROPOUT_INFORMER, self.informer
 
     def __exit__(self, *exc):
-        global _DROPOUT_HOOK
+        global _DROPOUT_HOOK, _DROPOUT_INFORMER
         _DROPOUT_HOOK = self.prev
+        _DROPOUT_INFORMER = self.prev_inf
 
 
 def _drop(x: Tensor, where: str, perceive: bool = True) -> Tensor:
@@ -329,7 +332,7 @@ def ffn(sd: SD, p: str, x: Tensor, act: str, perceive: bool = False) -> Tensor:
 
 def encoder_layer(sd, p, x, n_heads, factor, act, draw, informer_layout, tops=None) -> Tensor:
     """Post-norm encoder block (cross_modal_transformer.py:288-301; TransformerEncoderDecoder.py:43-53)."""
-    perceive = not informer_layout
+    perceive = (not informer_layout) or _DROPOUT_INFORMER  # TransformerEncoderDecoder.py:46-50 has the same three dropout sites
     a = attention_layer(sd, p + ".attention", x, x, n_heads, "prob", factor, draw, informer_layout, tops)
     x = _ln(sd, p + ".norm1", x + _drop(a, p + ".attention.out", perceive))
     return _ln(sd, p + ".norm2", x + ffn(sd, p, x, act, perceive))
@@ -337,7 +340,7 @@ def encoder_layer(sd, p, x, n_heads, factor, act, draw, informer_layout, tops=No
 
 def decoder_layer(sd, p, x, cross, n_heads, factor, act, draw, informer_layout, cross_kind, tops=None) -> Tensor:
     """Decoder block (cross_modal_transformer.py:223-233; TransformerEncoderDecoder.py:104-116)."""
-    perceive = not informer_layout
+    perceive = (not informer_layout) or _DROPOUT_INFORMER  # TransformerEncoderDecoder.py:106-113
     a = attention_layer(sd, p + ".self_attention", x, x, n_heads, "prob_masked", factor, draw, informer_layout, tops)
     x = _ln(sd, p + ".norm1", x + _drop(a, p + ".self_attention.out", perceive))
     c = attention_layer(sd, p + ".cross_attention", x, cross, n_heads, cross_kind, factor, draw, informer_layout, tops)
@@ -406,7 +409,7 @@ def informer_embedding(sd: SD, p: str, x: Tensor) -> Tensor:
     h = circular_conv3(x, sd[p + ".value_embedding.tokenConv.weight"], None, 1)
     h = h + F.linear(t, sd[p + ".temporal_embedding.embed.weight"])
     pe = sd[p + ".position_embedding.pe"][0, :L] if (p + ".position_embedding.pe") in sd else pe_table(L, D)
-    return h + pe
+    return _drop(h + pe, p + ".dropout", _DROPOUT_INFORMER)  # Embedding.py:126
 
 
 def informer(sd: SD, p: str, x: Tensor, cfg: OracleConfig, draw, training: bool = False,

@@ -428,6 +428,22 @@ class CircularConv3(Function):
         return dx, None, None, None, None, None, None, None
 
 
+class Dropout(Function):
+    """nn.Dropout in training mode on a 2-D view (Informer DataEmbedding, Embedding.py:122-126): stateless Philox mask keyed by
+    the site triple (seed, offset, device step base); the backward pass regenerates the same mask."""
+
+    @staticmethod
+    def forward(ctx, x, p, site):
+        ctx.cfg = (p, site)
+        return ops.dropout(x, torch.empty_like(x), p, *site)
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, site = ctx.cfg
+        dy = dy.contiguous()
+        return ops.dropout(dy, torch.empty_like(dy), p, *site), None, None
+
+
 class PatchEmbed(Function):
     """tokens[n*(GG+1), C] = patch rows (GG per frame) x W^T + b, plus the constant -1 token row per frame -- with a gradient for
     the projection (train_backbone: the reference un-freezes its backbone after epoch 10, TimmBackbone.py:123).

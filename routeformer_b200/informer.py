@@ -14,7 +14,7 @@ import torch.nn.functional as tF
 
 from . import functional as Fn
 from .layers import (AttentionLayer, Decoder, DecoderLayer, Encoder, EncoderLayer, LiveIndexSource, PositionalEmbedding,
-                     TokenEmbedding, _no_dropout)
+                     TokenEmbedding, _site)
 
 
 class TimeFeatureEmbedding(nn.Module):
@@ -38,10 +38,12 @@ class DataEmbedding(nn.Module):
         self.temporal_embedding = TimeFeatureEmbedding(d_model, freq)
         self.p_drop = dropout
 
-    def embed(self, x2, n, L):
-        _no_dropout(self, self.p_drop)
-        return Fn.CircularConv3.apply(x2, self.value_embedding.tokenConv.weight, None, self.position_embedding.table(),
-                                      self.temporal_embedding.embed.weight, n, L, 1)
+    def embed(self, x2, n, L, name=""):
+        h = Fn.CircularConv3.apply(x2, self.value_embedding.tokenConv.weight, None, self.position_embedding.table(),
+                                   self.temporal_embedding.embed.weight, n, L, 1)
+        if self.training and self.p_drop > 0.0:  # Embedding.py:126
+            h = Fn.Dropout.apply(h, self.p_drop, _site(h.device, self.p_drop, name + ".dropout", h.shape[0], h.shape[1]))
+        return h
 
 
 class ConvLayer(nn.Module):
@@ -94,7 +96,7 @@ class Informer(nn.Module):
         B, T, ld = x_pad.shape
         P = self.pred_len
         x_dec = Fn.DecoderInput.apply(x_pad, P, self.smart_decoder)
-        h = self.enc_embedding.embed(x_pad.view(B * T, ld), B, T)
+        h = self.enc_embedding.embed(x_pad.view(B * T, ld), B, T, f"{name}.enc_embedding")
         L = T
         n_layers = len(self.encoder.attn_layers)
         for i, layer in enumerate(self.encoder.attn_layers):
@@ -102,7 +104,7 @@ class Informer(nn.Module):
             if self.encoder.conv_layers is not None and i < n_layers - 1:
                 h, L = self.encoder.conv_layers[i].run(h, B, L)
         enc = Fn.LayerNorm.apply(h, self.encoder.norm.weight, self.encoder.norm.bias)
-        d = self.dec_embedding.embed(x_dec.view(B * (T + P), ld), B, T + P)
+        d = self.dec_embedding.embed(x_dec.view(B * (T + P), ld), B, T + P, f"{name}.dec_embedding")
         for i, layer in enumerate(self.decoder.layers):
             d = layer.run(d, enc, B, T + P, L, draw, record, f"{name}.decoder.layers.{i}")
         d = d.view(B, T + P, -1)[:, T:, :].reshape(B * P, -1)  # only the last P rows are projected / returned (Informer.py:164-167)

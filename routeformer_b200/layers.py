@@ -75,13 +75,6 @@ class PlannedIndexSource:
         return t
 
 
-def _no_dropout(module: nn.Module, p: float):
-    if p > 0.0 and module.training:
-        raise NotImplementedError(
-            "dropout > 0 in training mode is implemented for the Perceive encoder / decoder (feature_dropout) only; the Informer of "
-            "the Routeformer path is configured with dropout = 0.0 (full_comparison.py:171)")
-
-
 def _site(device, p: float, where: str, rows: int, cols: int):
     """One dropout call site of this step: (seed, offset) of its Philox sub-stream."""
     return ops.DropoutStream.next(device, where, rows, cols)
@@ -174,8 +167,6 @@ class EncoderLayer(nn.Module):
 
     def run(self, x2, B, L, draw, record=None, name="", tail: bool = False):
         """tail=True (last layer of an encoder whose caller keeps only the last token): returns [B, D] instead of [B*L, D]."""
-        if self.attention.informer_layout:
-            _no_dropout(self, self.p_drop)
         p = self.p_drop if self.training else 0.0
         x2 = self.attention.block(x2, None, B, L, L, draw, record, name + ".attention", p, tail=tail and p == 0.0)
         x2 = Fn.LayerNorm.apply(x2, self.norm1.weight, self.norm1.bias)
@@ -201,8 +192,6 @@ class DecoderLayer(nn.Module):
     _ffn_drop = EncoderLayer._ffn_drop
 
     def run(self, x2, cross2, B, L, S, draw, record=None, name=""):
-        if self.self_attention.informer_layout:
-            _no_dropout(self, self.p_drop)
         p = self.p_drop if self.training else 0.0
         x2 = self.self_attention.block(x2, None, B, L, L, draw, record, name + ".self_attention", p)
         x2 = Fn.LayerNorm.apply(x2, self.norm1.weight, self.norm1.bias)

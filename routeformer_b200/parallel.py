@@ -293,7 +293,7 @@ class DataParallelTrainer:
         graph, loss, launches = self._graphs[(pattern, self.graph_tag)]
         self.graph_launches = launches
         graph.replay()
-        if m.training and m.feature_dropout > 0.0:
+        if m.training and getattr(m, "uses_dropout", False):
             ops.DropoutStream.note_replay(self.arena.device)
         self._replayed = torch.cuda.Event()
         self._replayed.record()

@@ -109,6 +109,12 @@ class Routeformer(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
+    @property
+    def uses_dropout(self) -> bool:
+        """Element-wise dropout anywhere on the path (Perceive feature dropout, GPS-backbone dropout)."""
+        gb = float(getattr(self.configs.gps_backbone_config, "dropout", 0.0) or 0.0)
+        return self.feature_dropout > 0.0 or gb > 0.0
+
     # ------------------------------------------------------------------------------------------
     # host staging
     # ------------------------------------------------------------------------------------------
@@ -529,7 +535,7 @@ class Routeformer(nn.Module):
 
     def forward(self, batch, target_batch=None):
         c = self.configs
-        if self.training and self.feature_dropout > 0.0:
+        if self.training and self.uses_dropout:
             ops.DropoutStream.begin_step(batch["gps"].device)  # fresh Philox sub-streams for this step's dropout sites
         if self._pending_plan is None:
             self.prepare_draws(batch)

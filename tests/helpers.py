@@ -31,12 +31,12 @@ def rel_err(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
 
 
-def build_product(cfg, spec, fov="frame", **overrides):
+def build_product(cfg, spec, fov="frame", informer_dropout: float = 0.0, **overrides):
     """routeformer_b200.Routeformer for an OracleConfig / BackboneSpec pair."""
     import routeformer_b200 as R
 
     g = R.GPSBackboneConfig(seq_len=cfg.seq_len, label_len=cfg.seq_len, pred_len=cfg.pred_len, factor=cfg.factor, distil=cfg.distil,
-                            dropout=0.0, activation=cfg.activation, d_model=cfg.d_model, n_heads=cfg.n_heads, e_layers=cfg.e_layers,
+                            dropout=informer_dropout, activation=cfg.activation, d_model=cfg.d_model, n_heads=cfg.n_heads, e_layers=cfg.e_layers,
                             d_layers=cfg.d_layers, d_ff=cfg.d_ff)
     vb = None
     if spec is not None:

@@ -709,6 +709,51 @@ def test_training_step_with_feature_dropout():
     assert torch.equal(a, b)
 
 
+def test_informer_dropout():
+    """GPSBackboneConfig.dropout > 0 (the paper configuration uses 0.0, full_comparison.py:170): DataEmbedding dropout and the
+    three dropout sites of every Informer encoder / decoder layer, with the CUDA masks replayed inside the oracle."""
+    import routeformer_b200 as R
+    from routeformer_b200 import ops
+
+    gold = load_golden("full_small_train")
+    cfg, spec, sd, batch = case_from_golden(gold)
+    t_wp, t_dense = targets_for(cfg, gold["B"], gold["dseed"] + 1000)
+    p = 0.15
+    model = build_product(cfg, spec, informer_dropout=p).to(DEV).train()
+    model.load_state_dict(sd)
+    model.record_tops = []
+    ops.DropoutStream.log = []
+    try:
+        lossf = R.FutureDiscountedLoss({0: 0.97}, epsilon=1.0, loss_function="smooth_l1")
+        torch.manual_seed(12345)
+        wp, dense = model(to_device(batch, DEV))
+        loss = lossf(wp, t_wp.to(DEV)) + 0.5 * lossf(dense, t_dense.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+        log = list(ops.DropoutStream.log)
+    finally:
+        ops.DropoutStream.log = None
+    # 2 embeddings + 3 sites per encoder layer + 5 per decoder layer (self out, cross out, ffn hidden, ffn out; no prob dropout: ProbAttention)
+    assert len(log) == 2 + 3 * cfg.e_layers + 4 * cfg.d_layers, len(log)
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and not k.endswith(".pe") and
+                                          not k.startswith("video_backbone")) for k, v in sd.items()}
+    orc = O.Routeformer(params, cfg, spec)
+    hook = ReplayDropout(log, p)
+    torch.manual_seed(12345)
+    with O.dropout_hook(hook, informer=True):
+        rwp, rdense = orc.forward(batch, training=True, draw=ReplayDraw(tops_for_oracle(model.record_tops, ["right", "left", "front"])))
+    assert hook.exhausted()
+    rloss = O.future_discounted_loss(rwp, t_wp) + 0.5 * O.future_discounted_loss(rdense, t_dense)
+    assert rel_err(wp.detach().cpu(), rwp.detach()) < 1e-3
+    assert abs(loss.item() - rloss.item()) < 2e-3 * abs(rloss.item())
+    assert abs(loss.item() - gold["loss"]) > 1e-4 * abs(gold["loss"])  # dropout changed the result
+    named = dict(model.named_parameters())
+    assert all(named[k].grad is not None and torch.isfinite(named[k].grad).all() for k, v in params.items() if v.requires_grad)
+    rloss.backward()
+    k = "gps_backbone.decoder.projection.weight"
+    assert rel_err(named[k].grad.cpu(), params[k].grad) < 5e-2
+
+
 def test_view_and_gaze_dropout():
     """routeformer.py:300-301,402-410: whole camera views / the gaze stream are dropped by CPU torch.rand draws interleaved with the
     ProbSparse index draws; dropped views contribute zero features (and no frame-encoder work)."""
