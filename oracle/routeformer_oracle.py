@@ -240,26 +240,32 @@ def prob_attention(
 # come from a caller-installed hook `fn(x, where) -> dropped x` (tests replay the CUDA path's Philox masks through it); without a
 # hook dropout is the identity, i.e. the parity configuration feature_dropout = 0.
 _DROPOUT_HOOK: Optional[Callable] = None
-_DROPOUT_INFORMER = False  # hook also applied at the Informer's dropout sites (GPSBackboneConfig.dropout > 0; paper config: 0.0)
+_DROPOUT_INFORMER = False  # hook applied at the Informer's dropout sites (GPSBackboneConfig.dropout > 0; paper config: 0.0)
+_DROPOUT_PERCEIVE = True   # hook applied at the Perceive modules' sites (feature_dropout > 0)
 
 
 class dropout_hook:
-    def __init__(self, fn: Optional[Callable], informer: bool = False):
-        self.fn, self.informer = fn, informer
+    def __init__(self, fn: Optional[Callable], informer: bool = False, perceive: bool = True):
+        self.fn, self.informer, self.perceive = fn, informer, perceive
 
     def __enter__(self):
-        global _DROPOUT_HOOK, _DROPOUT_INFORMER
+        global _DROPOUT_HOOK, _DROPOUT_INFORMER, _DROPOUT_PERCEIVE
         self.prev, _DROPOUT_HOOK = _DROPOUT_HOOK, self.fn
         self.prev_inf, _DROPOUT_INFORMER = _DROPOUT_INFORMER, self.informer
+        self.prev_per, _DROPOUT_PERCEIVE = _DROPOUT_PERCEIVE, self.perceive
 
     def __exit__(self, *exc):
-        global _DROPOUT_HOOK, _DROPOUT_INFORMER
+        global _DROPOUT_HOOK, _DROPOUT_INFORMER, _DROPOUT_PERCEIVE
         _DROPOUT_HOOK = self.prev
         _DROPOUT_INFORMER = self.prev_inf
+        _DROPOUT_PERCEIVE = self.prev_per
 
 
-def _drop(x: Tensor, where: str, perceive: bool = True) -> Tensor:
-    return _DROPOUT_HOOK(x, where) if (_DROPOUT_HOOK is not None and perceive) else x
+def _drop(x: Tensor, where: str, enabled: Optional[bool] = None) -> Tensor:
+    """enabled: None = a Perceive-module site (follows _DROPOUT_PERCEIVE); otherwise the caller's decision."""
+    if enabled is None:
+        enabled = _DROPOUT_PERCEIVE
+    return _DROPOUT_HOOK(x, where) if (_DROPOUT_HOOK is not None and enabled) else x
 
 
 def full_attention(q: Tensor, k: Tensor, v: Tensor, where: Optional[str] = None) -> Tensor:
@@ -332,7 +338,7 @@ def ffn(sd: SD, p: str, x: Tensor, act: str, perceive: bool = False) -> Tensor:
 
 def encoder_layer(sd, p, x, n_heads, factor, act, draw, informer_layout, tops=None) -> Tensor:
     """Post-norm encoder block (cross_modal_transformer.py:288-301; TransformerEncoderDecoder.py:43-53)."""
-    perceive = (not informer_layout) or _DROPOUT_INFORMER  # TransformerEncoderDecoder.py:46-50 has the same three dropout sites
+    perceive = _DROPOUT_INFORMER if informer_layout else _DROPOUT_PERCEIVE  # TransformerEncoderDecoder.py:46-50: same three sites
     a = attention_layer(sd, p + ".attention", x, x, n_heads, "prob", factor, draw, informer_layout, tops)
     x = _ln(sd, p + ".norm1", x + _drop(a, p + ".attention.out", perceive))
     return _ln(sd, p + ".norm2", x + ffn(sd, p, x, act, perceive))
@@ -340,7 +346,7 @@ def encoder_layer(sd, p, x, n_heads, factor, act, draw, informer_layout, tops=No
 
 def decoder_layer(sd, p, x, cross, n_heads, factor, act, draw, informer_layout, cross_kind, tops=None) -> Tensor:
     """Decoder block (cross_modal_transformer.py:223-233; TransformerEncoderDecoder.py:104-116)."""
-    perceive = (not informer_layout) or _DROPOUT_INFORMER  # TransformerEncoderDecoder.py:106-113
+    perceive = _DROPOUT_INFORMER if informer_layout else _DROPOUT_PERCEIVE  # TransformerEncoderDecoder.py:106-113
     a = attention_layer(sd, p + ".self_attention", x, x, n_heads, "prob_masked", factor, draw, informer_layout, tops)
     x = _ln(sd, p + ".norm1", x + _drop(a, p + ".self_attention.out", perceive))
     c = attention_layer(sd, p + ".cross_attention", x, cross, n_heads, cross_kind, factor, draw, informer_layout, tops)

@@ -740,7 +740,7 @@ def test_informer_dropout():
     orc = O.Routeformer(params, cfg, spec)
     hook = ReplayDropout(log, p)
     torch.manual_seed(12345)
-    with O.dropout_hook(hook, informer=True):
+    with O.dropout_hook(hook, informer=True, perceive=False):
         rwp, rdense = orc.forward(batch, training=True, draw=ReplayDraw(tops_for_oracle(model.record_tops, ["right", "left", "front"])))
     assert hook.exhausted()
     rloss = O.future_discounted_loss(rwp, t_wp) + 0.5 * O.future_discounted_loss(rdense, t_dense)
