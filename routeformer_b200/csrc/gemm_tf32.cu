@@ -536,18 +536,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // boundaries over a 3-stage ring; warp 1 = MMA issuer ping-ponging between two TMEM accumulators; warps 2-9 = epilogue
 // (TMEM -> registers -> math -> swizzled smem -> TMA store / reduce-add).  The epilogue of tile j overlaps the operand loads
 // and MMAs of tiles j+1, j+2: for the K=128 layers of the frame encoder (4 k-blocks per tile) the loads never drain.
-constexpr int P_STAGES = 3;
+// Ring depth / staging layout (template parameters of the kernel):
+//   launches that also write the pre-activation output (FFN1 forward: gelu'(x)) stage (out, preact) pairs of 2 x 16 KiB and run
+//   a 3-stage operand ring; every other launch can stage 16 KiB out chunks only, which frees 64 KiB for a 5-stage ring
+//   (RF_GEMM_DEEP_RING=1; measured neutral, see the launch code).
+constexpr int P_STAGES_PREACT = 3;
+constexpr int P_STAGES_PLAIN = 5;
 constexpr int P_EPI_WARPS = 8;         // two warps per TMEM lane quarter: each takes one half of the tile's columns
 constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS + 32;  // + one warp that sums the A tiles column-wise (bias gradients)
 constexpr int P_REDUCER_WARP = 2 + P_EPI_WARPS;
-constexpr int EPI_PAIR_BYTES = 32768;  // one (out, preact) staging pair of 2 x 16 KiB; 2 pairs per column half
 
-template <int BLOCK_N>
+template <int BLOCK_N, int STAGES, int PAIR_BYTES>
 struct PTile {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int RING_BYTES = P_STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = RING_BYTES + 4 * EPI_PAIR_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = RING_BYTES + 4 * PAIR_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
 };
 
@@ -556,12 +560,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void epi_bar_sync(int half) { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int STAGES, int PAIR_BYTES>
 __global__ void __launch_bounds__(P_THREADS, 1)  // registers are granted per 4 warps: 352 threads count as 384 -> 168 per thread
 gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const Args a,
                             const int tiles_n, const int tiles_m, const int splits) {
-  using T = PTile<BLOCK_N>;
+  using T = PTile<BLOCK_N, STAGES, PAIR_BYTES>;
+  constexpr int P_STAGES = STAGES;
+  constexpr int EPI_PAIR_BYTES = PAIR_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* epi = smem + T::RING_BYTES;
@@ -897,13 +903,24 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
   // loads run ahead across tiles.  Long reductions are L2-bandwidth-bound -> two co-resident tile-wise CTAs per SM keep more
   // bytes in flight (2 x 3 stages) and measured 25-35 % faster there (profiles/r1_microbench_gemm_*).
   if (persistent && args.kb_per_split <= 12 && !f16) {
-    using PT = PTile<BLOCK_N>;
-    RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_tf32_persistent_kernel<BLOCK_N>), PT::SMEM_BYTES));
     const long long total = static_cast<long long>(tiles_n) * tiles_m * splits;
     RF_CHECK_ARG(total <= 2147483647LL, "rf_gemm_tf32: too many tiles");
     const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
-    RF_CUDA_OK(launch_pdl(gemm_tf32_persistent_kernel<BLOCK_N>, dim3(grid), dim3(P_THREADS), PT::SMEM_BYTES, stream, tmA, tmB, tmC, tmP, args, tiles_n,
-                          tiles_m, splits));
+    // RF_GEMM_DEEP_RING=1: opt-in.  Measured A/B on the training step (profiles/r2_gemm_deep_ring_ab.txt): 19.90 vs 19.98 ms per
+    // step, roofline fraction of the HBM-bound launches 0.527 vs 0.529 -- the bytes in flight of the operand ring are NOT what
+    // bounds these launches, so the round-1 configuration stays the default.
+    static const bool deep_ring = [] { const char* e = getenv("RF_GEMM_DEEP_RING"); return e && e[0] == '1'; }();
+    if (p->preact || !deep_ring || !args.tma_store) {
+      using PT = PTile<BLOCK_N, P_STAGES_PREACT, 32768>;
+      auto kernel = gemm_tf32_persistent_kernel<BLOCK_N, P_STAGES_PREACT, 32768>;
+      RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), PT::SMEM_BYTES));
+      RF_CUDA_OK(launch_pdl(kernel, dim3(grid), dim3(P_THREADS), PT::SMEM_BYTES, stream, tmA, tmB, tmC, tmP, args, tiles_n, tiles_m, splits));
+    } else {
+      using PT = PTile<BLOCK_N, P_STAGES_PLAIN, 16384>;
+      auto kernel = gemm_tf32_persistent_kernel<BLOCK_N, P_STAGES_PLAIN, 16384>;
+      RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), PT::SMEM_BYTES));
+      RF_CUDA_OK(launch_pdl(kernel, dim3(grid), dim3(P_THREADS), PT::SMEM_BYTES, stream, tmA, tmB, tmC, tmP, args, tiles_n, tiles_m, splits));
+    }
     return RF_OK;
   }
   if (args.colsum_a) {  // long reductions: the tile-wise kernels have no reducer warp, the column sums take their own pass
