@@ -213,14 +213,15 @@ def run_train(args):
     launches0 = ops.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if args.profile:
-        torch.cuda.nvtx.range_push("timed_step")  # ncu --nvtx --nvtx-include "timed_step/" captures exactly the timed launches
+        nvtx_range = torch.cuda.nvtx.range_start("timed_step")  # start/end range (process-wide: the backward pass launches from
+        # autograd's own thread); ncu --nvtx --nvtx-include "timed_step" captures exactly the timed launches
     e0.record()
     for _ in range(args.steps):
         loss = trainer.step(batch, targets)
     e1.record()
     barrier()
     if args.profile:
-        torch.cuda.nvtx.range_pop()
+        torch.cuda.nvtx.range_end(nvtx_range)
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = (ops.launch_count - launches0) // max(args.steps, 1) + trainer.graph_launches
     clocks = sampler.stop() if sampler else None
@@ -644,6 +645,73 @@ def run_fwd(args):
     finish(dist, world)
 
 
+def run_eval_step(args):
+    """`_eval_step` (full_comparison.py:654-679) -- torch.manual_seed(12345), five stochastic forwards of one batch,
+    their mean, per-clip loss / ADE / FDE.  `value` = clips/s with the five forwards as one five-fold pass
+    (`Routeformer.forward_samples`); the reference's loop of five forwards (same product kernels) is timed beside it."""
+    import routeformer_b200 as R
+    from routeformer_b200 import ops
+
+    dist, world, rank, local, dev, barrier, max_over_ranks = dist_setup(args)
+    B = args.batch_per_gpu
+    host_batch, host_targets = build_case(B, seed=100 + rank)
+    torch.manual_seed(0)
+    model = build_model(args.fov).to(dev).eval()
+    steps = R.ParallelTrainerSteps(model)
+    pinned = {k: v.contiguous().pin_memory() for k, v in host_batch.items()}
+    batch = {"train": model.stage_batch(pinned, dev), "target": {"gps": host_targets[0].to(dev)}}
+    in_bytes = sum(v.numel() * v.element_size() for v in batch["train"].values())
+
+    def timed(batched, n_steps):
+        steps.batched_samples = batched
+        for _ in range(args.warmup):
+            steps.eval_step(batch)
+        barrier()
+        launches0 = ops.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            out = steps.eval_step(batch)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), (ops.launch_count - launches0) // n_steps, out
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, out = timed(True, args.steps)
+    clocks = sampler.stop() if sampler else None
+    ms_seq, launches_seq, out_seq = timed(False, args.steps)
+    # end to end: pinned host batch -> staged frames -> eval_step -> the three per-clip metric vectors on the host
+    steps.batched_samples = True
+    e2e_steps = max(10, min(args.steps, 20))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        b = {"train": model.stage_batch(pinned, dev, out=batch["train"]), "target": batch["target"]}
+        host_metrics = [t.cpu() for t in steps.eval_step(b)]
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    if rank == 0:
+        agree = max(float((a - b_).abs().max() / b_.abs().max().clamp_min(1e-12)) for a, b_ in zip(out, out_seq))
+        print(json.dumps({
+            "metric": "routeformer_eval_step_clips_per_sec", "mode": "eval_step", "value": round(world * B * args.steps / (ms / 1e3), 2),
+            "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 (fp32 storage, fp32 accumulate; fp16 patch embedding)", "data": "synthetic",
+            "config": {"workload": "SURVEY 8(f) N2: _eval_step, 5 stochastic forwards per batch + per-clip loss/ADE/FDE, paper config, "
+                                   "GEM-shaped clips; a clip counts once (not once per sample)", "batch_per_gpu": B, "samples": steps.n_eval_samples,
+                       "fov": args.fov, "cuda_graph": False, "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB per step per GPU)"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "sequential_loop": {"value": round(world * B * args.steps / (ms_seq / 1e3), 2), "ms_per_step": round(ms_seq / args.steps, 3),
+                                "gpu_launches": int(launches_seq), "max_rel_metric_difference_vs_batched": agree},
+            "e2e": {"value": round(world * B * e2e_steps / (ms_e2e / 1e3), 2), "unit": "clips/s", "h2d_bytes_per_step": int(in_bytes),
+                    "d2h_bytes_per_step": int(sum(t.numel() * 4 for t in host_metrics)), "steps": e2e_steps}}), flush=True)
+    finish(dist, world)
+
+
 def run_dreyeve_sweep(args):
     """BASELINE.json configs[3]: DR(eye)VE-shaped clips (216x768 / 216x384 roof camera, 240x320 eye-tracker camera, two gaze samples
     per frame, rotate_motion), full-modality inference, batch 32...1024; plus the longer-video axis (5 fps: 39 frames per view)."""
@@ -777,9 +845,9 @@ def main():
     ap.add_argument("--no-wgrad-overlap", action="store_true", help="keep the weight-gradient GEMMs on the main stream")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one captured CUDA graph")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up + --steps steps, no e2e / roofline / CPU legs")
-    ap.add_argument("--mode", default="train", choices=["train", "fwd", "dreyeve_sweep", "crop_micro"],
+    ap.add_argument("--mode", default="train", choices=["train", "fwd", "eval_step", "dreyeve_sweep", "crop_micro"],
                     help="train = the headline metric (BASELINE configs[2], default); fwd = configs[1]; dreyeve_sweep = configs[3]; "
-                         "crop_micro = configs[4]")
+                         "crop_micro = configs[4]; eval_step = the _eval_step caller (SURVEY 8(f) N2)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU comparator")
     ap.add_argument("--u8-frames", action="store_true", help="host batch holds raw uint8 frames (half the H2D bytes); converted in the crop kernel")
     ap.add_argument("--paper-dropout", action="store_true", help="train with the paper's dropouts (view 0.6 / gaze 0.2 / feature 0.05)")
@@ -790,6 +858,8 @@ def main():
         args.warmup = 1
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "eval_step":
+        run_eval_step(args)
     elif args.mode == "fwd":
         run_fwd(args)
     elif args.mode == "dreyeve_sweep":

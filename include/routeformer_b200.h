@@ -119,6 +119,9 @@ int rf_gemm_tf32(const RfGemmParams* p, void* stream);
 /* Profiling hook: installs (or clears with NULL) a device buffer of >= 8 u64; CTA (0,0,0) of every later GEMM launch records
  * %globaltimer (ns) at: start, after setup, first operands landed, last MMA issued, accumulator ready, epilogue done, exit. */
 int rf_debug_gemm_stamps(unsigned long long* device_buffer);
+/* Profiling hook: bottleneck probe of the persistent GEMM kernel (bit mask, see gemm_tf32.cu g_probe).  TIMING ONLY: while a bit
+ * is set the kernel skips work and its results are wrong; 0 restores the normal kernel.  tools/gemm_probe.py --stages. */
+int rf_debug_gemm_probe(int mode);
 
 /* ------------------------------------------------------------------------------------------------
  * (3) Circular Conv1d(k=3) assembly.  The conv is computed as ONE GEMM Z = X [W_0;W_1;W_2]^T

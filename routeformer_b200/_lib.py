@@ -131,6 +131,7 @@ SIGNATURES = {
     "rf_adamw_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P, _F, _P],
     "rf_struct_size": [_I],
     "rf_debug_gemm_stamps": [_P],
+    "rf_debug_gemm_probe": [C.c_int],
     "rf_debug_attn_stamps": [_P],
     "rf_stage_frames_h2d": [_P, _P, _I, _I, C.POINTER(C.c_int), _I, _L, _P],
 }

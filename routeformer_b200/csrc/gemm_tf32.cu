@@ -193,6 +193,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // Optional in-kernel timeline (profiling hook): when rf_debug_gemm_stamps() has installed a buffer, CTA (0,0,0) records
 // %globaltimer at its phase boundaries.  One extra global load per CTA otherwise.
 __device__ unsigned long long* g_stamps = nullptr;
+// Bottleneck probe of the persistent kernel (rf_debug_gemm_probe; TIMING ONLY, results are wrong while a bit is set):
+//   1 = the epilogue stages its chunks but issues no bulk store      2 = the epilogue only drains TMEM (no math, no staging, no store)
+//   4 = the B operand is loaded for the first tile of a CTA only      8 = the MMA issuer commits without issuing MMAs
+__device__ int g_probe = 0;
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -580,6 +584,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total = tiles_n * tiles_m * splits;
+  const int probe = g_probe;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmA);
@@ -620,11 +625,12 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         int m0, n0, kb_begin, nkb;
         decode(t, m0, n0, kb_begin, nkb);
+        const bool skip_b = (probe & 4) && t != static_cast<int>(blockIdx.x);
         for (int i = 0; i < nkb; ++i, ++it) {
           const int s = it % P_STAGES;
           const uint32_t ph = (it / P_STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], T::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[s], skip_b ? A_BYTES : T::STAGE_BYTES);
           uint8_t* sa = smem + s * T::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const int k0 = (kb_begin + i) * BLOCK_K;
@@ -634,6 +640,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 #pragma unroll
             for (int g = 0; g < BLOCK_M / 32; ++g) tma_load_2d(sa + g * GROUP_BYTES, &tmA, &full_bar[s], m0 + 32 * g, k0);
           }
+          if (skip_b) continue;
           if (!a.b_mn) {
             tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
           } else {
@@ -671,7 +678,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                                           : make_smem_desc(a_base + kk * UMMA_K * 4, 16, 1024, 2);
             const uint64_t bdesc = a.b_mn ? make_smem_desc(b_base + kk * 1024, GROUP_BYTES, 512, 1)
                                           : make_smem_desc(b_base + kk * UMMA_K * 4, 16, 1024, 2);
-            umma_tf32(tmem_d, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
+            if (!(probe & 8)) umma_tf32(tmem_d, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -773,6 +780,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[ab]);
         }
+        if (probe & 2) continue;
         float v[32], pre[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
@@ -790,7 +798,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           if (a.preact) RowEpilogue::stage_row(pbuf, row_in_tile, pre);
           fence_proxy_async_smem();
           epi_bar_sync(half);
-          if (elected) {
+          if (elected && !(probe & 1)) {
             if (a.accumulate) tma_reduce_add_2d(&tmC, obuf, nb, m0);
             else if (a.group_in > 0) tma_store_3d(&tmC, obuf, nb, 0, m0 / a.group_in);
             else tma_store_2d(&tmC, obuf, nb, m0);
@@ -835,6 +843,16 @@ static bool tf32_round_in_tma() {
   return v == 1;
 }
 
+static CUtensorMapL2promotion l2_promotion() {  // RF_TMA_L2_PROMO=0..3: none / 64 B / 128 B / 256 B (default)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RF_TMA_L2_PROMO");
+    v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
+  }
+  return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+       : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
+
 // fp32 tensor map of rank 2 or 3: dim0 = `inner` contiguous elements (box 32 = 128 B), dim1 = rows of pitch ld (box box_rows),
 // optional dim2 = groups of pitch ld2 (box box_groups).  `round_tf32`: TFLOAT32 type (operands are rounded RN on load).
 static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_rows, bool mn_major,
@@ -854,7 +872,7 @@ static int make_map(CUtensorMap* map, const float* base, long long inner, long l
                                         : ((round_tf32 && tf32_round_in_tma()) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   CUresult r = fn(map, dtype, rank,
                   const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(),
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%lld outer=%lld ld=%lld box_rows=%d groups=%lld", static_cast<int>(r),
@@ -953,6 +971,12 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
 extern "C" int rf_debug_gemm_stamps(unsigned long long* device_buffer) {
   using namespace rf;
   RF_CUDA_OK(cudaMemcpyToSymbol(gemm::g_stamps, &device_buffer, sizeof(device_buffer)));
+  return RF_OK;
+}
+
+extern "C" int rf_debug_gemm_probe(int mode) {
+  using namespace rf;
+  RF_CUDA_OK(cudaMemcpyToSymbol(gemm::g_probe, &mode, sizeof(mode)));
   return RF_OK;
 }
 

@@ -4,7 +4,9 @@
 `preprocess_batch(target, training=False)` for the dense supervision, the two FutureDiscountedLosses and the dense-loss
 re-weighting (`dense_loss_ratio * trajectory_loss / max(dense_loss, 1e-6)`, detached, switched on after epoch 10), plus the
 logged ADE / FDE.  `eval_step` = `_eval_step` (:654-679): `torch.manual_seed(12345)`, five stochastic forwards, their mean,
-then per-clip loss / ADE / FDE -- here ONE kernel (`rf_eval_samples`) instead of a Python loop of 3 x B tiny reductions.
+then per-clip loss / ADE / FDE -- here the five forwards run as ONE five-fold batch with per-sample index tables
+(`Routeformer.forward_samples`: same CPU draws in the same order; the crop / patch embedding / token embedding they share is
+computed once) and the metrics are ONE kernel (`rf_eval_samples`) instead of a Python loop of 3 x B tiny reductions.
 The Lightning plumbing around them (logging, PCI buckets, optimiser config) stays with the caller.
 """
 from __future__ import annotations
@@ -22,6 +24,7 @@ class ParallelTrainerSteps:
         c = model.configs
         self.model = model
         self.n_eval_samples = n_eval_samples
+        self.batched_samples = True  # eval_step: the stochastic forwards as one n-fold batch (False: the reference's loop)
         # full_comparison.py:445-454
         self.trajectory_loss = FutureDiscountedLoss(c.discount_factor, c.epsilon, loss_function="smooth_l1")
         self.dense_loss = FutureDiscountedLoss(c.discount_factor, c.visual_epsilon, loss_function="smooth_l1")
@@ -93,15 +96,19 @@ class ParallelTrainerSteps:
         model = self.model
         torch.manual_seed(12345)
         inp, target_gps = batch["train"], batch["target"]["gps"]
-        preds = []
-        for _ in range(self.n_eval_samples):
-            out = model(inp)
-            preds.append(out[0] if model.configs.dense_prediction else out)
+        if self.batched_samples and hasattr(model, "forward_samples"):
+            preds = model.forward_samples(inp, self.n_eval_samples)[0]  # [n, B, P, 2]: the n forwards as one pass, same draws
+        else:
+            preds = []
+            for _ in range(self.n_eval_samples):
+                out = model(inp)
+                preds.append(out[0] if model.configs.dense_prediction else out)
+            preds = torch.stack(preds)
         loss = self.trajectory_loss
         if loss.current_epoch in loss.discount_factor_dict:
             loss.current_discount_factor = loss.discount_factor_dict[loss.current_epoch]
         eps = 0.0 if loss.epsilon is None else float(loss.epsilon)
-        self.last_mean_prediction, per_clip = ops.eval_samples(torch.stack(preds), target_gps, float(loss.current_discount_factor), eps,
+        self.last_mean_prediction, per_clip = ops.eval_samples(preds.contiguous(), target_gps, float(loss.current_discount_factor), eps,
                                                                loss.loss_function)
         torch.seed()
         return per_clip[:, 0], per_clip[:, 1], per_clip[:, 2]

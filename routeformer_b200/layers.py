@@ -254,10 +254,14 @@ class PerceiveEncoder(nn.Module):
             None, norm_layer=nn.LayerNorm(d_model))
         self.projection = nn.Linear(d_model, out_channels, bias=True)
 
-    def encode(self, x2: torch.Tensor, n: int, L: int, draw, record=None, name="") -> torch.Tensor:
-        """x2 [n*L, Cp] (channel-padded) -> [n*min(L,out_len), out_channels]."""
+    def encode(self, x2: torch.Tensor, n: int, L: int, draw, record=None, name="", samples: int = 1) -> torch.Tensor:
+        """x2 [n*L, Cp] (channel-padded) -> [samples*n*min(L,out_len), out_channels].  samples > 1 (Routeformer.forward_samples):
+        the deterministic token embedding is computed once, the layers run on `samples` copies of the sequences, sample-major."""
         conv = self.value_embedding.tokenConv
         h = Fn.CircularConv3.apply(x2, conv.weight, conv.bias, self.position_embedding.table(), None, n, L, 1)
+        if samples > 1:
+            h = h.repeat(samples, 1)
+            n = n * samples
         n_layers = len(self.encoder.attn_layers)
         tail = False
         for i, layer in enumerate(self.encoder.attn_layers):

@@ -104,6 +104,9 @@ class Routeformer(nn.Module):
         # called (no arguments) in the backward pass as soon as the gradient w.r.t. the GPS backbone's input is complete, i.e.
         # when every gradient of the backbone's own parameters has been enqueued (data-parallel trainer: early all-reduce)
         self.backbone_grads_ready_hook = None
+        # > 1 only inside `forward_samples`: that many stochastic forwards of one batch run as ONE pass (the index tables of
+        # every attention call then hold one table per sample, `idx_group` keeps the samples apart)
+        self._samples = 1
 
     @property
     def device(self):
@@ -322,6 +325,38 @@ class Routeformer(nn.Module):
     def _source(self, keys_tables, groups=0):
         return PlannedIndexSource([(k, t, groups) for k, t in keys_tables], self.forced_tops)
 
+    def prepare_sample_draws(self, batch, n: int):
+        """The CPU draws of `n` consecutive eval forwards of the same batch (full_comparison.py:659-665), in the order those
+        forwards would make them (forward 0: visual path then GPS backbone, forward 1: ...), uploaded with one copy.  Returns
+        the plan of ONE forward whose every table is stacked [n, L_Q, U]."""
+        dev = batch["gps"].device
+        visual, backbone, log = [], [], []
+        for _ in range(n):
+            if self.with_video:
+                visual.append(self._plan_visual(batch, False))
+                log += visual[-1]["log"]
+            if isinstance(self.gps_backbone, Informer):
+                backbone.append(self._plan_backbone(batch["gps"].shape[1], self.gps_backbone.pred_len))
+                log += backbone[-1][1]
+
+        def stacked(per_sample_draws, slot):
+            n_draws = len(per_sample_draws[0])
+            views = self._upload([per_sample_draws[s_][i] for i in range(n_draws) for s_ in range(n)], dev, slot)
+            # the n tables of draw i are adjacent in the staging buffer: one strided view instead of a concatenation
+            return [views[i * n].as_strided((n, *views[i * n].shape[1:]), (views[i * n][0].numel(), views[i * n].shape[2], 1))
+                    for i in range(n_draws)]
+
+        plan = {"visual": None, "backbone": None}
+        if visual:
+            pv = dict(visual[0])
+            pv["tables"] = stacked([v["draws"] for v in visual], "visual_samples")
+            plan["visual"] = pv
+            self.last_pattern = (bool(pv["drop_left"]), bool(pv["drop_right"]), bool(pv["drop_gaze"]))
+        if backbone:
+            plan["backbone"] = (backbone[0][1], stacked([b[0] for b in backbone], "backbone_samples"))
+        self.last_draw_log = log
+        return plan
+
     # ------------------------------------------------------------------------------------------
     # visual streams
     # ------------------------------------------------------------------------------------------
@@ -368,16 +403,22 @@ class Routeformer(nn.Module):
             tokens = torch.cat(feats, 0).reshape(-1, feats[0].shape[-1]).contiguous()
         n_layers = c.encoder_layers
         keys_tables = []
+        ns = self._samples
         for layer in range(n_layers):
             ids = [plan["frame_sets"][name][layer] for name in order]
-            keys_tables.append((plan["log"][ids[0]], torch.cat([dev_tables[i] for i in ids], 0).contiguous()))
-        src = self._source(keys_tables, groups=n_per_view if len(order) > 1 else 0)
+            if ns == 1:
+                table = torch.cat([dev_tables[i] for i in ids], 0).contiguous()
+            else:  # sequences are ordered [sample][view][frame]: tables likewise
+                table = torch.stack([dev_tables[i] for i in ids], 1).reshape(ns * len(ids), *dev_tables[ids[0]].shape[1:])
+            keys_tables.append((plan["log"][ids[0]], table))
+        src = self._source(keys_tables, groups=n_per_view if len(order) * ns > 1 else 0)
         n_total = n_per_view * len(order)
-        feats = self.frame_encoder.encode(tokens, n_total, S, src, self.record_tops, "frame_encoder")  # [n_total, E]
+        feats = self.frame_encoder.encode(tokens, n_total, S, src, self.record_tops, "frame_encoder", samples=ns)  # [ns*n_total, E]
         E = c.image_embedding_size
         out = {}
+        feats = feats.view(ns, len(views), n_per_view, E)
         for i, v in enumerate(views):
-            out[v["name"]] = feats[i * n_per_view:(i + 1) * n_per_view].view(v["B"], len(v["t_idx"]), E)
+            out[v["name"]] = feats[:, i].reshape(ns * v["B"], len(v["t_idx"]), E)
         return out
 
     overlap_branches = True  # run the gaze encoder concurrently with the frame path (class-level switch, e.g. for debugging)
@@ -393,7 +434,9 @@ class Routeformer(nn.Module):
         E, T = c.image_embedding_size, plan["T_vid"]
         dev = self.device
         rel_v, rel_g = c.output_fps // c.video_fps, c.output_fps // c.gaze_fps
-        B = batch["gps"].shape[0]
+        ns = self._samples
+        B = batch["gps"].shape[0] * ns
+        groups = batch["gps"].shape[0] if ns > 1 else 0  # sequences per index table (sample-major batch of forward_samples)
         # The gaze encoder (B*40 tokens: ~100 small launches forward, ~200 backward) depends on nothing the frame encoder
         # produces: it is forked onto a side stream BEFORE the frame path is enqueued and joined where the gaze-video decoder
         # needs both, so its launches fill the SMs the big frame-encoder kernels leave idle.  Autograd replays the same stream
@@ -402,15 +445,15 @@ class Routeformer(nn.Module):
         if self.with_gaze and not plan["drop_gaze"]:
             Lg = c.gps_backbone_config.seq_len
             gaze = batch["gaze"].to(torch.float32).contiguous()
-            src = self._source([(plan["log"][i], dev_tables[i]) for i in plan["entries"]["gaze_encoder"]])
+            src = self._source([(plan["log"][i], dev_tables[i]) for i in plan["entries"]["gaze_encoder"]], groups)
             main = torch.cuda.current_stream()
             side = self._branch_stream(dev) if self.overlap_branches else None
             if side is not None:
                 side.wait_stream(main)
             with torch.cuda.stream(side if side is not None else main):
                 gaze_ds = ops.median_downsample(gaze, Lg)  # utils/filter.py:5-43 (raises if Lg >= samples)
-                gq = self.gaze_encoder.encode(torch.nn.functional.pad(gaze_ds.view(B * Lg, 2), (0, 2)), B, Lg, src, self.record_tops,
-                                              "gaze_encoder")  # [B*Lg, E]
+                gaze_in = torch.nn.functional.pad(gaze_ds.view(-1, 2), (0, 2))
+                gq = self.gaze_encoder.encode(gaze_in, B // ns, Lg, src, self.record_tops, "gaze_encoder", samples=ns)  # [B*Lg, E]
             if side is not None:
                 gaze.record_stream(side)
         feats = self._encode_frames(batch, plan, dev_tables, training)
@@ -443,7 +486,7 @@ class Routeformer(nn.Module):
                 if self.overlap_branches:  # join: the decoder reads the gaze-encoder output on the main stream
                     torch.cuda.current_stream().wait_stream(self._branch_stream(dev))
                     gq.record_stream(torch.cuda.current_stream())
-                src = self._source([(plan["log"][i], dev_tables[i]) for i in ent["gaze_video_decoder"]])
+                src = self._source([(plan["log"][i], dev_tables[i]) for i in ent["gaze_video_decoder"]], groups)
                 g = self.gaze_video_decoder.decode(front_full.view(B * T, E), gq, B, T, Lg, src, self.record_tops, "gaze_video_decoder")
                 g = g.view(B, Lg, -1)[:, :T].contiguous()  # routeformer.py:327
                 streams.append((True, True, 0, 0, 1))
@@ -455,7 +498,7 @@ class Routeformer(nn.Module):
         meta = dict(B=B, T=T, E=E, streams=streams)
         tokens = Fn.TokenStreams.apply(meta, *srcs, *embs)  # [B, n_streams*T, E]
         n_streams = len(streams)
-        src = self._source([(plan["log"][i], dev_tables[i]) for i in plan["entries"]["video_encoder"]])
+        src = self._source([(plan["log"][i], dev_tables[i]) for i in plan["entries"]["video_encoder"]], groups)
         vis = self.video_encoder.encode(tokens.view(B * n_streams * T, E), B, n_streams * T, src, self.record_tops, "video_encoder")
         return vis.view(B, -1, c.encoder_hidden_size)
 
@@ -509,7 +552,8 @@ class Routeformer(nn.Module):
                 draws, log = self._plan_backbone(T, gb.pred_len)
                 tables = self._upload(draws, x.device, f"backbone_p{gb.pred_len}")
                 self.last_draw_log += log
-            out = gb.run(x, PlannedIndexSource([(k, t, 0) for k, t in zip(log, tables)], self.forced_tops), self.record_tops)
+            groups = B // self._samples if self._samples > 1 else 0
+            out = gb.run(x, PlannedIndexSource([(k, t, groups) for k, t in zip(log, tables)], self.forced_tops), self.record_tops)
         else:  # foreign GPS backbone plugin (routeformer.py:241)
             out = gb(x[:, :, :enc_in])
         if c.decoder_mode == "recursive":
@@ -532,6 +576,35 @@ class Routeformer(nn.Module):
             rest = rest[:, :, E:]
         assert rest.shape[-1] == 0, f"Output should be empty at this point, but is {rest.shape}."
         return motion, wp, dense
+
+    @torch.no_grad()
+    def forward_samples(self, batch, n: int):
+        """`n` stochastic eval-mode forwards of one batch as ONE pass -> (waypoints [n,B,P,2], dense [n,B,P,E] or None).
+
+        Equals `[self(batch) for _ in range(n)]` (the loop of full_comparison.py:659-665) draw for draw: the ProbSparse index
+        tables are drawn in the order of the sequential forwards and each sample keeps its own tables.  What the samples share
+        is computed once (FoV crop, patch embedding, token embedding of the frame encoder, median filters); everything after
+        the first sampled attention runs on the n-fold batch.  Autoregressive models keep the sequential loop."""
+        c = self.configs
+        if self.training:
+            raise RuntimeError("forward_samples is an evaluation path: call model.eval() first")
+        if c.autoregressive or n == 1:
+            outs = [self(batch) for _ in range(n)]
+            if c.dense_prediction:
+                return torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs])
+            return torch.stack(outs), None
+        B = batch["gps"].shape[0]
+        self._pending_plan = self.prepare_sample_draws(batch, n)
+        self._samples = n
+        try:
+            motion, visual = self.preprocess_batch(batch)
+            motion = motion.repeat(n, 1, 1)
+            out, origin = self._forward(motion, visual)
+            _, wp, dense = self.postprocess_batch(batch["gps"][:, -1:, :].repeat(n, 1, 1), out, origin)
+        finally:
+            self._samples = 1
+        wp = wp.view(n, B, *wp.shape[1:])
+        return wp, (dense.reshape(n, B, *dense.shape[1:]) if dense is not None else None)
 
     def forward(self, batch, target_batch=None):
         c = self.configs

@@ -618,13 +618,16 @@ def test_training_step_caller(epoch):
     assert not missing, missing
 
 
-def test_eval_step_caller():
-    """ParallelTrainerSteps.eval_step (full_comparison.py:654-679): RNG order over the five forwards, mean prediction, per-clip metrics."""
+@pytest.mark.parametrize("batched", [True, False])
+def test_eval_step_caller(batched):
+    """ParallelTrainerSteps.eval_step (full_comparison.py:654-679): RNG order over the five forwards, mean prediction, per-clip
+    metrics -- as ONE five-fold batch (`Routeformer.forward_samples`, the default) and as the reference's loop of five forwards."""
     import routeformer_b200 as R
 
     gold, cfg, spec, sd, batch, model, dev_batch = _steps_case()
     model.eval()
     steps = R.ParallelTrainerSteps(model)
+    steps.batched_samples = batched
     logs = []
     orig = model.prepare_draws
 
@@ -636,6 +639,9 @@ def test_eval_step_caller():
     model.prepare_draws = spy
     losses, ades, fdes = steps.eval_step(dev_batch)
     torch.cuda.synchronize()
+    if batched:
+        assert not logs  # one plan for all five forwards
+        logs = model.last_draw_log
     e = gold["eval"]
     assert [(lk, (lq, u)) for lk, lq, u in logs] == [tuple(d) for d in e["draws"]]
     assert rel_err(steps.last_mean_prediction.cpu(), e["mean_prediction"]) < 5e-3
@@ -646,6 +652,39 @@ def test_eval_step_caller():
     t = batch["target"]["gps"]
     ref_ade = torch.stack([O.ade(mean[i:i + 1], t[i:i + 1]) for i in range(mean.shape[0])])
     assert torch.allclose(ades.cpu(), ref_ade, rtol=2e-5)
+
+
+@pytest.mark.parametrize("case", ["full_small_eval", "dreyeve_small", "no_scene_small", "gps_only_paper", "full_paper_b64_eval"])
+def test_forward_samples_equals_sequential_forwards(case):
+    """`forward_samples(batch, 5)` against five sequential eval forwards after the same `torch.manual_seed`: identical CPU draw
+    log, every sample's waypoints / dense features equal to its sequential forward (the arithmetic per sequence is the same;
+    only the batch the kernels see is five times larger)."""
+    gold = load_golden(case)
+    cfg, spec, sd, batch = case_from_golden(gold)
+    model = build_product(cfg, spec).to(DEV).eval()
+    model.load_state_dict(sd)
+    dev_batch = {k: v.to(DEV) for k, v in batch.items()}
+    n = 5
+    torch.manual_seed(12345)
+    seq, seq_log = [], []
+    with torch.no_grad():
+        for _ in range(n):
+            seq.append(model(dev_batch))
+            seq_log += model.last_draw_log
+    torch.manual_seed(12345)
+    wp, dense = model.forward_samples(dev_batch, n)
+    torch.cuda.synchronize()
+    assert model.last_draw_log == seq_log
+    dense_pred = bool(cfg.dense_prediction) and model.with_video
+    worst = 0.0
+    for s_ in range(n):
+        ref_wp = seq[s_][0] if cfg.dense_prediction else seq[s_]
+        worst = max(worst, rel_err(wp[s_].cpu(), ref_wp.cpu()))
+        if dense_pred:
+            worst = max(worst, rel_err(dense[s_].cpu(), seq[s_][1].cpu()))
+    print(f"forward_samples vs sequential [{case}]: worst relative difference {worst:.2e}")
+    assert worst < 1e-4, worst
+    assert wp.shape[:2] == (n, batch["gps"].shape[0])
 
 
 def test_training_step_with_feature_dropout():

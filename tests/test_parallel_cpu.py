@@ -121,6 +121,35 @@ def test_deferred_draws_fill_the_same_pinned_tables():
     assert ref and all(torch.equal(ref[k], v[0]) for k, v in model._idx_slots.items())
 
 
+def test_sample_draw_plan_equals_sequential_plans():
+    """prepare_sample_draws(batch, n) (eval_step's n stochastic forwards as one pass): the same CPU draws in the same order as n
+    sequential eval forwards, and table s of every stacked [n, L_Q, U] entry is exactly forward s's table."""
+    import torch
+
+    from tests.helpers import build_product, case_from_golden, load_golden
+
+    for case in ("full_small_eval", "dreyeve_small", "gps_only_paper"):
+        cfg, spec, sd, batch = case_from_golden(load_golden(case))
+        model = build_product(cfg, spec).eval()
+        n = 3
+        torch.manual_seed(7)
+        log, seq = [], []
+        for _ in range(n):
+            plan = model.prepare_draws(batch, False)
+            log += model.last_draw_log
+            seq.append(([t.clone() for t in plan["visual"]["tables"]] if plan["visual"] else [], [t.clone() for t in plan["backbone"][1]]))
+        torch.manual_seed(7)
+        plan = model.prepare_sample_draws(batch, n)
+        assert model.last_draw_log == log
+        stacked = (plan["visual"]["tables"] if plan["visual"] else [], plan["backbone"][1])
+        for part in (0, 1):
+            assert len(stacked[part]) == len(seq[0][part])
+            for i, t in enumerate(stacked[part]):
+                assert t.shape[0] == n
+                for s_ in range(n):
+                    assert torch.equal(t[s_], seq[s_][part][i][0]), (case, part, i, s_)
+
+
 def test_early_allreduce_ranges_partition_the_gradient_arena():
     """The overlapped all-reduce sends the GPS backbone's slices of the flat gradient arena early and the rest after backward:
     the two range lists must partition [0, n_trainable) and the early one must hold exactly the backbone's parameters."""
