@@ -675,15 +675,20 @@ def test_forward_samples_equals_sequential_forwards(case):
     wp, dense = model.forward_samples(dev_batch, n)
     torch.cuda.synchronize()
     assert model.last_draw_log == seq_log
-    dense_pred = bool(cfg.dense_prediction) and model.with_video
-    worst = 0.0
-    for s_ in range(n):
-        ref_wp = seq[s_][0] if cfg.dense_prediction else seq[s_]
-        worst = max(worst, rel_err(wp[s_].cpu(), ref_wp.cpu()))
-        if dense_pred:
-            worst = max(worst, rel_err(dense[s_].cpu(), seq[s_][1].cpu()))
-    print(f"forward_samples vs sequential [{case}]: worst relative difference {worst:.2e}")
-    assert worst < 1e-4, worst
+    ref_wp = torch.stack([(o[0] if cfg.dense_prediction else o) for o in seq]).cpu()   # [n, B, P, 2]
+    got = wp.cpu()
+    per_clip = ((got - ref_wp).flatten(2).norm(dim=2) / ref_wp.flatten(2).norm(dim=2).clamp_min(1e-12)).flatten()
+    if bool(cfg.dense_prediction) and model.with_video:
+        ref_d = torch.stack([o[1] for o in seq]).cpu()
+        d_err = ((dense.cpu() - ref_d).flatten(2).norm(dim=2) / ref_d.flatten(2).norm(dim=2).clamp_min(1e-12)).flatten()
+        per_clip = torch.maximum(per_clip, d_err)
+    moved = int((per_clip > 1e-4).sum())
+    print(f"forward_samples vs sequential [{case}]: median {float(per_clip.median()):.2e}, max {float(per_clip.max()):.2e}, "
+          f"{moved} of {per_clip.numel()} (sample, clip) pairs above 1e-4")
+    # Same arithmetic per sequence: the kernel variants the launch heuristics pick for a five-fold batch (thread count of the
+    # generic attention kernel, tile schedule of the GEMMs) keep the summation order, so the samples agree bit for bit -- which
+    # matters because ProbSparse's top-u selection would turn a rounding-level difference into a different selected query.
+    assert moved == 0 and float(per_clip.max()) < 1e-6, (moved, float(per_clip.max()))
     assert wp.shape[:2] == (n, batch["gps"].shape[0])
 
 
