@@ -5,7 +5,8 @@ import time
 
 import torch
 
-from routeformer_b200 import ops
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+from routeformer_b200 import ops  # noqa: E402
 
 DEV = "cuda"
 PEAKS = json.load(open("MEASURED_PEAKS.json")) if __import__("os").path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
