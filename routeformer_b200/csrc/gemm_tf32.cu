@@ -980,6 +980,11 @@ extern "C" int rf_debug_gemm_probe(int mode) {
   return RF_OK;
 }
 
+static int split_fill() {  // CTAs (in units of the SM count) that the automatic split of a linear epilogue aims for
+  static const int v = [] { const char* e = getenv("RF_GEMM_SPLIT_FILL"); return (e && e[0] >= '1' && e[0] <= '9') ? e[0] - '0' : 1; }();
+  return v;
+}
+
 extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   using namespace rf;
   RF_CHECK_ARG(p != nullptr, "rf_gemm_tf32: null params");
@@ -1008,7 +1013,8 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   if (splits <= 0) {
     splits = 1;
     if (p->accumulate && plain) {
-      const int want = max(1, (2 * num_sms()) / tiles);       // fill, but do not overflow, one wave of 2 CTAs per SM
+      static const int wfill = [] { const char* e = getenv("RF_GEMM_WGRAD_FILL"); return (e && e[0] >= '1' && e[0] <= '9') ? e[0] - '0' : 2; }();
+      const int want = max(1, (wfill * num_sms()) / tiles);   // fill, but do not overflow, one wave of 2 CTAs per SM
       splits = max(1, min(want, kb_total / 4));              // keep >= 4 k-blocks per split
     }
   }
@@ -1019,13 +1025,13 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   // 0 adds the linear terms, and all splits meet in the TMA reduce-add.
   bool split_linear = false;
   if (p->split_k == 0 && !p->accumulate && !f16 && p->act == RF_ACT_NONE && !p->preact && !p->dact && !p->round_f16 &&
-      p->out_group_in == 0 && 2 * tiles <= num_sms() && kb_total >= 8) {
+      p->out_group_in == 0 && 2 * tiles <= split_fill() * num_sms() && kb_total >= 8) {
     const char* cb = reinterpret_cast<const char*>(p->C);
     const char* ce = cb + (static_cast<long long>(p->M - 1) * p->ldc + p->N) * 4;
     const char* rb = reinterpret_cast<const char*>(p->residual);
     const bool res_aliases = rb && rb < ce && rb + (static_cast<long long>(p->M - 1) * p->ld_res + p->N) * 4 > cb;
     static const bool enabled = [] { const char* e = getenv("RF_GEMM_SPLIT_LINEAR"); return !(e && e[0] == '0'); }();
-    const int want = min(num_sms() / tiles, kb_total / 4);
+    const int want = min(split_fill() * num_sms() / tiles, kb_total / 4);
     if (enabled && !res_aliases && want >= 2) {
       splits = want;
       split_linear = true;
