@@ -5,16 +5,10 @@
 // with zeros outside the frame, then normalised per channel, written either planar [n,3,S,S] or directly in the
 // patch-major layout the patch-embedding GEMM consumes as its A operand (no im2col pass).
 //
-// fov_crop_tiled_kernel (default): the bilinear resample is SEPARABLE, and both the column taps (x0, wx) and the row taps
-// (y0, wy) are shared by the three channels.  A CTA owns ROWS_PER_TILE output rows of one frame and runs two passes:
-//   V: for every output row and channel, the vertical blend  t[j] = src[y0][j] * wy0 + src[y0+1][j] * wy1  over the source
-//      columns the frame's window covers, read from HBM with coalesced 2-element vector loads (a warp reads 128..256
-//      contiguous bytes per instruction) and staged in shared memory;
-//   H: every thread produces 2 adjacent output pixels per (row, channel) from 2 x 2 shared-memory taps, normalises, and
-//      stores one packed 4 B (fp16 / bf16) or 8 B (fp32) word, a warp writing 128 / 256 contiguous bytes.
-// ~10 instructions per output element instead of ~35 for the direct 4-tap gather (which was issue-bound at 0.33 of the HBM
-// roofline).  Tiles whose rows all fall into the zero padding (3/4 of a pad-to-square scene view) only store constants.
-// fov_crop_kernel (the round-1 direct gather) remains for mirrored windows (fw <= 0), which the tiled kernel does not handle.
+// fov_crop_walk_kernel (default): the bilinear resample is SEPARABLE and its column taps are shared by the three channels.
+// A thread owns two adjacent output columns and walks down the output rows of its CTA's strip with the horizontal blends
+// of the current two source rows in registers (no shared-memory staging); see the kernel's comment.
+// fov_crop_kernel (the round-1 direct 4-tap gather, issue-bound at 0.3 of the HBM roofline) remains behind RF_CROP_DIRECT=1.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -34,6 +28,18 @@ struct u8h { unsigned char v; };
 template <> __device__ __forceinline__ float load_px<u8h>(const u8h* p) {
   return __half2float(__float2half_rn(__ldg(&p->v) * (1.0f / 255.0f)));
 }
+// the same in two steps -- the raw element as loaded, converted later -- for kernels that keep loads in flight across other work
+template <typename T> struct RawPx { typedef T type; };
+template <> struct RawPx<u8h> { typedef unsigned char type; };
+template <typename T> __device__ __forceinline__ typename RawPx<T>::type load_raw(const T* p) { return __ldg(p); }
+template <> __device__ __forceinline__ unsigned char load_raw<u8h>(const u8h* p) { return __ldg(&p->v); }
+template <typename T> __device__ __forceinline__ typename RawPx<T>::type zero_raw() { return static_cast<typename RawPx<T>::type>(0); }
+template <> __device__ __forceinline__ __half zero_raw<__half>() { return __ushort_as_half(0); }
+template <typename T> __device__ __forceinline__ float cvt_px(typename RawPx<T>::type r);
+template <> __device__ __forceinline__ float cvt_px<__half>(__half r) { return __half2float(r); }
+template <> __device__ __forceinline__ float cvt_px<float>(float r) { return r; }
+template <> __device__ __forceinline__ float cvt_px<unsigned char>(unsigned char r) { return r * (1.0f / 255.0f); }
+template <> __device__ __forceinline__ float cvt_px<u8h>(unsigned char r) { return __half2float(__float2half_rn(r * (1.0f / 255.0f))); }
 
 __device__ __forceinline__ void store4(float* dst, const float (&v)[4]) {
   *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
@@ -173,26 +179,14 @@ __global__ void __launch_bounds__(256) fov_crop_kernel(const Args a) {
   }
 }
 
-// ---- strip kernel: shared-memory staged source window, separable blend, register reuse down the rows -------------
-constexpr int TILE_THREADS = 256;
-constexpr int STRIP_ROWS = 32;        // output rows per CTA
-constexpr int STAGE_FLOATS = 15872;   // 62 KiB staging buffer (3 channels x rows x pitch floats)
-
-// two adjacent source elements (element offset even, pointer 2-element aligned) -> float2
-template <typename T> __device__ __forceinline__ float2 load_px2(const T* p);
-template <> __device__ __forceinline__ float2 load_px2<__half>(const __half* p) {
-  const unsigned u = __ldg(reinterpret_cast<const unsigned*>(p));
-  return __half22float2(*reinterpret_cast<const __half2*>(&u));
-}
-template <> __device__ __forceinline__ float2 load_px2<float>(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-template <> __device__ __forceinline__ float2 load_px2<unsigned char>(const unsigned char* p) {
-  const unsigned short u = __ldg(reinterpret_cast<const unsigned short*>(p));
-  return make_float2((u & 0xFF) * (1.0f / 255.0f), (u >> 8) * (1.0f / 255.0f));
-}
-template <> __device__ __forceinline__ float2 load_px2<u8h>(const u8h* p) {
-  const unsigned short u = __ldg(reinterpret_cast<const unsigned short*>(p));
-  return __half22float2(__floats2half2_rn((u & 0xFF) * (1.0f / 255.0f), (u >> 8) * (1.0f / 255.0f)));
-}
+// ---- column-walker kernel (default): separable blend, everything in registers ---------------------------------
+// packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issue slot)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float2 upk(f32x2 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 
 __device__ __forceinline__ void store2(float* dst, float a, float b) { *reinterpret_cast<float2*>(dst) = make_float2(a, b); }
 __device__ __forceinline__ void store2(__half* dst, float a, float b) { *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(a, b); }
@@ -200,333 +194,242 @@ __device__ __forceinline__ void store2(__nv_bfloat16* dst, float a, float b) {
   *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(a, b);
 }
 
-struct TiledArgs {
-  Args a;
-  int vec2;    // 1: W even and the frame base 2-element aligned -> 2-element vector loads while staging
+constexpr int WALK_ROWS = 32;     // output rows per CTA
+constexpr int WALK_THREADS = 128; // one thread per pair of adjacent output columns (S <= 256)
+struct __align__(16) WalkRow {    // per output row of the CTA's strip, computed once, read as one broadcast 16 B shared load
+  int y0;          // floor of the sample row
+  float wy0, wy1;  // weights of source rows y0 / y0 + 1
+  int off;         // output offset of the row inside the frame (elements; the thread adds its column / channel part)
 };
 
-// one bilinear sample with zero padding, taps in ATen's order (mirrored windows only: rare, slow, correct)
-template <typename TS>
-__device__ __forceinline__ float direct_sample(const TS* pl, float sx, float sy, int H, int W) {
-  const float fx0 = floorf(sx), fy0 = floorf(sy);
-  const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
-  const float wx1 = sx - fx0, wx0 = 1.0f - wx1, wy1 = sy - fy0, wy0 = 1.0f - wy1;
-  const bool xa = x0 >= 0 && x0 < W, xb = x0 + 1 >= 0 && x0 + 1 < W, ya = y0 >= 0 && y0 < H, yb = y0 + 1 >= 0 && y0 + 1 < H;
-  const float v00 = (xa && ya) ? load_px<TS>(pl + static_cast<long long>(y0) * W + x0) : 0.0f;
-  const float v01 = (xb && ya) ? load_px<TS>(pl + static_cast<long long>(y0) * W + x0 + 1) : 0.0f;
-  const float v10 = (xa && yb) ? load_px<TS>(pl + static_cast<long long>(y0 + 1) * W + x0) : 0.0f;
-  const float v11 = (xb && yb) ? load_px<TS>(pl + static_cast<long long>(y0 + 1) * W + x0 + 1) : 0.0f;
-  return v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
+// The horizontal blend of one source row for the thread's two output columns, all three channels:
+//   h[c] = (src[c][y][xa] * wa0 + src[c][y][xa + 1] * wa1,  src[c][y][xb] * wb0 + src[c][y][xb + 1] * wb1)
+// Three per-thread variants (fixed for the whole walk):
+//   WALK_NARROW: xb - xa in {0, 1} and taps xa .. xa+2 inside the frame (every interior thread of an up-sampling crop): three
+//                loads per channel from one address, the second column's weights laid over the three taps (one of them is 0);
+//   WALK_WIDE  : all four taps inside the frame, any distance: two addresses per channel, immediate offsets;
+//   WALK_EDGE  : taps outside the frame read nothing and contribute exactly zero.
+// Addresses are signed 32-bit element offsets from the frame base (taps left of the frame give small negative offsets that
+// are never dereferenced).
+constexpr int WALK_NARROW = 0, WALK_WIDE = 1, WALK_EDGE = 2;
+// base + off * sizeof(T) as ONE instruction (the compiler otherwise re-derives the 64-bit frame base for every address)
+template <typename T>
+__device__ __forceinline__ T* at_s32(T* base, int off) {
+  unsigned long long r;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(off), "n"(sizeof(T)), "l"(reinterpret_cast<unsigned long long>(base)));
+  return reinterpret_cast<T*>(r);
 }
-
-// The four staged floats [e, e+3] of one line, e even: two 8 B shared loads
-struct Win4 { float f[4]; };
-__device__ __forceinline__ Win4 load_win(const float* line, int e) {
-  const float2 lo = *reinterpret_cast<const float2*>(line + e), hi = *reinterpret_cast<const float2*>(line + e + 2);
-  Win4 w;
-  w.f[0] = lo.x; w.f[1] = lo.y; w.f[2] = hi.x; w.f[3] = hi.y;
-  return w;
-}
-
-// packed fp32 pairs (Blackwell FFMA2 / FMUL2: two IEEE fp32 operations per issue slot)
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ float2 upk(f32x2 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-
-// the four staged floats [e, e+3] of one line (e even) as two packed pairs: two 8 B shared loads
-struct Win { f32x2 lo, hi; };
-__device__ __forceinline__ Win load_w(const float* line) {
-  Win w;
-  w.lo = *reinterpret_cast<const f32x2*>(line);
-  w.hi = *reinterpret_cast<const f32x2*>(line + 2);
-  return w;
-}
-
-struct RowInfo {  // per output row of a chunk, written once per CTA
-  int ia, ib;      // float offsets of the staged lines of source rows y0 / y0+1 (channel 0)
-  float wy0, wy1;  // their weights (0 outside the frame)
-  long long o;     // output offset of (row, this thread's columns excluded, channel 0)
-  int y0, pad;
+struct WalkCols {
+  int k[3][2];       // per channel: c * plane + xa, c * plane + xb
+  bool ok[4];        // taps xa, xa+1, xb, xb+1 inside the frame (EDGE)
+  float w[5];        // NARROW: wa0, wa1, wb'0, wb'1, wb'2;  otherwise wa0, wa1, wb0, wb1
 };
-
-__device__ __forceinline__ void store1(float* dst, float a) { *dst = a; }
-__device__ __forceinline__ void store1(__half* dst, float a) { *dst = __float2half_rn(a); }
-__device__ __forceinline__ void store1(__nv_bfloat16* dst, float a) { *dst = __float2bfloat16_rn(a); }
-
-// Rows [my_a, my_b) of the chunk for one thread.  PAIR: the thread's two adjacent output pixels read the same 4-float window
-// (<= 1 source column per output column) and leave as one packed store; otherwise the routine is called once per pixel.
-// The source rows of the previous output row stay in registers; all control flow is CTA-uniform.
-template <bool PAIR, typename TD>
-__device__ __forceinline__ void strip_rows(const float* __restrict__ stage, const RowInfo* __restrict__ rows, int my_a, int my_b, int pitch,
-                                           int e0, const float (&wa)[4], const float (&wb)[4], long long col_off, long long ch_stride,
-                                           const float (&mean)[3], const float (&inv_std)[3], TD* __restrict__ out) {
-  Win A[3], B[3];
-  const f32x2 walo = pk(wa[0], wa[1]), wahi = pk(wa[2], wa[3]);
-  const f32x2 wblo = pk(wb[0], wb[1]), wbhi = pk(wb[2], wb[3]);
-  int cur_y = -(1 << 30);
-  for (int r = my_a; r < my_b; ++r) {
-    const RowInfo ri = rows[r];
-    if (ri.y0 != cur_y) {
-      const bool shift = ri.y0 == cur_y + 1;
-      const float* la = stage + ri.ia + e0;
-      const float* lb = stage + ri.ib + e0;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (shift) A[c] = B[c];
-        else A[c] = load_w(la + c * pitch);
-        B[c] = load_w(lb + c * pitch);
-      }
-      cur_y = ri.y0;
-    }
-    const f32x2 wy0 = pk(ri.wy0, ri.wy0), wy1 = pk(ri.wy1, ri.wy1);
-    TD* dst = out + ri.o + col_off;
+// raw (unconverted) taps of one source row, all three channels; a row outside the frame is all zeros
+template <typename TS, int MODE>
+struct WalkTaps { typename RawPx<TS>::type v[3][MODE == WALK_NARROW ? 3 : 4]; };
+template <typename TS, int MODE>
+__device__ __forceinline__ void walk_load(const TS* __restrict__ src, int y, int H, int W, const WalkCols& q, WalkTaps<TS, MODE>& t) {
+  const typename RawPx<TS>::type zero = zero_raw<TS>();
+  if (y >= 0 && y < H) {  // CTA-uniform
+    const int rowoff = y * W;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      // vertical blend of the window, then the horizontal 4-tap dot product(s)
-      const f32x2 tlo = fma2(B[c].lo, wy1, mul2(A[c].lo, wy0)), thi = fma2(B[c].hi, wy1, mul2(A[c].hi, wy0));
-      const float2 p0 = upk(fma2(thi, wahi, mul2(tlo, walo)));
-      if (PAIR) {
-        const float2 p1 = upk(fma2(thi, wbhi, mul2(tlo, wblo)));
-        store2(dst + c * ch_stride, ((p0.x + p0.y) - mean[c]) * inv_std[c], ((p1.x + p1.y) - mean[c]) * inv_std[c]);
+      const TS* pa = at_s32(src, rowoff + q.k[c][0]);
+      if (MODE == WALK_NARROW) {
+        t.v[c][0] = load_raw<TS>(pa); t.v[c][1] = load_raw<TS>(pa + 1); t.v[c][2] = load_raw<TS>(pa + 2);
       } else {
-        store1(dst + c * ch_stride, ((p0.x + p0.y) - mean[c]) * inv_std[c]);
+        const TS* pb = at_s32(src, rowoff + q.k[c][1]);
+        if (MODE == WALK_EDGE) {
+          t.v[c][0] = q.ok[0] ? load_raw<TS>(pa) : zero; t.v[c][1] = q.ok[1] ? load_raw<TS>(pa + 1) : zero;
+          t.v[c][2] = q.ok[2] ? load_raw<TS>(pb) : zero; t.v[c][3] = q.ok[3] ? load_raw<TS>(pb + 1) : zero;
+        } else {
+          t.v[c][0] = load_raw<TS>(pa); t.v[c][1] = load_raw<TS>(pa + 1);
+          t.v[c][2] = load_raw<TS>(pb); t.v[c][3] = load_raw<TS>(pb + 1);
+        }
       }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int k = 0; k < (MODE == WALK_NARROW ? 3 : 4); ++k) t.v[c][k] = zero;
+  }
+}
+template <typename TS, int MODE>
+__device__ __forceinline__ void walk_blend(const WalkTaps<TS, MODE>& t, const WalkCols& q, f32x2 (&h)[3]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < (MODE == WALK_NARROW ? 3 : 4); ++k) v[k] = cvt_px<TS>(t.v[c][k]);
+    if (MODE == WALK_NARROW) h[c] = pk(fmaf(v[1], q.w[1], v[0] * q.w[0]), fmaf(v[2], q.w[4], fmaf(v[1], q.w[3], v[0] * q.w[2])));
+    else h[c] = pk(fmaf(v[1], q.w[1], v[0] * q.w[0]), fmaf(v[3], q.w[3], v[2] * q.w[2]));
+  }
+}
+
+// A CTA owns WALK_ROWS output rows of one frame; a thread owns two adjacent output columns and walks DOWN the rows.
+// The bilinear resample is separable: the horizontal blend h of a source row (fixed columns and weights for the whole walk)
+// is computed once and stays in registers for every output row that uses it -- an up-sampling crop (0.72 source rows per
+// output row for the gaze window) needs a new source row for ~3 of 4 output rows and shifts the previous one down; the
+// vertical blend, the normalisation and the store are packed f32x2 operations on the column pair.  ~12 instructions per
+// output value against ~40 for the direct 4-tap gather, no shared-memory staging and no barrier after the row table; a warp
+// reads ~100 contiguous bytes per load instruction and writes 128 (fp16 / bf16) or 256 (fp32).
+// The taps of source row cur_y + 2 are always IN FLIGHT while the current output rows are blended and stored (software
+// prefetch into registers): a thread's walk is a serial chain of ~24 source rows, and without it every one of them would
+// expose a full memory round trip.
+// All control flow in the walk is CTA-uniform.  Mirrored windows (fw, fh < 0) take the same code: column taps are per-thread
+// constants of any order, and a row that is neither the current nor the next one simply reloads both source rows.
+// (A NaN pixel in the source can reach one output column more than in the reference: NARROW multiplies its third tap by 0.)
+template <typename TS, typename TD, int MODE>
+__device__ __forceinline__ void walk_rows(const Args& a, const WalkRow* __restrict__ rows, int nrows, const TS* __restrict__ src,
+                                          const WalkCols& q, TD* __restrict__ out0, long long ch_stride) {
+  const int H = a.H, W = a.W;
+  f32x2 hA[3], hB[3];
+  f32x2 shift[3], istd[3];  // (x - mean) * inv_std as one fused multiply-add
+  TD* oc[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    shift[c] = pk(-a.mean[c] * a.inv_std[c], -a.mean[c] * a.inv_std[c]);
+    istd[c] = pk(a.inv_std[c], a.inv_std[c]);
+    oc[c] = out0 + c * ch_stride;
+  }
+  int cur_y = -(1 << 30);
+  WalkTaps<TS, MODE> nxt;  // taps of source row cur_y + 2
+#pragma unroll 1
+  for (int r = 0; r < nrows; ++r) {
+    const WalkRow ri = rows[r];
+    if (ri.y0 != cur_y) {
+      if (ri.y0 == cur_y + 1) {
+        hA[0] = hB[0]; hA[1] = hB[1]; hA[2] = hB[2];
+        walk_blend<TS, MODE>(nxt, q, hB);
+      } else {
+        WalkTaps<TS, MODE> ta, tb;
+        walk_load<TS, MODE>(src, ri.y0, H, W, q, ta);
+        walk_load<TS, MODE>(src, ri.y0 + 1, H, W, q, tb);
+        walk_blend<TS, MODE>(ta, q, hA);
+        walk_blend<TS, MODE>(tb, q, hB);
+      }
+      cur_y = ri.y0;
+      walk_load<TS, MODE>(src, cur_y + 2, H, W, q, nxt);
+    }
+    const f32x2 wy0 = pk(ri.wy0, ri.wy0), wy1 = pk(ri.wy1, ri.wy1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float2 o = upk(fma2(fma2(hB[c], wy1, mul2(hA[c], wy0)), istd[c], shift[c]));
+      store2(oc[c] + ri.off, o.x, o.y);
     }
   }
 }
 
-// A CTA owns STRIP_ROWS output rows of one frame and works through them in chunks whose source rows fit the staging buffer:
-//   stage  : the source rows x columns the chunk touches, converted to fp32, loaded with independent coalesced vector loads
-//            (every thread issues its whole share before the first use: the pass is bandwidth-, not latency-bound);
-//   compute: a thread owns two adjacent output columns and walks DOWN its rows; the column taps are a 4-float window of the
-//            staged line with a fixed 4-vector of weights (no indexing in the loop), the two source rows of the previous
-//            output row stay in registers (an up-sampling crop needs a new source row for ~2 of 3 output rows), the vertical
-//            blend is shared by the two pixels.  ~10 instructions per output element against ~35 for the direct gather.
 template <typename TS, typename TD>
-__global__ void __launch_bounds__(TILE_THREADS, 2) fov_crop_tiled_kernel(const TiledArgs ta) {
-  extern __shared__ __align__(16) float stage[];  // [rows][3][pitch]
-  __shared__ RowInfo s_rows[STRIP_ROWS];
-  const Args& a = ta.a;
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * STRIP_ROWS;
-  const int tid = threadIdx.x;
+__global__ void __launch_bounds__(WALK_THREADS) fov_crop_walk_kernel(const Args a) {
+  __shared__ WalkRow s_rows[WALK_ROWS];
+  const int n = blockIdx.y, r0 = blockIdx.x * WALK_ROWS, tid = threadIdx.x;
   const int S = a.S, H = a.H, W = a.W;
-
+  const int nrows = min(WALK_ROWS, S - r0);
   const float cx = __ldg(a.centers + 2 * n), cy = __ldg(a.centers + 2 * n + 1);
   const float fw = __ldg(a.windows + 2 * n), fh = __ldg(a.windows + 2 * n + 1);
   const long long src_frame = a.frame_ids ? __ldg(a.frame_ids + n) : n;
-  const long long plane = static_cast<long long>(H) * W;
+  const int plane = H * W;
   const TS* src = reinterpret_cast<const TS*>(a.frames) + src_frame * 3ll * plane;
   const float inv_s = 1.0f / S;
-  TD* out = reinterpret_cast<TD*>(a.out);
 
-  // same expressions as the direct kernel / the oracle: sample position of output column ox / output row oy
-  auto sample_x = [&](int ox) { return ((fw * ((2 * ox + 1) * inv_s - 1.0f) + (2.0f * cx - 1.0f) + 1.0f) * W - 1.0f) * 0.5f; };
-  auto sample_y = [&](int oy) { return ((fh * ((2 * oy + 1) * inv_s - 1.0f) + (2.0f * cy - 1.0f) + 1.0f) * H - 1.0f) * 0.5f; };
-
-  const int pairs = S >> 1;
-  const int groups = TILE_THREADS / pairs;            // row groups that fit the CTA (S = 256 -> 2, 224 -> 2, 64 -> 8)
-  const int pg = tid / pairs, pp = tid - pg * pairs;  // one integer division per thread
-  const int ox = pp << 1;
-  const bool worker = pg < groups;
-  const bool mirrored = !(fw > 0.0f) || !(fh > 0.0f);  // CTA-uniform; sample positions then do not grow with the index
-  const int r_end = min(r0 + STRIP_ROWS, S);
-
-  // output addressing
-  long long obase, row_stride, ch_stride;
-  int patch_rows_left = 1 << 30;  // patch-major: rows until the strip crosses into the next row of patches
-  if (a.patch > 0) {
-    const int px = fast_div(ox, a.patch_magic), ix = ox - px * a.patch;
-    const int py = fast_div(r0, a.patch_magic), iy = r0 - py * a.patch;
-    obase = (static_cast<long long>(n) * a.G * a.G + py * a.G + px) * a.out_ld + iy * a.patch + ix;
-    row_stride = a.patch;
-    ch_stride = static_cast<long long>(a.patch) * a.patch;
-    patch_rows_left = a.patch - iy;
-  } else {
-    obase = (static_cast<long long>(n) * 3 * S + r0) * S + ox;
-    row_stride = S;
-    ch_stride = static_cast<long long>(S) * S;
-  }
-  auto out_offset = [&](int r) {  // r = row inside the strip
-    long long o = obase + r * row_stride;
-    int left = patch_rows_left, rr = r;
-    while (rr >= left) {  // next row(s) of patches: + G patches, back to the first row of that patch
-      o += static_cast<long long>(a.G) * a.out_ld - static_cast<long long>(a.patch) * a.patch;
-      rr -= a.patch;
+  if (tid < nrows) {  // the strip's row table; same expressions as the direct kernel / the oracle
+    const int oy = r0 + tid;
+    const float gy = (2 * oy + 1) * inv_s - 1.0f;
+    const float sy = ((fh * gy + (2.0f * cy - 1.0f) + 1.0f) * H - 1.0f) * 0.5f;
+    const float fy0 = floorf(sy);
+    WalkRow ri;
+    // rows far outside the frame all behave like "both taps out": clamped so that y0 + 1 cannot overflow
+    ri.y0 = static_cast<int>(fminf(fmaxf(fy0, -3.0f), static_cast<float>(H)));
+    ri.wy1 = sy - fy0;
+    ri.wy0 = 1.0f - ri.wy1;
+    if (a.patch > 0) {
+      const int py = fast_div(oy, a.patch_magic), iy = oy - py * a.patch;
+      ri.off = py * a.G * static_cast<int>(a.out_ld) + iy * a.patch;
+    } else {
+      ri.off = oy * S;
     }
-    return o;
-  };
-
-  if (mirrored) {  // direct gather, any orientation
-    if (worker)
-      for (int r = r0 + pg; r < r_end; r += groups) {
-        const float sy = sample_y(r);
-        const long long o = out_offset(r - r0);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float v0 = direct_sample<TS>(src + c * plane, sample_x(ox), sy, H, W);
-          const float v1 = direct_sample<TS>(src + c * plane, sample_x(ox + 1), sy, H, W);
-          store2(out + o + c * ch_stride, (v0 - a.mean[c]) * a.inv_std[c], (v1 - a.mean[c]) * a.inv_std[c]);
-        }
-      }
-    return;
+    s_rows[tid] = ri;
   }
 
-  // Source-column span the window covers, clipped to the frame, first column rounded down to an even one.  sx grows with ox,
-  // so every in-frame tap of every output column lies in [j_lo, j_hi].
-  const int j_lo = max(static_cast<int>(floorf(sample_x(0))), 0) & ~1;
-  const int j_hi = min(static_cast<int>(floorf(sample_x(S - 1))) + 1, W - 1);
-  const int span = j_hi - j_lo + 1;                       // <= 0: the window misses the frame horizontally
-  const int pitch = ((max(span, 0) + 1) & ~1) + 4;        // even, >= span + 4: the 4-float windows never leave the line
-  const int max_rows = max(span > 0 ? STAGE_FLOATS / (3 * pitch) : 0, 0);
-
-  // Column taps of the two pixels: window start e (even) and a 4-vector of weights over slots e..e+3 of the staged line.
-  // narrow (<= 1 source column per output column): both pixels share the window of pixel 0.
-  const bool narrow = fw * W <= 0.999f * static_cast<float>(S);  // (margin: the two floors must never differ by 2)
-  int e[2];
-  float wgt[2][4];
+  // column taps of the thread's two pixels
+  const int ox = 2 * tid;
+  int x0[2];
+  float w0[2], w1[2];
+  WalkCols q;
+  bool interior = true;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const float sx = sample_x(ox + i);
+    const float gx = (2 * (ox + i) + 1) * inv_s - 1.0f;
+    const float sx = ((fw * gx + (2.0f * cx - 1.0f) + 1.0f) * W - 1.0f) * 0.5f;
     const float fx0 = floorf(sx);
-    const int x0 = static_cast<int>(fx0);
-    const float w1 = sx - fx0, w0 = 1.0f - w1;
-    const int rel = x0 - j_lo;
-    const int start = (i == 1 && narrow) ? e[0] : min(max(rel, 0) & ~1, max(pitch - 4, 0));
-    e[i] = start;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int col = j_lo + start + k;
-      float w = 0.0f;
-      if (col >= 0 && col < W) {
-        if (col == x0) w = w0;
-        else if (col == x0 + 1) w = w1;
-      }
-      wgt[i][k] = w;
-    }
+    x0[i] = static_cast<int>(fminf(fmaxf(fx0, -2.0f), static_cast<float>(W)));
+    w1[i] = sx - fx0;
+    w0[i] = 1.0f - w1[i];
+    q.ok[2 * i] = x0[i] >= 0 && x0[i] < W;
+    q.ok[2 * i + 1] = x0[i] + 1 >= 0 && x0[i] + 1 < W;
+    interior = interior && q.ok[2 * i] && q.ok[2 * i + 1];
   }
-
-  int ra = r0;
-  while (ra < r_end) {  // chunks of rows whose source rows fit the staging buffer (CTA-uniform control flow)
-    // rows of the chunk: [ra, rb); source rows [y_lo, y_hi] clipped to the frame
-    const int ya0 = static_cast<int>(floorf(sample_y(ra)));
-    int rb = ra + 1;
-    int y_last = ya0;
-    if (max_rows >= 2) {
-      // sy grows with the row: extend the chunk while its last source row still fits
-      while (rb < r_end) {
-        const int yn = static_cast<int>(floorf(sample_y(rb)));
-        if (min(yn + 1, H - 1) - max(ya0, 0) + 1 > max_rows) break;
-        y_last = yn;
-        ++rb;
-      }
-    }
-    const int y_lo = min(max(ya0, 0), H - 1), y_hi = min(max(y_last + 1, 0), H - 1);
-    const bool rows_out = (y_last + 1 < 0) || (ya0 >= H);  // every tap row of the chunk is outside the frame
-    const bool constant = rows_out || span <= 0 || max_rows < 2;
-    const bool fits = max_rows >= 2 || rows_out || span <= 0;
-    const int n_rows = y_hi - y_lo + 1;
-
-    if (!constant) {
-      // ---- stage: n_rows x 3 lines of `pitch` floats (tail zero-filled) --------------------------------------
-      const int npairs = pitch >> 1;
-      const int lane = tid & 31, warp = tid >> 5;
-      for (int line_id = warp; line_id < n_rows * 3; line_id += TILE_THREADS / 32) {  // one (row, channel) line per warp pass
-        const int yr = line_id / 3, c = line_id - yr * 3;
-        const TS* row = src + c * plane + static_cast<long long>(y_lo + yr) * W + j_lo;
-        float* line = stage + line_id * pitch;
-#pragma unroll 4
-        for (int jp = lane; jp < npairs; jp += 32) {  // independent loads: the compiler batches four of them per lane
-          const int j = jp << 1;
-          float2 v = make_float2(0.0f, 0.0f);
-          if (j + 1 < span) v = ta.vec2 ? load_px2<TS>(row + j) : make_float2(load_px<TS>(row + j), load_px<TS>(row + j + 1));
-          else if (j < span) v.x = load_px<TS>(row + j);
-          *reinterpret_cast<float2*>(line + j) = v;
-        }
-      }
-    }
-    if (!constant && tid < rb - ra) {  // per-row constants of the chunk, once per CTA
-      const int r = ra + tid;
-      const float sy = sample_y(r);
-      const float fy0 = floorf(sy);
-      const int y0 = static_cast<int>(fy0);
-      const float w1 = sy - fy0;
-      RowInfo ri;
-      ri.y0 = y0;
-      ri.pad = 0;
-      ri.wy0 = (y0 >= 0 && y0 < H) ? 1.0f - w1 : 0.0f;
-      ri.wy1 = (y0 + 1 >= 0 && y0 + 1 < H) ? w1 : 0.0f;
-      ri.ia = (min(max(y0, y_lo), y_hi) - y_lo) * 3 * pitch;
-      ri.ib = (min(max(y0 + 1, y_lo), y_hi) - y_lo) * 3 * pitch;
-      ri.o = out_offset(r - r0) - obase;
-      s_rows[tid] = ri;
-    }
-    __syncthreads();
-
-    if (worker) {
-      const int per = (rb - ra + groups - 1) / groups;
-      const int my_a = ra + pg * per, my_b = min(my_a + per, rb);
-      if (!fits) {  // frame too wide for even two staged rows: direct gather for this chunk
-        for (int r = my_a; r < my_b; ++r) {
-          const float sy = sample_y(r);
-          const long long o = out_offset(r - r0);
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float v0 = direct_sample<TS>(src + c * plane, sample_x(ox), sy, H, W);
-            const float v1 = direct_sample<TS>(src + c * plane, sample_x(ox + 1), sy, H, W);
-            store2(out + o + c * ch_stride, (v0 - a.mean[c]) * a.inv_std[c], (v1 - a.mean[c]) * a.inv_std[c]);
-          }
-        }
-      } else if (constant) {
-        for (int r = my_a; r < my_b; ++r) {
-          const long long o = out_offset(r - r0);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) store2(out + o + c * ch_stride, (0.0f - a.mean[c]) * a.inv_std[c], (0.0f - a.mean[c]) * a.inv_std[c]);
-        }
-      } else {
-        // ---- compute: walk down the rows, the two source rows of the previous output row stay in registers ----
-        const long long col_off = obase;  // (row / patch-row part comes from RowInfo.o, measured from the strip's first row)
-        if (narrow) {
-          strip_rows<true, TD>(stage, s_rows, my_a - ra, my_b - ra, pitch, e[0], wgt[0], wgt[1], col_off, ch_stride, a.mean, a.inv_std, out);
-        } else {  // > 1 source column per output column: each pixel has its own window; one pass per pixel, scalar stores
-          strip_rows<false, TD>(stage, s_rows, my_a - ra, my_b - ra, pitch, e[0], wgt[0], wgt[0], col_off, ch_stride, a.mean, a.inv_std, out);
-          strip_rows<false, TD>(stage, s_rows, my_a - ra, my_b - ra, pitch, e[1], wgt[1], wgt[1], col_off + 1, ch_stride, a.mean, a.inv_std, out);
-        }
-      }
-    }
-    __syncthreads();  // the staging buffer is reused by the next chunk
-    ra = rb;
+  for (int c = 0; c < 3; ++c) {
+    q.k[c][0] = c * plane + x0[0];
+    q.k[c][1] = c * plane + x0[1];
   }
+  const int d = x0[1] - x0[0];
+  const bool narrow = interior && (d == 0 || d == 1) && x0[0] + 2 < W;
+  q.w[0] = w0[0]; q.w[1] = w1[0];
+  if (narrow) {
+    q.w[2] = d ? 0.0f : w0[1];
+    q.w[3] = d ? w0[1] : w1[1];
+    q.w[4] = d ? w1[1] : 0.0f;
+  } else {
+    q.w[2] = w0[1]; q.w[3] = w1[1]; q.w[4] = 0.0f;
+  }
+  __syncthreads();
+  if (ox >= S) return;
+
+  TD* out = reinterpret_cast<TD*>(a.out);
+  long long ch_stride;
+  if (a.patch > 0) {
+    const int px = fast_div(ox, a.patch_magic), ix = ox - px * a.patch;
+    out += (static_cast<long long>(n) * a.G * a.G + px) * a.out_ld + ix;
+    ch_stride = static_cast<long long>(a.patch) * a.patch;
+  } else {
+    out += static_cast<long long>(n) * 3 * S * S + ox;
+    ch_stride = static_cast<long long>(S) * S;
+  }
+  if (narrow) walk_rows<TS, TD, WALK_NARROW>(a, s_rows, nrows, src, q, out, ch_stride);
+  else if (interior) walk_rows<TS, TD, WALK_WIDE>(a, s_rows, nrows, src, q, out, ch_stride);
+  else walk_rows<TS, TD, WALK_EDGE>(a, s_rows, nrows, src, q, out, ch_stride);
 }
 
-// RF_CROP_TILED=1 selects the tiled kernel (read per call so tests can toggle it).  Off by default: its first version is
-// latency-bound in pass V and measured 2.6x slower than the direct gather (profiles/r2_bench_crop_micro_v1_tiled_kernel.json).
-static bool tiled_enabled() {
-  const char* e = getenv("RF_CROP_TILED");
+// RF_CROP_DIRECT=1 selects the round-1 direct gather (read per call so tests and A/B runs can toggle it).
+static bool direct_forced() {
+  const char* e = getenv("RF_CROP_DIRECT");
   return e && e[0] == '1';
 }
 
 template <typename TS, typename TD>
-static int launch_tiled(const RfFovCropParams* p, const Args& a, cudaStream_t s) {
-  TiledArgs ta;
-  ta.a = a;
-  ta.vec2 = (p->W % 2 == 0) && (reinterpret_cast<uintptr_t>(p->frames) % (2 * sizeof(TS)) == 0);
-  const size_t smem = sizeof(float) * STAGE_FLOATS;
-  RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(fov_crop_tiled_kernel<TS, TD>), smem));
-  fov_crop_tiled_kernel<TS, TD><<<dim3(ceil_div(p->out_size, STRIP_ROWS), p->n_frames), TILE_THREADS, smem, s>>>(ta);
+static int launch_walk(const RfFovCropParams* p, const Args& a, cudaStream_t s) {
+  const int threads = ((p->out_size / 2 + 31) / 32) * 32;
+  fov_crop_walk_kernel<TS, TD><<<dim3(ceil_div(p->out_size, WALK_ROWS), p->n_frames), threads, 0, s>>>(a);
   RF_LAUNCH_OK();
   return RF_OK;
 }
 
 template <typename TS>
 static int dispatch_out(const RfFovCropParams* p, const Args& a, cudaStream_t s) {
-  // strip kernel: 2 px per thread -> even S, at most 256 threads per output row
-  if (tiled_enabled() && p->out_size >= 8 && p->out_size <= 2 * TILE_THREADS) {
-    if (p->out_dtype == RF_F32) return launch_tiled<TS, float>(p, a, s);
-    if (p->out_dtype == RF_F16) return launch_tiled<TS, __half>(p, a, s);
-    return launch_tiled<TS, __nv_bfloat16>(p, a, s);
+  // the walker keeps per-frame source and output offsets in signed 32 bits.  Its gain is the re-use of source rows down the
+  // output rows; a frame more than twice as tall as the crop is (for the usual windows of ~half a frame or more) down-sampled,
+  // every output row needs two new source rows and the direct gather with its independent threads is the faster kernel
+  // (full-resolution 1080 x 1088 frames: 0.051 ms direct vs 0.072 ms walker per 128 frames)
+  const long long frame_elems = p->patch > 0 ? static_cast<long long>(a.G) * a.G * p->out_ld : 3ll * p->out_size * p->out_size;
+  const bool walk_forced = getenv("RF_CROP_WALK") && getenv("RF_CROP_WALK")[0] == '1';
+  if (!direct_forced() && frame_elems < (1ll << 31) && 3ll * p->H * p->W + 4 < (1ll << 31) && (p->H <= 2 * p->out_size || walk_forced)) {
+    if (p->out_dtype == RF_F32) return launch_walk<TS, float>(p, a, s);
+    if (p->out_dtype == RF_F16) return launch_walk<TS, __half>(p, a, s);
+    return launch_walk<TS, __nv_bfloat16>(p, a, s);
   }
   const int quads = p->out_size / 4;
   dim3 grid(ceil_div(p->out_size, ROWS_PER_CTA), p->n_frames);

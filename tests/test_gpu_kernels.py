@@ -191,9 +191,10 @@ def test_gemm_dact_and_accumulate(ops):
 @pytest.mark.parametrize("H,W,S,patch", [(324, 326, 224, 28), (86, 384, 256, 32), (36, 34, 32, 8), (240, 320, 64, 0), (37, 35, 32, 8),
                                          (216, 768, 256, 32), (64, 1088, 224, 28)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.uint8])
-@pytest.mark.parametrize("tiled", ["0", "1"])  # direct 4-tap gather (default) / separable shared-memory-staged kernel
-def test_fov_crop(ops, monkeypatch, H, W, S, patch, dtype, tiled):
-    monkeypatch.setenv("RF_CROP_TILED", tiled)
+@pytest.mark.parametrize("direct", ["0", "1"])  # separable column-walker kernel (default) / round-1 direct 4-tap gather
+def test_fov_crop(ops, monkeypatch, H, W, S, patch, dtype, direct):
+    monkeypatch.setenv("RF_CROP_DIRECT", direct)
+    monkeypatch.setenv("RF_CROP_WALK", "1")  # (the walker also for tall frames, which the dispatcher would hand to the direct kernel)
     gen = g(H + W)
     n = 5
     if dtype == torch.uint8:
@@ -225,14 +226,15 @@ def test_fov_crop(ops, monkeypatch, H, W, S, patch, dtype, tiled):
     assert torch.equal(hf.cpu(), got.half())  # same values, rounded to fp16 (the A operand of the fp16 patch GEMM)
 
 
-@pytest.mark.parametrize("tiled", ["0", "1"])
-def test_fov_crop_uint8_frames_like_the_reference_loader(ops, monkeypatch, tiled):
+@pytest.mark.parametrize("direct", ["0", "1"])
+def test_fov_crop_uint8_frames_like_the_reference_loader(ops, monkeypatch, direct):
     """raw uint8 frames staged on the device (half the host->device bytes) and converted inside the crop kernel
     exactly as the reference's loader converts them on the host, `astype(float16) / 255.0` (io/dataset.py:1505-1522): the crop of
     the uint8 frames must equal the crop of the host-converted fp16 frames BIT FOR BIT."""
     import numpy as np
 
-    monkeypatch.setenv("RF_CROP_TILED", tiled)
+    monkeypatch.setenv("RF_CROP_DIRECT", direct)
+    monkeypatch.setenv("RF_CROP_WALK", "1")  # (the walker also for tall frames, which the dispatcher would hand to the direct kernel)
     gen = g(5)
     n, H, W, S, patch = 4, 60, 62, 32, 8
     u8 = torch.randint(0, 256, (n, 3, H, W), generator=gen, dtype=torch.uint8)
@@ -253,11 +255,12 @@ def test_fov_crop_uint8_frames_like_the_reference_loader(ops, monkeypatch, tiled
     assert torch.equal(ident[0, 0].cpu(), want)
 
 
-@pytest.mark.parametrize("tiled", ["0", "1"])
-def test_fov_crop_mirrored_and_offscreen(ops, monkeypatch, tiled):
-    """Windows the tiled kernel special-cases: mirrored (fw < 0: direct gather path), entirely outside the frame (constant
-    tile), touching the left / right / top / bottom border (clamped taps with zero weight)."""
-    monkeypatch.setenv("RF_CROP_TILED", tiled)
+@pytest.mark.parametrize("direct", ["0", "1"])
+def test_fov_crop_mirrored_and_offscreen(ops, monkeypatch, direct):
+    """Windows off the walker kernel's common path: mirrored (fw < 0: sample positions decrease with the index), entirely
+    outside the frame (no loads at all), touching the left / right / top / bottom border (per-tap predicates)."""
+    monkeypatch.setenv("RF_CROP_DIRECT", direct)
+    monkeypatch.setenv("RF_CROP_WALK", "1")  # (the walker also for tall frames, which the dispatcher would hand to the direct kernel)
     gen = g(77)
     H, W, S = 48, 50, 32
     frames = torch.rand(6, 3, H, W, generator=gen).half()

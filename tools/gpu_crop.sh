@@ -1,0 +1,18 @@
+#!/bin/bash
+# FoV crop: parity tests of both kernels, then the crop micro-benchmark with the walker (default) and the direct gather.
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k fov_crop --timeout 300 -p no:cacheprovider > gpurun_out/kernels_fov_crop.log 2>&1
+echo "== fov_crop tests: exit $?"; tail -n 15 gpurun_out/kernels_fov_crop.log
+timeout 300 python bench.py --mode crop_micro > gpurun_out/bench_crop_micro_walk.json 2> gpurun_out/bench_crop_micro_walk.err; echo "walk exit $?"
+RF_CROP_WALK=1 timeout 300 python bench.py --mode crop_micro > gpurun_out/bench_crop_micro_walkall.json 2> /dev/null; echo "walkall exit $?"
+RF_CROP_DIRECT=1 timeout 300 python bench.py --mode crop_micro > gpurun_out/bench_crop_micro_direct.json 2> gpurun_out/bench_crop_micro_direct.err; echo "direct exit $?"
+python - <<'PY'
+import json
+for k in ("walk", "walkall", "direct"):
+    try:
+        d = json.loads(open(f"gpurun_out/bench_crop_micro_{k}.json").read().strip().splitlines()[-1])
+        for r in d["crop"]:
+            print(k, r["case"], r["layout"], r["out_dtype"], r["ms"], r["gbs"], r["frac_of_hbm_peak"])
+    except Exception as e:
+        print(k, "failed", e)
+PY
