@@ -194,13 +194,20 @@ __device__ __forceinline__ void store2(__nv_bfloat16* dst, float a, float b) {
   *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(a, b);
 }
 
-constexpr int WALK_ROWS = 32;     // output rows per CTA
-constexpr int WALK_THREADS = 128; // one thread per pair of adjacent output columns (S <= 256)
+constexpr int WALK_MAX_ROWS = 32;            // output rows per CTA (28 when S is a multiple of 28 only: strips then match patch rows)
+constexpr int WALK_THREADS = 128;            // one thread per pair of adjacent output columns (S <= 256)
+constexpr int WALK_STAGE_BYTES = 26 * 1024;  // staged source window per CTA: 8 CTAs of 128 threads per SM
 struct __align__(16) WalkRow {    // per output row of the CTA's strip, computed once, read as one broadcast 16 B shared load
-  int y0;          // floor of the sample row
+  int code;        // (y0 + 4) | flags << 24;  y0 = floor of the sample row, clamped to [-3, H]
   float wy0, wy1;  // weights of source rows y0 / y0 + 1
   int off;         // output offset of the row inside the frame (elements; the thread adds its column / channel part)
 };
+// flags: what the walk does before it blends this row (relative to the row above it)
+constexpr int WALK_NEW = 1;    // y0 differs from the previous row's: source rows must be loaded
+constexpr int WALK_SHIFT = 2;  // y0 = previous y0 + 1: the previous lower row becomes the upper row, one new row is loaded
+constexpr int WALK_A_IN = 4;   // source row y0 is inside the frame
+constexpr int WALK_B_IN = 8;   // source row y0 + 1 is inside the frame
+__device__ __forceinline__ int walk_y0(int code) { return (code & 0xFFFFFF) - 4; }
 
 // The horizontal blend of one source row for the thread's two output columns, all three channels:
 //   h[c] = (src[c][y][xa] * wa0 + src[c][y][xa + 1] * wa1,  src[c][y][xb] * wb0 + src[c][y][xb + 1] * wb1)
@@ -209,8 +216,8 @@ struct __align__(16) WalkRow {    // per output row of the CTA's strip, computed
 //                loads per channel from one address, the second column's weights laid over the three taps (one of them is 0);
 //   WALK_WIDE  : all four taps inside the frame, any distance: two addresses per channel, immediate offsets;
 //   WALK_EDGE  : taps outside the frame read nothing and contribute exactly zero.
-// Addresses are signed 32-bit element offsets from the frame base (taps left of the frame give small negative offsets that
-// are never dereferenced).
+// Tap addresses are signed 32-bit element offsets (taps left of the frame give negative offsets that are never dereferenced)
+// from the staged window in shared memory (STAGED) or from the frame in global memory.
 constexpr int WALK_NARROW = 0, WALK_WIDE = 1, WALK_EDGE = 2;
 // base + off * sizeof(T) as ONE instruction (the compiler otherwise re-derives the 64-bit frame base for every address)
 template <typename T>
@@ -220,71 +227,97 @@ __device__ __forceinline__ T* at_s32(T* base, int off) {
   return reinterpret_cast<T*>(r);
 }
 struct WalkCols {
-  int k[3][2];       // per channel: c * plane + xa, c * plane + xb
+  int k[2];          // column offsets of xa / xb (elements)
   bool ok[4];        // taps xa, xa+1, xb, xb+1 inside the frame (EDGE)
   float w[5];        // NARROW: wa0, wa1, wb'0, wb'1, wb'2;  otherwise wa0, wa1, wb0, wb1
 };
-// raw (unconverted) taps of one source row, all three channels; a row outside the frame is all zeros
-template <typename TS, int MODE>
-struct WalkTaps { typename RawPx<TS>::type v[3][MODE == WALK_NARROW ? 3 : 4]; };
-template <typename TS, int MODE>
-__device__ __forceinline__ void walk_load(const TS* __restrict__ src, int y, int H, int W, const WalkCols& q, WalkTaps<TS, MODE>& t) {
-  const typename RawPx<TS>::type zero = zero_raw<TS>();
-  if (y >= 0 && y < H) {  // CTA-uniform
-    const int rowoff = y * W;
+// where the taps come from.  Global: frame base pointer, strides in elements.  STAGED: 32-bit shared-memory address of the
+// staged window, strides (and WalkCols::k) in BYTES.
+template <typename TS>
+struct WalkSrc {
+  const typename RawPx<TS>::type* base;
+  unsigned sbase;
+  int y_lo, row_stride, ch_stride;
+};
+// ld.shared with an immediate byte offset (a generic pointer into shared memory makes the compiler re-derive the window base)
+template <int IMM> __device__ __forceinline__ __half lds_px(unsigned addr, __half) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(addr), "n"(IMM));
+  return __ushort_as_half(v);
+}
+template <int IMM> __device__ __forceinline__ float lds_px(unsigned addr, float) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+template <int IMM> __device__ __forceinline__ unsigned char lds_px(unsigned addr, unsigned char) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+  return static_cast<unsigned char>(v);
+}
+template <typename TS, int MODE, bool STAGED>
+__device__ __forceinline__ void walk_row(const WalkSrc<TS>& ws, int rowoff, const WalkCols& q, f32x2 (&h)[3]) {
+  constexpr int NT = MODE == WALK_NARROW ? 3 : 4;
+  typedef typename RawPx<TS>::type Raw;
+  constexpr int ES = sizeof(Raw);
+  Raw t[3][NT];
+  const Raw zero = zero_raw<TS>();
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const TS* pa = at_s32(src, rowoff + q.k[c][0]);
+  for (int c = 0; c < 3; ++c) {
+    const int oa = rowoff + c * ws.ch_stride + q.k[0], ob = rowoff + c * ws.ch_stride + q.k[1];
+    if (STAGED) {
+      const unsigned pa = ws.sbase + oa, pb = ws.sbase + ob;
       if (MODE == WALK_NARROW) {
-        t.v[c][0] = load_raw<TS>(pa); t.v[c][1] = load_raw<TS>(pa + 1); t.v[c][2] = load_raw<TS>(pa + 2);
+        t[c][0] = lds_px<0>(pa, zero); t[c][1] = lds_px<ES>(pa, zero); t[c][2] = lds_px<2 * ES>(pa, zero);
+      } else if (MODE == WALK_EDGE) {
+        t[c][0] = q.ok[0] ? lds_px<0>(pa, zero) : zero; t[c][1] = q.ok[1] ? lds_px<ES>(pa, zero) : zero;
+        t[c][2] = q.ok[2] ? lds_px<0>(pb, zero) : zero; t[c][3] = q.ok[3] ? lds_px<ES>(pb, zero) : zero;
       } else {
-        const TS* pb = at_s32(src, rowoff + q.k[c][1]);
+        t[c][0] = lds_px<0>(pa, zero); t[c][1] = lds_px<ES>(pa, zero);
+        t[c][2] = lds_px<0>(pb, zero); t[c][3] = lds_px<ES>(pb, zero);
+      }
+    } else {
+      const Raw* pa = at_s32(ws.base, oa);
+      if (MODE == WALK_NARROW) {
+        t[c][0] = __ldg(pa); t[c][1] = __ldg(pa + 1); t[c][2] = __ldg(pa + 2);
+      } else {
+        const Raw* pb = at_s32(ws.base, ob);
         if (MODE == WALK_EDGE) {
-          t.v[c][0] = q.ok[0] ? load_raw<TS>(pa) : zero; t.v[c][1] = q.ok[1] ? load_raw<TS>(pa + 1) : zero;
-          t.v[c][2] = q.ok[2] ? load_raw<TS>(pb) : zero; t.v[c][3] = q.ok[3] ? load_raw<TS>(pb + 1) : zero;
+          t[c][0] = q.ok[0] ? __ldg(pa) : zero; t[c][1] = q.ok[1] ? __ldg(pa + 1) : zero;
+          t[c][2] = q.ok[2] ? __ldg(pb) : zero; t[c][3] = q.ok[3] ? __ldg(pb + 1) : zero;
         } else {
-          t.v[c][0] = load_raw<TS>(pa); t.v[c][1] = load_raw<TS>(pa + 1);
-          t.v[c][2] = load_raw<TS>(pb); t.v[c][3] = load_raw<TS>(pb + 1);
+          t[c][0] = __ldg(pa); t[c][1] = __ldg(pa + 1);
+          t[c][2] = __ldg(pb); t[c][3] = __ldg(pb + 1);
         }
       }
     }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int k = 0; k < (MODE == WALK_NARROW ? 3 : 4); ++k) t.v[c][k] = zero;
   }
-}
-template <typename TS, int MODE>
-__device__ __forceinline__ void walk_blend(const WalkTaps<TS, MODE>& t, const WalkCols& q, f32x2 (&h)[3]) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float v[4];
+    float v[NT];
 #pragma unroll
-    for (int k = 0; k < (MODE == WALK_NARROW ? 3 : 4); ++k) v[k] = cvt_px<TS>(t.v[c][k]);
+    for (int k = 0; k < NT; ++k) v[k] = cvt_px<TS>(t[c][k]);
     if (MODE == WALK_NARROW) h[c] = pk(fmaf(v[1], q.w[1], v[0] * q.w[0]), fmaf(v[2], q.w[4], fmaf(v[1], q.w[3], v[0] * q.w[2])));
     else h[c] = pk(fmaf(v[1], q.w[1], v[0] * q.w[0]), fmaf(v[3], q.w[3], v[2] * q.w[2]));
   }
 }
 
-// A CTA owns WALK_ROWS output rows of one frame; a thread owns two adjacent output columns and walks DOWN the rows.
+// Output rows [ra, rb) of the strip for one thread (two adjacent output columns, three channels), walking DOWN the rows.
 // The bilinear resample is separable: the horizontal blend h of a source row (fixed columns and weights for the whole walk)
 // is computed once and stays in registers for every output row that uses it -- an up-sampling crop (0.72 source rows per
-// output row for the gaze window) needs a new source row for ~3 of 4 output rows and shifts the previous one down; the
-// vertical blend, the normalisation and the store are packed f32x2 operations on the column pair.  ~12 instructions per
-// output value against ~40 for the direct 4-tap gather, no shared-memory staging and no barrier after the row table; a warp
-// reads ~100 contiguous bytes per load instruction and writes 128 (fp16 / bf16) or 256 (fp32).
-// The taps of source row cur_y + 2 are always IN FLIGHT while the current output rows are blended and stored (software
-// prefetch into registers): a thread's walk is a serial chain of ~24 source rows, and without it every one of them would
-// expose a full memory round trip.
-// All control flow in the walk is CTA-uniform.  Mirrored windows (fw, fh < 0) take the same code: column taps are per-thread
-// constants of any order, and a row that is neither the current nor the next one simply reloads both source rows.
+// output row for the gaze window) needs a new source row for ~3 of 4 output rows; the vertical blend, the normalisation and
+// the store are packed f32x2 operations on the column pair: ~11 instructions per output value against ~40 for the direct
+// 4-tap gather.  A warp writes 128 (fp16 / bf16) or 256 (fp32) contiguous bytes per store.
+// What happens before a row is blended (nothing / shift + one new source row / two new rows) was decided once per strip and
+// sits in the row table (WalkRow::code): all control flow is CTA-uniform.  The two row blends live in h[0] / h[1] and swap
+// roles at a shift (the loop body exists twice), so a shift moves no registers.
+// Mirrored windows (fw, fh < 0) take the same code: column taps are per-thread constants of any order, and a row that is
+// neither the current nor the next one reloads both source rows.
 // (A NaN pixel in the source can reach one output column more than in the reference: NARROW multiplies its third tap by 0.)
-template <typename TS, typename TD, int MODE>
-__device__ __forceinline__ void walk_rows(const Args& a, const WalkRow* __restrict__ rows, int nrows, const TS* __restrict__ src,
+template <typename TS, typename TD, int MODE, bool STAGED>
+__device__ __forceinline__ void walk_rows(const Args& a, const WalkRow* __restrict__ rows, int ra, int rb, const WalkSrc<TS>& ws,
                                           const WalkCols& q, TD* __restrict__ out0, long long ch_stride) {
-  const int H = a.H, W = a.W;
-  f32x2 hA[3], hB[3];
+  f32x2 h[2][3];
   f32x2 shift[3], istd[3];  // (x - mean) * inv_std as one fused multiply-add
   TD* oc[3];
 #pragma unroll
@@ -293,56 +326,101 @@ __device__ __forceinline__ void walk_rows(const Args& a, const WalkRow* __restri
     istd[c] = pk(a.inv_std[c], a.inv_std[c]);
     oc[c] = out0 + c * ch_stride;
   }
-  int cur_y = -(1 << 30);
-  WalkTaps<TS, MODE> nxt;  // taps of source row cur_y + 2
-#pragma unroll 1
-  for (int r = 0; r < nrows; ++r) {
-    const WalkRow ri = rows[r];
-    if (ri.y0 != cur_y) {
-      if (ri.y0 == cur_y + 1) {
-        hA[0] = hB[0]; hA[1] = hB[1]; hA[2] = hB[2];
-        walk_blend<TS, MODE>(nxt, q, hB);
-      } else {
-        WalkTaps<TS, MODE> ta, tb;
-        walk_load<TS, MODE>(src, ri.y0, H, W, q, ta);
-        walk_load<TS, MODE>(src, ri.y0 + 1, H, W, q, tb);
-        walk_blend<TS, MODE>(ta, q, hA);
-        walk_blend<TS, MODE>(tb, q, hB);
-      }
-      cur_y = ri.y0;
-      walk_load<TS, MODE>(src, cur_y + 2, H, W, q, nxt);
-    }
-    const f32x2 wy0 = pk(ri.wy0, ri.wy0), wy1 = pk(ri.wy1, ri.wy1);
+  auto load = [&](bool in_frame, int rowoff, f32x2 (&dst)[3]) {
+    if (in_frame) walk_row<TS, MODE, STAGED>(ws, rowoff, q, dst);  // CTA-uniform
+    else dst[0] = dst[1] = dst[2] = 0ull;
+  };
+  auto emit = [&](const WalkRow& e, const f32x2 (&hA)[3], const f32x2 (&hB)[3]) {
+    const f32x2 wy0 = pk(e.wy0, e.wy0), wy1 = pk(e.wy1, e.wy1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float2 o = upk(fma2(fma2(hB[c], wy1, mul2(hA[c], wy0)), istd[c], shift[c]));
-      store2(oc[c] + ri.off, o.x, o.y);
+      store2(oc[c] + e.off, o.x, o.y);
     }
+  };
+  int r = ra;
+  WalkRow e = rows[r];
+  {  // the first row of a walk always loads both of its source rows
+    const int rowoff = (walk_y0(e.code) - ws.y_lo) * ws.row_stride;
+    load((e.code >> 24) & WALK_A_IN, rowoff, h[0]);
+    load((e.code >> 24) & WALK_B_IN, rowoff + ws.row_stride, h[1]);
   }
+  // one copy of the loop body per assignment of (upper, lower) source row to (h[A], h[B]); a shift leaves to the other copy
+#define RF_WALK_BODY(A, B)                                                              \
+  for (;;) {                                                                            \
+    emit(e, h[A], h[B]);                                                                \
+    if (++r >= rb) return;                                                              \
+    e = rows[r];                                                                        \
+    const int f = e.code >> 24;                                                         \
+    if (f & WALK_NEW) {                                                                 \
+      const int rowoff = (walk_y0(e.code) - ws.y_lo) * ws.row_stride;                   \
+      if (f & WALK_SHIFT) {                                                             \
+        load(f & WALK_B_IN, rowoff + ws.row_stride, h[A]);                              \
+        break;                                                                          \
+      }                                                                                 \
+      load(f & WALK_A_IN, rowoff, h[A]);                                                \
+      load(f & WALK_B_IN, rowoff + ws.row_stride, h[B]);                                \
+    }                                                                                   \
+  }
+  for (;;) {
+    RF_WALK_BODY(0, 1)
+    RF_WALK_BODY(1, 0)
+  }
+#undef RF_WALK_BODY
+}
+template <typename TS, typename TD, bool STAGED>
+__device__ __forceinline__ void walk_dispatch(int mode, const Args& a, const WalkRow* rows, int ra, int rb, const WalkSrc<TS>& ws,
+                                              const WalkCols& q, TD* out0, long long ch_stride) {
+  if (mode == WALK_NARROW) walk_rows<TS, TD, WALK_NARROW, STAGED>(a, rows, ra, rb, ws, q, out0, ch_stride);
+  else if (mode == WALK_WIDE) walk_rows<TS, TD, WALK_WIDE, STAGED>(a, rows, ra, rb, ws, q, out0, ch_stride);
+  else walk_rows<TS, TD, WALK_EDGE, STAGED>(a, rows, ra, rb, ws, q, out0, ch_stride);
 }
 
-template <typename TS, typename TD>
-__global__ void __launch_bounds__(WALK_THREADS) fov_crop_walk_kernel(const Args a) {
-  __shared__ WalkRow s_rows[WALK_ROWS];
-  const int n = blockIdx.y, r0 = blockIdx.x * WALK_ROWS, tid = threadIdx.x;
+template <int IMM>
+__device__ __forceinline__ void cp_async_4(unsigned smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%2], 4;" ::"r"(smem_dst), "l"(gmem_src), "n"(IMM) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// A CTA owns `strip_rows` output rows of one frame.
+// STAGED: the source window of the strip -- the rows and columns its taps touch, ~25 rows x 3 channels x 330 B for the gaze
+//   crop -- is first copied into shared memory with asynchronous 4-byte copies (cp.async: a warp moves 128 contiguous bytes per
+//   instruction, no registers, no conversion; TMA cannot be used because the 652-byte row pitch of the 326-pixel front frames is
+//   not a multiple of 16), so the walk itself never waits for global memory.  If the window of the strip does not fit
+//   WALK_STAGE_BYTES the strip is processed in chunks of rows.
+// !STAGED: the same walk reading its taps from global memory (rows whose pitch or base is not 4-byte aligned, e.g. raw uint8
+//   frames of 326 pixels).
+template <typename TS, typename TD, bool STAGED>
+__global__ void __launch_bounds__(WALK_THREADS, 8) fov_crop_walk_kernel(const Args a, const int strip_rows) {
+  typedef typename RawPx<TS>::type Raw;
+  extern __shared__ __align__(16) unsigned char walk_stage[];
+  __shared__ WalkRow s_rows[WALK_MAX_ROWS];
+  const int n = blockIdx.y, r0 = blockIdx.x * strip_rows, tid = threadIdx.x;
   const int S = a.S, H = a.H, W = a.W;
-  const int nrows = min(WALK_ROWS, S - r0);
+  const int nrows = min(strip_rows, S - r0);
   const float cx = __ldg(a.centers + 2 * n), cy = __ldg(a.centers + 2 * n + 1);
   const float fw = __ldg(a.windows + 2 * n), fh = __ldg(a.windows + 2 * n + 1);
   const long long src_frame = a.frame_ids ? __ldg(a.frame_ids + n) : n;
   const int plane = H * W;
-  const TS* src = reinterpret_cast<const TS*>(a.frames) + src_frame * 3ll * plane;
+  const Raw* src = reinterpret_cast<const Raw*>(a.frames) + src_frame * 3ll * plane;
   const float inv_s = 1.0f / S;
+  // same expressions as the direct kernel / the oracle
+  auto sample_x = [&](int ox) { return ((fw * ((2 * ox + 1) * inv_s - 1.0f) + (2.0f * cx - 1.0f) + 1.0f) * W - 1.0f) * 0.5f; };
+  auto sample_y = [&](int oy) { return ((fh * ((2 * oy + 1) * inv_s - 1.0f) + (2.0f * cy - 1.0f) + 1.0f) * H - 1.0f) * 0.5f; };
+  // positions far outside the frame all behave like "every tap out": clamped so that +1 / +2 cannot overflow
+  auto floor_clamped = [](float v, int hi) { return static_cast<int>(fminf(fmaxf(floorf(v), -3.0f), static_cast<float>(hi))); };
 
-  if (tid < nrows) {  // the strip's row table; same expressions as the direct kernel / the oracle
+  if (tid < nrows) {  // the strip's row table
     const int oy = r0 + tid;
-    const float gy = (2 * oy + 1) * inv_s - 1.0f;
-    const float sy = ((fh * gy + (2.0f * cy - 1.0f) + 1.0f) * H - 1.0f) * 0.5f;
-    const float fy0 = floorf(sy);
+    const float sy = sample_y(oy);
+    const int y0 = floor_clamped(sy, H), yp = floor_clamped(sample_y(oy - 1), H);
+    const int flags = (y0 != yp ? WALK_NEW : 0) | (y0 == yp + 1 ? WALK_SHIFT : 0) | (y0 >= 0 && y0 < H ? WALK_A_IN : 0) |
+                      (y0 + 1 >= 0 && y0 + 1 < H ? WALK_B_IN : 0);
     WalkRow ri;
-    // rows far outside the frame all behave like "both taps out": clamped so that y0 + 1 cannot overflow
-    ri.y0 = static_cast<int>(fminf(fmaxf(fy0, -3.0f), static_cast<float>(H)));
-    ri.wy1 = sy - fy0;
+    ri.code = (y0 + 4) | (flags << 24);
+    ri.wy1 = sy - floorf(sy);
     ri.wy0 = 1.0f - ri.wy1;
     if (a.patch > 0) {
       const int py = fast_div(oy, a.patch_magic), iy = oy - py * a.patch;
@@ -361,23 +439,17 @@ __global__ void __launch_bounds__(WALK_THREADS) fov_crop_walk_kernel(const Args 
   bool interior = true;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const float gx = (2 * (ox + i) + 1) * inv_s - 1.0f;
-    const float sx = ((fw * gx + (2.0f * cx - 1.0f) + 1.0f) * W - 1.0f) * 0.5f;
-    const float fx0 = floorf(sx);
-    x0[i] = static_cast<int>(fminf(fmaxf(fx0, -2.0f), static_cast<float>(W)));
-    w1[i] = sx - fx0;
+    const float sx = sample_x(ox + i);
+    x0[i] = floor_clamped(sx, W);
+    w1[i] = sx - floorf(sx);
     w0[i] = 1.0f - w1[i];
     q.ok[2 * i] = x0[i] >= 0 && x0[i] < W;
     q.ok[2 * i + 1] = x0[i] + 1 >= 0 && x0[i] + 1 < W;
     interior = interior && q.ok[2 * i] && q.ok[2 * i + 1];
   }
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    q.k[c][0] = c * plane + x0[0];
-    q.k[c][1] = c * plane + x0[1];
-  }
   const int d = x0[1] - x0[0];
   const bool narrow = interior && (d == 0 || d == 1) && x0[0] + 2 < W;
+  const int mode = narrow ? WALK_NARROW : (interior ? WALK_WIDE : WALK_EDGE);
   q.w[0] = w0[0]; q.w[1] = w1[0];
   if (narrow) {
     q.w[2] = d ? 0.0f : w0[1];
@@ -386,34 +458,114 @@ __global__ void __launch_bounds__(WALK_THREADS) fov_crop_walk_kernel(const Args 
   } else {
     q.w[2] = w0[1]; q.w[3] = w1[1]; q.w[4] = 0.0f;
   }
-  __syncthreads();
-  if (ox >= S) return;
 
   TD* out = reinterpret_cast<TD*>(a.out);
   long long ch_stride;
   if (a.patch > 0) {
-    const int px = fast_div(ox, a.patch_magic), ix = ox - px * a.patch;
+    const int px = fast_div(min(ox, S - 2), a.patch_magic), ix = ox - px * a.patch;
     out += (static_cast<long long>(n) * a.G * a.G + px) * a.out_ld + ix;
     ch_stride = static_cast<long long>(a.patch) * a.patch;
   } else {
     out += static_cast<long long>(n) * 3 * S * S + ox;
     ch_stride = static_cast<long long>(S) * S;
   }
-  if (narrow) walk_rows<TS, TD, WALK_NARROW>(a, s_rows, nrows, src, q, out, ch_stride);
-  else if (interior) walk_rows<TS, TD, WALK_WIDE>(a, s_rows, nrows, src, q, out, ch_stride);
-  else walk_rows<TS, TD, WALK_EDGE>(a, s_rows, nrows, src, q, out, ch_stride);
+  const bool worker = ox < S;
+
+  if (!STAGED) {
+    __syncthreads();
+    if (!worker) return;
+    WalkSrc<TS> ws;
+    ws.base = src; ws.sbase = 0; ws.y_lo = 0; ws.row_stride = W; ws.ch_stride = plane;
+    q.k[0] = x0[0]; q.k[1] = x0[1];
+    walk_dispatch<TS, TD, false>(mode, a, s_rows, 0, nrows, ws, q, out, ch_stride);
+    return;
+  }
+
+  // ---- staged: columns [j_lo, j_hi] of the frame that the strip's taps touch, first column on a 4-byte boundary ----
+  constexpr int ES = sizeof(Raw), EPW = 4 / ES;  // elements per 4-byte word
+  const int xf = floor_clamped(sample_x(0), W), xl = floor_clamped(sample_x(S - 1), W);
+  const int j_lo = (max(min(xf, xl), 0) / EPW) * EPW;
+  const int j_hi = min(max(xf, xl) + 2, W - 1);
+  const int words = j_hi >= j_lo ? (j_hi - j_lo + EPW) / EPW : 0;  // 4-byte words per staged line
+  const int pitch_b = 4 * words;                                    // bytes
+  const int rows_fit = words > 0 ? WALK_STAGE_BYTES / (3 * pitch_b) : (1 << 20);
+  q.k[0] = (x0[0] - j_lo) * ES; q.k[1] = (x0[1] - j_lo) * ES;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const bool cp0 = lane < words, cp1 = lane + 32 < words, cp2 = lane + 64 < words, cp3 = lane + 96 < words;
+  unsigned stage_addr = static_cast<unsigned>(__cvta_generic_to_shared(walk_stage));
+  asm volatile("" : "+r"(stage_addr));  // keep it in a register (the compiler would re-derive it from %cluster_ctaid in the walk)
+  __syncthreads();  // row table
+
+  int ra = 0;
+  while (ra < nrows) {  // chunks of output rows whose source rows fit the staging buffer (CTA-uniform; normally one)
+    int lo = walk_y0(s_rows[ra].code), hi = lo, rb;
+    {
+      const int ye = walk_y0(s_rows[nrows - 1].code);  // sample rows are monotone in the row index: the extremes are at the ends
+      const int l2 = min(lo, ye), h2 = max(hi, ye);
+      if (min(max(h2 + 1, 0), H - 1) - min(max(l2, 0), H - 1) + 1 <= rows_fit) {
+        lo = l2; hi = h2; rb = nrows;
+      } else {
+        rb = ra + 1;
+        while (rb < nrows) {
+          const int y = walk_y0(s_rows[rb].code);
+          const int nl = min(lo, y), nh = max(hi, y);
+          if (min(max(nh + 1, 0), H - 1) - min(max(nl, 0), H - 1) + 1 > rows_fit) break;
+          lo = nl; hi = nh; ++rb;
+        }
+      }
+    }
+    const bool any_row = hi + 1 >= 0 && lo < H;  // else every source row of the chunk is outside the frame: nothing to stage
+    const int y_lo = min(max(lo, 0), H - 1), y_hi = min(max(hi + 1, 0), H - 1);
+    const int n_src = y_hi - y_lo + 1;
+    if (any_row && words > 0) {
+      // one (row, channel) line per warp pass; lane l copies words l, l+32, l+64, l+96 (predicates fixed for the whole kernel)
+      for (int c = 0; c < 3; ++c) {
+        const unsigned char* g = reinterpret_cast<const unsigned char*>(src + (c * plane + (y_lo + warp) * W + j_lo)) + 4 * lane;
+        unsigned sa = stage_addr + static_cast<unsigned>(c * n_src + warp) * pitch_b + 4 * lane;
+        for (int yr = warp; yr < n_src; yr += nwarps, g += nwarps * W * ES, sa += nwarps * pitch_b) {
+          if (cp0) cp_async_4<0>(sa, g);
+          if (cp1) cp_async_4<128>(sa, g);
+          if (cp2) cp_async_4<256>(sa, g);
+          if (cp3) cp_async_4<384>(sa, g);
+          for (int wd = lane + 128; wd < words; wd += 32) cp_async_4<0>(sa + 4 * (wd - lane), g + 4 * (wd - lane));  // very wide windows
+        }
+      }
+      cp_async_wait_all();
+    }
+    __syncthreads();
+    if (worker) {
+      WalkSrc<TS> ws;
+      ws.base = nullptr; ws.sbase = stage_addr; ws.y_lo = y_lo; ws.row_stride = pitch_b; ws.ch_stride = n_src * pitch_b;
+      walk_dispatch<TS, TD, true>(mode, a, s_rows, ra, rb, ws, q, out, ch_stride);
+    }
+    ra = rb;
+    if (ra < nrows) __syncthreads();  // the staging buffer is reused by the next chunk
+  }
 }
 
-// RF_CROP_DIRECT=1 selects the round-1 direct gather (read per call so tests and A/B runs can toggle it).
-static bool direct_forced() {
-  const char* e = getenv("RF_CROP_DIRECT");
+// RF_CROP_DIRECT=1 selects the round-1 direct gather, RF_CROP_NOSTAGE=1 the walker without shared-memory staging (read per
+// call so tests and A/B runs can toggle them).
+static bool env_on(const char* name) {
+  const char* e = getenv(name);
   return e && e[0] == '1';
 }
 
 template <typename TS, typename TD>
 static int launch_walk(const RfFovCropParams* p, const Args& a, cudaStream_t s) {
-  const int threads = ((p->out_size / 2 + 31) / 32) * 32;
-  fov_crop_walk_kernel<TS, TD><<<dim3(ceil_div(p->out_size, WALK_ROWS), p->n_frames), threads, 0, s>>>(a);
+  const int S = p->out_size;
+  const int strip = (S % 32 != 0 && S % 28 == 0) ? 28 : WALK_MAX_ROWS;
+  const int threads = ((S / 2 + 31) / 32) * 32;
+  const dim3 grid(ceil_div(S, strip), p->n_frames);
+  const size_t es = sizeof(typename RawPx<TS>::type);
+  // cp.async moves 4-byte words: frame base and row pitch must be 4-byte aligned, and two staged rows must fit
+  const bool staged = !env_on("RF_CROP_NOSTAGE") && reinterpret_cast<uintptr_t>(p->frames) % 4 == 0 && (p->W * es) % 4 == 0 &&
+                      6 * (p->W * es + 8) <= static_cast<size_t>(WALK_STAGE_BYTES);
+  if (staged) {
+    RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(fov_crop_walk_kernel<TS, TD, true>), WALK_STAGE_BYTES));
+    fov_crop_walk_kernel<TS, TD, true><<<grid, threads, WALK_STAGE_BYTES, s>>>(a, strip);
+  } else {
+    fov_crop_walk_kernel<TS, TD, false><<<grid, threads, 0, s>>>(a, strip);
+  }
   RF_LAUNCH_OK();
   return RF_OK;
 }
@@ -425,8 +577,8 @@ static int dispatch_out(const RfFovCropParams* p, const Args& a, cudaStream_t s)
   // every output row needs two new source rows and the direct gather with its independent threads is the faster kernel
   // (full-resolution 1080 x 1088 frames: 0.051 ms direct vs 0.072 ms walker per 128 frames)
   const long long frame_elems = p->patch > 0 ? static_cast<long long>(a.G) * a.G * p->out_ld : 3ll * p->out_size * p->out_size;
-  const bool walk_forced = getenv("RF_CROP_WALK") && getenv("RF_CROP_WALK")[0] == '1';
-  if (!direct_forced() && frame_elems < (1ll << 31) && 3ll * p->H * p->W + 4 < (1ll << 31) && (p->H <= 2 * p->out_size || walk_forced)) {
+  const bool walk_forced = env_on("RF_CROP_WALK");
+  if (!env_on("RF_CROP_DIRECT") && frame_elems < (1ll << 31) && 3ll * p->H * p->W + 4 < (1ll << 31) && (p->H <= 2 * p->out_size || walk_forced)) {
     if (p->out_dtype == RF_F32) return launch_walk<TS, float>(p, a, s);
     if (p->out_dtype == RF_F16) return launch_walk<TS, __half>(p, a, s);
     return launch_walk<TS, __nv_bfloat16>(p, a, s);

@@ -188,13 +188,23 @@ def test_gemm_dact_and_accumulate(ops):
 
 
 # ------------------------------------------------------------------------------------------------ FoV crop
+# the three crop kernels: separable column walker with cp.async-staged source window (default), the same walk reading global
+# memory (unaligned frames), and the round-1 direct 4-tap gather (tall frames)
+CROP_KERNELS = ["staged", "walk", "direct"]
+
+
+def select_crop_kernel(monkeypatch, kernel):
+    monkeypatch.setenv("RF_CROP_DIRECT", "1" if kernel == "direct" else "0")
+    monkeypatch.setenv("RF_CROP_NOSTAGE", "1" if kernel == "walk" else "0")
+    monkeypatch.setenv("RF_CROP_WALK", "1")  # (the walker also for tall frames, which the dispatcher would hand to the direct kernel)
+
+
 @pytest.mark.parametrize("H,W,S,patch", [(324, 326, 224, 28), (86, 384, 256, 32), (36, 34, 32, 8), (240, 320, 64, 0), (37, 35, 32, 8),
                                          (216, 768, 256, 32), (64, 1088, 224, 28)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.uint8])
-@pytest.mark.parametrize("direct", ["0", "1"])  # separable column-walker kernel (default) / round-1 direct 4-tap gather
-def test_fov_crop(ops, monkeypatch, H, W, S, patch, dtype, direct):
-    monkeypatch.setenv("RF_CROP_DIRECT", direct)
-    monkeypatch.setenv("RF_CROP_WALK", "1")  # (the walker also for tall frames, which the dispatcher would hand to the direct kernel)
+@pytest.mark.parametrize("kernel", CROP_KERNELS)
+def test_fov_crop(ops, monkeypatch, H, W, S, patch, dtype, kernel):
+    select_crop_kernel(monkeypatch, kernel)
     gen = g(H + W)
     n = 5
     if dtype == torch.uint8:
@@ -226,15 +236,14 @@ def test_fov_crop(ops, monkeypatch, H, W, S, patch, dtype, direct):
     assert torch.equal(hf.cpu(), got.half())  # same values, rounded to fp16 (the A operand of the fp16 patch GEMM)
 
 
-@pytest.mark.parametrize("direct", ["0", "1"])
-def test_fov_crop_uint8_frames_like_the_reference_loader(ops, monkeypatch, direct):
+@pytest.mark.parametrize("kernel", CROP_KERNELS)
+def test_fov_crop_uint8_frames_like_the_reference_loader(ops, monkeypatch, kernel):
     """raw uint8 frames staged on the device (half the host->device bytes) and converted inside the crop kernel
     exactly as the reference's loader converts them on the host, `astype(float16) / 255.0` (io/dataset.py:1505-1522): the crop of
     the uint8 frames must equal the crop of the host-converted fp16 frames BIT FOR BIT."""
     import numpy as np
 
-    monkeypatch.setenv("RF_CROP_DIRECT", direct)
-    monkeypatch.setenv("RF_CROP_WALK", "1")  # (the walker also for tall frames, which the dispatcher would hand to the direct kernel)
+    select_crop_kernel(monkeypatch, kernel)
     gen = g(5)
     n, H, W, S, patch = 4, 60, 62, 32, 8
     u8 = torch.randint(0, 256, (n, 3, H, W), generator=gen, dtype=torch.uint8)
@@ -255,12 +264,11 @@ def test_fov_crop_uint8_frames_like_the_reference_loader(ops, monkeypatch, direc
     assert torch.equal(ident[0, 0].cpu(), want)
 
 
-@pytest.mark.parametrize("direct", ["0", "1"])
-def test_fov_crop_mirrored_and_offscreen(ops, monkeypatch, direct):
+@pytest.mark.parametrize("kernel", CROP_KERNELS)
+def test_fov_crop_mirrored_and_offscreen(ops, monkeypatch, kernel):
     """Windows off the walker kernel's common path: mirrored (fw < 0: sample positions decrease with the index), entirely
     outside the frame (no loads at all), touching the left / right / top / bottom border (per-tap predicates)."""
-    monkeypatch.setenv("RF_CROP_DIRECT", direct)
-    monkeypatch.setenv("RF_CROP_WALK", "1")  # (the walker also for tall frames, which the dispatcher would hand to the direct kernel)
+    select_crop_kernel(monkeypatch, kernel)
     gen = g(77)
     H, W, S = 48, 50, 32
     frames = torch.rand(6, 3, H, W, generator=gen).half()
