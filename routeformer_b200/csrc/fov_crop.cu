@@ -327,7 +327,8 @@ __device__ __forceinline__ void walk_rows(const Args& a, const WalkRow* __restri
     oc[c] = out0 + c * ch_stride;
   }
   auto load = [&](bool in_frame, int rowoff, f32x2 (&dst)[3]) {
-    if (in_frame) walk_row<TS, MODE, STAGED>(ws, rowoff, q, dst);  // CTA-uniform
+    // (CTA-uniform; the staged window holds zero lines for the rows outside the frame: no test at all)
+    if (STAGED || in_frame) walk_row<TS, MODE, STAGED>(ws, rowoff, q, dst);
     else dst[0] = dst[1] = dst[2] = 0ull;
   };
   auto emit = [&](const WalkRow& e, const f32x2 (&hA)[3], const f32x2 (&hB)[3]) {
@@ -502,32 +503,36 @@ __global__ void __launch_bounds__(WALK_THREADS, 8) fov_crop_walk_kernel(const Ar
     {
       const int ye = walk_y0(s_rows[nrows - 1].code);  // sample rows are monotone in the row index: the extremes are at the ends
       const int l2 = min(lo, ye), h2 = max(hi, ye);
-      if (min(max(h2 + 1, 0), H - 1) - min(max(l2, 0), H - 1) + 1 <= rows_fit) {
+      if (h2 + 1 - l2 + 1 <= rows_fit) {
         lo = l2; hi = h2; rb = nrows;
       } else {
         rb = ra + 1;
         while (rb < nrows) {
           const int y = walk_y0(s_rows[rb].code);
           const int nl = min(lo, y), nh = max(hi, y);
-          if (min(max(nh + 1, 0), H - 1) - min(max(nl, 0), H - 1) + 1 > rows_fit) break;
+          if (nh + 1 - nl + 1 > rows_fit) break;
           lo = nl; hi = nh; ++rb;
         }
       }
     }
-    const bool any_row = hi + 1 >= 0 && lo < H;  // else every source row of the chunk is outside the frame: nothing to stage
-    const int y_lo = min(max(lo, 0), H - 1), y_hi = min(max(hi + 1, 0), H - 1);
-    const int n_src = y_hi - y_lo + 1;
-    if (any_row && words > 0) {
+    // staged rows [y_lo, y_lo + n_src): y0 is clamped to [-3, H], so at most a few of them lie outside the frame; those become
+    // zero lines, and the walk needs no row test
+    const int y_lo = lo, n_src = hi + 1 - lo + 1;
+    if (words > 0) {
       // one (row, channel) line per warp pass; lane l copies words l, l+32, l+64, l+96 (predicates fixed for the whole kernel)
       for (int c = 0; c < 3; ++c) {
         const unsigned char* g = reinterpret_cast<const unsigned char*>(src + (c * plane + (y_lo + warp) * W + j_lo)) + 4 * lane;
         unsigned sa = stage_addr + static_cast<unsigned>(c * n_src + warp) * pitch_b + 4 * lane;
         for (int yr = warp; yr < n_src; yr += nwarps, g += nwarps * W * ES, sa += nwarps * pitch_b) {
-          if (cp0) cp_async_4<0>(sa, g);
-          if (cp1) cp_async_4<128>(sa, g);
-          if (cp2) cp_async_4<256>(sa, g);
-          if (cp3) cp_async_4<384>(sa, g);
-          for (int wd = lane + 128; wd < words; wd += 32) cp_async_4<0>(sa + 4 * (wd - lane), g + 4 * (wd - lane));  // very wide windows
+          if (y_lo + yr >= 0 && y_lo + yr < H) {  // warp-uniform
+            if (cp0) cp_async_4<0>(sa, g);
+            if (cp1) cp_async_4<128>(sa, g);
+            if (cp2) cp_async_4<256>(sa, g);
+            if (cp3) cp_async_4<384>(sa, g);
+            for (int wd = lane + 128; wd < words; wd += 32) cp_async_4<0>(sa + 4 * (wd - lane), g + 4 * (wd - lane));  // very wide windows
+          } else {
+            for (int wd = lane; wd < words; wd += 32) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa + 4 * (wd - lane)), "r"(0) : "memory");
+          }
         }
       }
       cp_async_wait_all();
