@@ -77,7 +77,7 @@ typedef struct {
 int rf_fov_crop(const RfFovCropParams* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * (2) Tensor-core GEMM (tcgen05.mma kind::tf32, or kind::f16 for fp16 operands; TMA-fed, TMEM accumulators, fp32 accumulate)
+ * (2) Tensor-core GEMM (tcgen05.mma kind::tf32, or kind::f16 for fp16 / bf16 operands; TMA-fed, TMEM accumulators, fp32 accumulate)
  * replaces: every aten::addmm / mm / 1x1 aten::convolution on the path:
  *           cross_modal_transformer.py:177-198,297-299,356-368; SelfAttentionFamily.py:176-194;
  *           TransformerEncoderDecoder.py:12-18,48-50; Embedding.py:32-45; and their autograd.
@@ -106,14 +106,18 @@ typedef struct {
                                                 non-accumulating calls are never split.  >1 = explicit (accumulate=1 only) */
   int out_group_in, out_group_out, out_row_offset; /* if out_group_in>0: row m is stored at (m/gi)*go + m%gi + offset */
   int round_f16;                             /* 1: round the result through fp16 (backbone plugin returns input dtype) */
-  int ab_dtype;                              /* RF_F32: A, B are fp32, multiplied as TF32 (kind::tf32).  RF_F16: A, B point to fp16
-                                                (kind::f16, fp32 accumulate; the reference backbone runs under fp16 autocast,
-                                                TimmBackbone.py:106-145); K-major operands only, pitches multiples of 8 */
+  int ab_dtype;                              /* RF_F32: A, B are fp32, multiplied as TF32 (kind::tf32).  RF_F16 / RF_BF16: A, B point to
+                                                fp16 / bf16 (kind::f16, fp32 accumulate; the reference backbone runs under fp16
+                                                autocast, TimmBackbone.py:106-145; bf16 = the north star's "bf16 operands" mode);
+                                                K-major operands only, pitches multiples of 8 */
   float* colsum_a;                           /* optional [K]: colsum_a[k] += sum_m A[m][k] (fp32, K-major A, no split-K).  In a dgrad
                                                 call A is the output gradient, so this is the bias gradient of the producing
                                                 layer, taken from the operand tiles already in shared memory instead of a
                                                 second pass over A (short reductions: sums of the TF32-rounded tiles; otherwise a separate
                                                 fp32 kernel runs) */
+  int c_dtype;                               /* RF_F32 (0, default): C is fp32.  RF_BF16: C points to bf16 and ldc counts bf16 elements
+                                                (the result is rounded once, after the epilogue; 16-bit operands only, no accumulate /
+                                                preact): lets a producer hand its output to the next GEMM as a bf16 operand */
 } RfGemmParams;
 int rf_gemm_tf32(const RfGemmParams* p, void* stream);
 /* Profiling hook: installs (or clears with NULL) a device buffer of >= 8 u64; CTA (0,0,0) of every later GEMM launch records

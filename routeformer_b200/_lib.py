@@ -38,7 +38,7 @@ class RfGemmParams(C.Structure):
         ("dact_aux", c_fp), ("ld_aux", c_ll), ("dact", C.c_int),
         ("accumulate", C.c_int), ("split_k", C.c_int),
         ("out_group_in", C.c_int), ("out_group_out", C.c_int), ("out_row_offset", C.c_int),
-        ("round_f16", C.c_int), ("ab_dtype", C.c_int), ("colsum_a", c_fp),
+        ("round_f16", C.c_int), ("ab_dtype", C.c_int), ("colsum_a", c_fp), ("c_dtype", C.c_int),
     ]
 
 

@@ -91,7 +91,11 @@ class PatchEmbedBackbone(VideoBackboneModule):
         # uint8 clips (raw frames staged on the device: half the host->device bytes) are converted in the crop kernel exactly as the
         # reference's loader converts them on the host (fp16(v / 255), io/dataset.py:1505-1522) and then follow the fp16 path.
         half = all(v["video"].dtype in (torch.float16, torch.uint8) for v in views) and not self.proj.weight.requires_grad
-        patches = torch.empty(n_total * G * G, 3 * p * p, device=dev, dtype=torch.float16 if half else torch.float32)
+        # bf16 operand mode (ops.bf16_operands): bf16 patches x bf16 weight; in inference the features are also STORED in bf16 for
+        # the frame encoder's token convolution (the autograd path keeps fp32 features for the weight gradient)
+        bf16 = half and ops.BF16_MODE
+        op_dtype = torch.bfloat16 if bf16 else (torch.float16 if half else torch.float32)
+        patches = torch.empty(n_total * G * G, 3 * p * p, device=dev, dtype=op_dtype)
         row = 0
         round_f16 = True
         for v in views:
@@ -106,28 +110,30 @@ class PatchEmbedBackbone(VideoBackboneModule):
             else:
                 centers, windows = self._frame_fov(n, H, W, dev)
             ops.fov_crop(video, centers, windows, S, c.mean, c.std, patch=p, frame_ids=ids, n_frames=n,
-                         out=patches[row * G * G:(row + n) * G * G], u8_as_f16=half)
+                         out=patches[row * G * G:(row + n) * G * G], out_dtype=op_dtype, u8_as_f16=half)
             round_f16 = round_f16 and video.dtype in (torch.float16, torch.uint8)
             row += n
         # the plugin returns features in the input dtype (fp16 video -> fp16 features, TimmBackbone.py:141-143)
         if torch.is_grad_enabled() and self.proj.weight.requires_grad:  # train_backbone: fp32 patches, TF32 GEMM, weight gradient
             from . import functional as Fn
             return Fn.PatchEmbed.apply(patches, self.proj.weight, self.proj.bias, G * G, round_f16)
-        tokens = torch.empty(n_total * (G * G + 1), C, device=dev, dtype=torch.float32)
+        bf16_features = bf16 and not torch.is_grad_enabled()
+        tokens = torch.empty(n_total * (G * G + 1), C, device=dev, dtype=torch.bfloat16 if bf16_features else torch.float32)
         tokens.view(n_total, G * G + 1, C)[:, G * G, :] = -1.0
-        ops.gemm(patches, self._weight_matrix(half), tokens, bias=self.proj.bias, out_group=(G * G, G * G + 1, 0), round_f16=round_f16)
+        ops.gemm(patches, self._weight_matrix(op_dtype), tokens, bias=self.proj.bias, out_group=(G * G, G * G + 1, 0),
+                 round_f16=round_f16 and not bf16)
         return tokens
 
-    def _weight_matrix(self, half: bool) -> torch.Tensor:
-        """[C, 3*p*p] view of the projection weight; for the fp16 path a cached fp16 copy, refreshed when the weight changes."""
+    def _weight_matrix(self, dtype: torch.dtype) -> torch.Tensor:
+        """[C, 3*p*p] view of the projection weight; for the 16-bit paths a cached copy, refreshed when the weight changes."""
         w = self.proj.weight
         mat = w.view(w.shape[0], -1)
-        if not half:
+        if dtype == torch.float32:
             return mat
-        key = (w.data_ptr(), w._version)
+        key = (w.data_ptr(), w._version, dtype)
         cached = getattr(self, "_w16", None)
         if cached is None or cached[0] != key:
-            self._w16 = (key, mat.detach().to(torch.float16).contiguous())
+            self._w16 = (key, mat.detach().to(dtype).contiguous())
         return self._w16[1]
 
     def forward(self, images: torch.Tensor) -> torch.Tensor:

@@ -22,6 +22,7 @@
 // with a linear epilogue), programmatic dependent launch.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -61,7 +62,8 @@ struct Args {
   int kb_total, kb_per_split;
   int split_epilogue;  // split-K of a GEMM with a LINEAR epilogue: bias / rowadd / residual are added by split 0 only
   float* colsum_a;  // persistent kernel: += column sums of A taken from the operand tiles in shared memory
-  int f16;  // operands are fp16 (kind::f16, 64 elements per 128 B k-block row) instead of fp32 read as tf32
+  int f16;  // operands are 16-bit (kind::f16, 64 elements per 128 B k-block row) instead of fp32 read as tf32: 1 = fp16, 2 = bf16
+  int c_bf16;  // C holds bf16 (direct stores only)
   int group_in, group_out, row_offset;
   int round_f16;
   int tma_store;  // 1: epilogue stages 128x32 chunks in (swizzled) smem and writes them with TMA bulk stores
@@ -219,7 +221,7 @@ struct RowEpilogue {
     add_linear = !a.split_epilogue || z == 0;
     long long out_row = m;
     if (a.group_in > 0) out_row = static_cast<long long>(m / a.group_in) * a.group_out + (m % a.group_in) + a.row_offset;
-    c_row = a.C + out_row * a.ldc;
+    c_row = a.c_bf16 ? reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(a.C) + out_row * a.ldc) : a.C + out_row * a.ldc;
     rowadd_row = (a.rowadd && add_linear) ? a.rowadd + static_cast<long long>(m % a.rowadd_period) * a.ld_rowadd : nullptr;
     res_row = (a.residual && add_linear) ? a.residual + static_cast<long long>(m) * a.ld_res : nullptr;
     pre_row = a.preact ? a.preact + static_cast<long long>(m) * a.ld_pre : nullptr;
@@ -318,6 +320,25 @@ struct RowEpilogue {
         if (j < ncols) pre_row[nb + j] = pre[j];
     }
     const bool vec_ok = ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0) && !a.accumulate;
+    if (a.c_bf16) {  // c_row was formed with ldc counted in bf16 elements (init)
+      __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(c_row) + nb;
+      if (ncols == 32 && ((a.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0) && ((nb & 7) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 u;
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+          u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
+          u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
+          *reinterpret_cast<uint4*>(crow + j) = u;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) crow[j] = __float2bfloat16_rn(v[j]);
+      }
+      return;
+    }
     if (a.accumulate) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -417,8 +438,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D fp32; A/B format tf32 (2) or f16 (0); major-ness; N >> 3; M >> 4
-      const uint32_t fmt = a.f16 ? 0u : 2u;
+      // instruction descriptor: D fp32; A/B format tf32 (2), f16 (0) or bf16 (1); major-ness; N >> 3; M >> 4
+      const uint32_t fmt = a.f16 == 1 ? 0u : (a.f16 == 2 ? 1u : 2u);
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) |
                              (static_cast<uint32_t>(a.a_mn) << 15) | (static_cast<uint32_t>(a.b_mn) << 16) |
                              (static_cast<uint32_t>(BLOCK_N >> 3) << 17) | (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
@@ -856,7 +877,7 @@ static CUtensorMapL2promotion l2_promotion() {  // RF_TMA_L2_PROMO=0..3: none / 
 // fp32 tensor map of rank 2 or 3: dim0 = `inner` contiguous elements (box 32 = 128 B), dim1 = rows of pitch ld (box box_rows),
 // optional dim2 = groups of pitch ld2 (box box_groups).  `round_tf32`: TFLOAT32 type (operands are rounded RN on load).
 static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_rows, bool mn_major,
-                    bool round_tf32 = true, long long groups = 0, long long ld2 = 0, int box_groups = 0, bool f16 = false) {
+                    bool round_tf32 = true, long long groups = 0, long long ld2 = 0, int box_groups = 0, int f16 = 0) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -868,7 +889,7 @@ static int make_map(CUtensorMap* map, const float* base, long long inner, long l
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * esize, static_cast<cuuint64_t>(ld2) * esize};
   cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / esize), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_groups)};
   cuuint32_t estr[3] = {1, 1, 1};
-  const CUtensorMapDataType dtype = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+  const CUtensorMapDataType dtype = f16 == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : f16 == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                         : ((round_tf32 && tf32_round_in_tma()) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   CUresult r = fn(map, dtype, rank,
                   const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -887,7 +908,7 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
   using T = Tile<BLOCK_N>;
   CUtensorMap tmA, tmB;
   int rc;
-  const bool f16 = args.f16 != 0;
+  const int f16 = args.f16;
   if (!p->a_mn_major) rc = make_map(&tmA, p->A, p->K, p->M, p->lda, BLOCK_M, false, true, 0, 0, 0, f16);
   else rc = make_map(&tmA, p->A, p->M, p->K, p->lda, 32, true);
   if (rc != RF_OK) return rc;
@@ -990,12 +1011,15 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   RF_CHECK_ARG(p != nullptr, "rf_gemm_tf32: null params");
   RF_CHECK_ARG(p->M > 0 && p->N > 0 && p->K > 0, "rf_gemm_tf32: empty problem M=%d N=%d K=%d", p->M, p->N, p->K);
   RF_CHECK_ARG(p->A && p->B && p->C, "rf_gemm_tf32: null operand");
-  RF_CHECK_ARG(p->ab_dtype == RF_F32 || p->ab_dtype == RF_F16, "rf_gemm_tf32: ab_dtype must be RF_F32 or RF_F16");
-  const bool f16 = p->ab_dtype == RF_F16;
+  RF_CHECK_ARG(p->ab_dtype == RF_F32 || p->ab_dtype == RF_F16 || p->ab_dtype == RF_BF16, "rf_gemm_tf32: ab_dtype must be RF_F32, RF_F16 or RF_BF16");
+  const bool f16 = p->ab_dtype != RF_F32;  // 16-bit operands
+  RF_CHECK_ARG(p->c_dtype == RF_F32 || p->c_dtype == RF_BF16, "rf_gemm_tf32: c_dtype must be RF_F32 or RF_BF16");
+  RF_CHECK_ARG(p->c_dtype == RF_F32 || (f16 && !p->accumulate && !p->preact && p->split_k <= 1),
+               "rf_gemm_tf32: a bf16 C needs 16-bit operands, no accumulate / preact / split-K");
   const int pitch_mult = f16 ? 8 : 4;
   RF_CHECK_ARG((p->lda % pitch_mult) == 0 && (p->ldb % pitch_mult) == 0, "rf_gemm_tf32: lda=%lld ldb=%lld must be multiples of %d (TMA 16 B pitch)",
                p->lda, p->ldb, pitch_mult);
-  RF_CHECK_ARG(!f16 || (!p->a_mn_major && !p->b_mn_major), "rf_gemm_tf32: fp16 operands must be K-major");
+  RF_CHECK_ARG(!f16 || (!p->a_mn_major && !p->b_mn_major), "rf_gemm_tf32: 16-bit operands must be K-major");
   RF_CHECK_ARG((reinterpret_cast<uintptr_t>(p->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->B) & 15) == 0,
                "rf_gemm_tf32: A/B must be 16-byte aligned");
   RF_CHECK_ARG(p->lda >= (p->a_mn_major ? p->M : p->K) && p->ldb >= (p->b_mn_major ? p->N : p->K) && p->ldc >= p->N,
@@ -1049,7 +1073,8 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
   a.residual = p->residual; a.ld_res = p->ld_res; a.act = p->act; a.preact = p->preact; a.ld_pre = p->ld_pre;
   a.dact_aux = p->dact_aux; a.ld_aux = p->ld_aux; a.dact = p->dact; a.accumulate = (p->accumulate || split_linear) ? 1 : 0;
   a.split_epilogue = split_linear ? 1 : 0;
-  a.kb_total = kb_total; a.kb_per_split = kb_per_split; a.f16 = f16 ? 1 : 0; a.colsum_a = p->colsum_a;
+  a.kb_total = kb_total; a.kb_per_split = kb_per_split; a.f16 = p->ab_dtype == RF_F16 ? 1 : (p->ab_dtype == RF_BF16 ? 2 : 0);
+  a.c_bf16 = p->c_dtype == RF_BF16 ? 1 : 0; a.colsum_a = p->colsum_a;
   a.group_in = p->out_group_in; a.group_out = p->out_group_out; a.row_offset = p->out_row_offset;
   a.round_f16 = p->round_f16;
   static int tma_store_enabled = -1;
@@ -1062,7 +1087,7 @@ extern "C" int rf_gemm_tf32(const RfGemmParams* p, void* stream) {
                         (gemm::BLOCK_M % p->out_group_in == 0 && p->out_row_offset == 0 && p->out_group_out >= p->out_group_in);
   const bool pre_ok = !p->preact || ((p->ld_pre % 4) == 0 && (reinterpret_cast<uintptr_t>(p->preact) & 15) == 0 && p->out_group_in == 0);
   const bool acc_ok = !p->accumulate || (p->out_group_in == 0 && !p->preact);
-  a.tma_store = (tma_store_enabled && c_ok && group_ok && pre_ok && acc_ok) ? 1 : 0;
+  a.tma_store = (tma_store_enabled && c_ok && group_ok && pre_ok && acc_ok && !a.c_bf16) ? 1 : 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return n64 ? gemm::launch<64>(p, a, splits, s) : gemm::launch<128>(p, a, splits, s);
 }

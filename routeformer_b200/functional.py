@@ -397,7 +397,12 @@ class CircularConv3(Function):
         wcat = torch.empty(3 * D, Cp, device=dev, dtype=torch.float32)
         ops.conv3_pack_weight(weight, wcat)
         z = torch.empty(n * L, 3 * D, device=dev, dtype=torch.float32)
-        ops.gemm(x2, wcat, z)
+        if x2.dtype == torch.bfloat16:  # bf16 operand mode, inference only: the patch embedding stored its features in bf16
+            if torch.is_grad_enabled():
+                raise RuntimeError("bf16 features reach the token convolution only under torch.no_grad() (ops.bf16_operands)")
+            ops.gemm(x2, wcat.to(torch.bfloat16), z)
+        else:
+            ops.gemm(x2, wcat, z)
         L_out = L + 2 * pad - 2
         y = torch.empty(n * L_out, D, device=dev, dtype=torch.float32)
         ops.conv3_assemble_fwd(z, y, n, L, D, pad, bias=bias, pe=pe, wtime=None if wtime is None else wtime.view(-1))

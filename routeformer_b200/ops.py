@@ -127,6 +127,33 @@ class precise:
                 _os.environ["RF_ATTN_TC"] = self.prev_tc
 
 
+# ---- bf16 operand mode (north star: "bf16 operands with a stated looser tolerance") ---------------------------------
+# RF_BF16=1 (or `with ops.bf16_operands():`): a GEMM operand is taken in bf16 wherever it can be PRODUCED in bf16 without an extra
+# pass over memory (fp32 accumulate, fp32 epilogue everywhere):
+#   * the patch embedding: the crop kernel writes bf16 patches, the projection weight is cast once per weight version
+#     (instead of the fp16 operands the reference's autocast uses);
+#   * inference (torch.no_grad): the patch embedding stores its features in bf16 and the frame encoder's token convolution
+#     (K = 1024, the other tensor-bound GEMM of the model) multiplies them as bf16 against a bf16 copy of its weight.
+# Everything downstream (the D = 128 layers, HBM-bound; attention scores and the top-u selection) stays fp32 / TF32: casting
+# their activations would cost a pass that the GEMM cannot win back.  Tolerance: tests/test_gpu_model.py::test_bf16_operand_mode
+# (measured errors in profiles/).
+BF16_MODE = _os.environ.get("RF_BF16", "0") == "1"
+
+
+class bf16_operands:
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        global BF16_MODE
+        self.prev, BF16_MODE = BF16_MODE, self.on
+        return self
+
+    def __exit__(self, *exc):
+        global BF16_MODE
+        BF16_MODE = self.prev
+
+
 def _tf32_split(t: torch.Tensor):
     """(hi, lo): hi = t rounded to 10 mantissa bits (round-half-away in magnitude), lo = t - hi (exact in fp32)."""
     rows, cols = t.shape
@@ -179,19 +206,24 @@ def _gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = F
          residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, preact: Optional[torch.Tensor] = None,
          dact_aux: Optional[torch.Tensor] = None, dact: int = ACT_NONE, accumulate: bool = False, split_k: int = 0,
          out_group=(0, 0, 0), round_f16: bool = False, M: Optional[int] = None, colsum_a: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[M,N] (+)= epilogue(A . B^T) on the tcgen05 kernel.  A, B are 2-D fp32 views (multiplied as TF32) or both fp16
-    (kind::f16, K-major only); out and the epilogue operands are fp32.
+    """out[M,N] (+)= epilogue(A . B^T) on the tcgen05 kernel.  A, B are 2-D fp32 views (multiplied as TF32) or both fp16 / both
+    bf16 (kind::f16, K-major only); the epilogue operands are fp32; out is fp32, or bf16 for 16-bit operands (rounded once, after
+    the epilogue: the next GEMM takes it as a bf16 operand).
 
     a_mn=False: A is [M,K] memory; True: A is [K,M] memory (logical A^T).  Same for B with N.
     """
     lib = _lib.load()
-    f16 = A.dtype == torch.float16
+    f16 = A.dtype in (torch.float16, torch.bfloat16)
     if f16:
-        if B.dtype != torch.float16 or a_mn or b_mn:
-            raise TypeError("gemm: fp16 operands need both A and B in fp16, K-major")
+        if B.dtype != A.dtype or a_mn or b_mn:
+            raise TypeError("gemm: 16-bit operands need A and B in the same 16-bit type, K-major")
     else:
         _f32(A, "A"), _f32(B, "B")
-    _f32(out, "out")
+    if out.dtype == torch.bfloat16:
+        if not f16 or accumulate or preact is not None:
+            raise TypeError("gemm: a bf16 output needs 16-bit operands and no accumulate / preact")
+    else:
+        _f32(out, "out")
     if a_mn:
         K, Ma = A.shape
     else:
@@ -222,7 +254,8 @@ def _gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = F
     p.accumulate, p.split_k = int(accumulate), (-1 if (split_k == 0 and not accumulate and not torch.is_grad_enabled()) else split_k)
     p.out_group_in, p.out_group_out, p.out_row_offset = out_group
     p.round_f16 = int(round_f16)
-    p.ab_dtype = F16 if f16 else F32
+    p.ab_dtype = _DTYPES[A.dtype] if f16 else F32
+    p.c_dtype = BF16 if out.dtype == torch.bfloat16 else F32
     if colsum_a is not None:  # colsum_a[k] += sum_m A[m, k]: the bias gradient when A is an output gradient
         if colsum_a.numel() != K or not colsum_a.is_contiguous():
             raise ValueError("gemm: colsum_a must be a contiguous [K] vector")

@@ -154,6 +154,35 @@ def test_gemm_strided_rows_and_row_remap(ops):
     assert torch.equal(got[:, :8].half().float(), got[:, :8])  # representable in fp16
 
 
+def test_gemm_bf16_operands_and_bf16_output(ops):
+    """bf16 operand mode (north star): kind::f16 MMAs on bf16 operands with fp32 accumulation; the result optionally stored as bf16
+    (rounded once, after the fp32 epilogue) with the patch embedding's 64 -> 65 row remap.  Against fp64 arithmetic on the SAME
+    bf16-rounded operands the fp32 result is exact to accumulation order; the bf16 result is within half a bf16 ulp (2^-9)."""
+    gen = g(17)
+    M, N, K = 3 * 64, 200, 328
+    A = (torch.randn(M, K, generator=gen) / math.sqrt(K)).to(torch.bfloat16)
+    W = torch.randn(N, K, generator=gen).to(torch.bfloat16)
+    bias = torch.randn(N, generator=gen)
+    ref = A.double() @ W.double().t() + bias.double()
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(A.to(DEV), W.to(DEV), out, bias=bias.to(DEV))
+    assert rel_err(out.cpu(), ref.float()) < 2e-6
+    # bf16 C through the row remap (groups of 64 rows stored with pitch 65, the 65th row untouched)
+    buf = torch.full((3 * 65, 208), -1.0, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A.to(DEV), W.to(DEV), buf[:, :N], bias=bias.to(DEV), out_group=(64, 65, 0))
+    got = buf.cpu().float().view(3, 65, 208)
+    want = ref.float().view(3, 64, N)
+    # (fp32 accumulation order differs from the fp64 reference: a value that sits on a bf16 rounding boundary may land on either
+    #  side, so the bound is one bf16 ulp, 2^-8 relative, and nearly all values are the correctly rounded ones)
+    assert ((got[:, :64, :N] - want).abs() <= 2.0 ** -8 * want.abs() + 1e-6).all()
+    assert (got[:, :64, :N] == want.to(torch.bfloat16).float()).float().mean() > 0.99
+    assert torch.equal(got[:, 64], torch.full((3, 208), -1.0)) and torch.equal(got[:, :, N:], torch.full((3, 65, 208 - N), -1.0))
+    with pytest.raises(TypeError):
+        ops.gemm(A.to(DEV), W.to(DEV).half(), out)
+    with pytest.raises(TypeError):
+        ops.gemm(A.to(DEV).float(), W.to(DEV).float(), buf[:, :N])
+
+
 def test_gemm_dact_and_accumulate(ops):
     gen = g(3)
     M, N, K = 5000, 96, 160
