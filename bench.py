@@ -169,6 +169,13 @@ def finish(dist, world) -> None:
         os._exit(0)
 
 
+def _dtype_note(args, default: str) -> str:
+    if getattr(args, "bf16", False):
+        return ("tf32 + bf16 operand mode (bf16 patch embedding; in inference bf16-stored patch features and a bf16 token convolution; fp32 "
+                "accumulate; stated tolerance: waypoints 4e-3 relative)")
+    return default
+
+
 def run_train(args):
     import routeformer_b200 as R
     from routeformer_b200 import ops
@@ -412,7 +419,7 @@ def run_train(args):
         line = {
             "metric": "routeformer_fwd_bwd_clips_per_sec", "value": round(value, 2), "unit": "clips/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate; fp16 operands in the patch embedding like the reference's autocast backbone)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": _dtype_note(args, "tf32 (fp32 storage, fp32 accumulate; fp16 operands in the patch embedding like the reference's autocast backbone)"), "data": "synthetic",
             "config": {"workload": "Routeformer GPS+scene video+gaze FoV training step (fwd+loss+bwd+allreduce+clip+AdamW), "
                                    "paper config, random-init patch backbone 256^2/p32/C1024, GEM-shaped clips",
                        "global_batch": world * B, "batch_per_gpu": B, "parallelism": f"dp{world}", "fov": args.fov,
@@ -633,7 +640,7 @@ def run_fwd(args):
     if rank == 0:
         line = {"metric": "routeformer_fwd_clips_per_sec", "mode": "fwd", "value": round(value, 2), "unit": "clips/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate; fp16 patch embedding)", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": _dtype_note(args, "tf32 (fp32 storage, fp32 accumulate; fp16 patch embedding)"), "data": "synthetic",
                 "config": {"workload": "BASELINE configs[1]: Routeformer GPS+scene video+gaze FoV forward (eval), paper config, random-init patch "
                                        "backbone, GEM-shaped clips", "batch_per_gpu": B, "global_batch": world * B, "fov": args.fov,
                            "cuda_graph": not args.no_graph, "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB per step per GPU)"},
@@ -700,7 +707,7 @@ def run_eval_step(args):
             "metric": "routeformer_eval_step_clips_per_sec", "mode": "eval_step", "value": round(world * B * args.steps / (ms / 1e3), 2),
             "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 (fp32 storage, fp32 accumulate; fp16 patch embedding)", "data": "synthetic",
+            "dtype": _dtype_note(args, "tf32 (fp32 storage, fp32 accumulate; fp16 patch embedding)"), "data": "synthetic",
             "config": {"workload": "SURVEY 8(f) N2: _eval_step, 5 stochastic forwards per batch + per-clip loss/ADE/FDE, paper config, "
                                    "GEM-shaped clips; a clip counts once (not once per sample)", "batch_per_gpu": B, "samples": steps.n_eval_samples,
                        "fov": args.fov, "cuda_graph": False, "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB per step per GPU)"},
@@ -748,7 +755,7 @@ def run_dreyeve_sweep(args):
     if rank == 0:
         best = max(r["clips_per_s"] for r in rows if r["video_fps"] == 1)
         print(json.dumps({"metric": "routeformer_fwd_clips_per_sec", "mode": "dreyeve_sweep", "value": best, "unit": "clips/s", "n_gpus": world,
-                          "higher_is_better": True, "data": "synthetic", "dtype": "tf32 / fp16 patch embedding",
+                          "higher_is_better": True, "data": "synthetic", "dtype": _dtype_note(args, "tf32 / fp16 patch embedding"),
                           "config": {"workload": "BASELINE configs[3]: DR(eye)VE-shaped full-modality inference sweep, inputs resident in HBM "
                                                  "(consumed frames only), paper config, rotate_motion", "cuda_graph": not args.no_graph},
                           "sweep": rows}), flush=True)
@@ -851,7 +858,12 @@ def main():
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU comparator")
     ap.add_argument("--u8-frames", action="store_true", help="host batch holds raw uint8 frames (half the H2D bytes); converted in the crop kernel")
     ap.add_argument("--paper-dropout", action="store_true", help="train with the paper's dropouts (view 0.6 / gaze 0.2 / feature 0.05)")
+    ap.add_argument("--bf16", action="store_true", help="bf16 operand mode (ops.bf16_operands): bf16 patch embedding; in inference also bf16-stored "
+                                                        "patch features into the token convolution.  Tolerance: waypoints 4e-3 (tests)")
     args = ap.parse_args()
+    if args.bf16 and args.impl == "ours":
+        from routeformer_b200 import ops as _ops
+        _ops.BF16_MODE = True
     if args.warmup < 3 and args.impl == "ours" and not args.profile:
         args.warmup = 3
     if args.profile:
