@@ -245,27 +245,47 @@ def run_train(args):
     h2d = in_bytes + sum(t.numel() * t.element_size() for t in pinned_t)
     prefetch = BatchPrefetcher(model, dev, depth=2)
 
-    def e2e_step():
+    # The loss of every step is read back on the host with a blocking loss.item().  --async-loss (experiment): read it one step
+    # behind instead (device->host copy into pinned memory, awaited after the NEXT step has been enqueued).
+    loss_pinned = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    losses_read = []
+
+    def e2e_step(i):
         # public-API pipeline: the H2D staging of the NEXT step's inputs (consumed frames + gps + gaze + targets, from pinned
-        # host memory, every step) runs on a side stream while this step computes; the loss is read back every step.
+        # host memory, every step) runs on a side stream while this step computes.
         # Order matters: the step is enqueued first so that its own tiny H2D copy (the index tables, first node of the graph)
         # does not queue behind the 529 MB staging transfer on the single H2D copy engine.
         b, t = prefetch.get()
         loss_t = trainer.step(b, t)
+        if args.async_loss:
+            loss_pinned[i & 1].copy_(loss_t.detach().reshape(1), non_blocking=True)
+            loss_ready[i & 1].record()
         prefetch.release(b)
         prefetch.submit(pinned, pinned_t)
         trainer.prefetch_draws()  # host RNG work of the next step, hidden behind this step's device time
-        return loss_t.item()
+        if not args.async_loss:
+            losses_read.append(loss_t.item())
+        elif i > 0:
+            loss_ready[(i - 1) & 1].synchronize()
+            losses_read.append(float(loss_pinned[(i - 1) & 1][0]))
 
     prefetch.submit(pinned, pinned_t)
-    for _ in range(3):
-        e2e_step()
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    losses_read.clear()
     barrier()
     e0.record()
-    for _ in range(e2e_steps):
-        loss_host = e2e_step()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    if args.async_loss:
+        loss_ready[(e2e_steps - 1) & 1].synchronize()
+        losses_read.append(float(loss_pinned[(e2e_steps - 1) & 1][0]))
     e1.record()
     barrier()
+    assert len(losses_read) == e2e_steps, (len(losses_read), e2e_steps)
+    loss_host = losses_read[-1]
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
 
@@ -434,7 +454,9 @@ def run_train(args):
                                   else "fp16 frames, as the reference's loader hands them over")},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                    "steps": e2e_steps, "loss": loss_host},
+                    "steps": e2e_steps, "loss": loss_host,
+                    "readback": ("every step's loss is copied to pinned host memory and read one step behind" if args.async_loss
+                                 else "blocking loss.item() every step")},
             "gpu_launches": int(launches),
             "roofline": roofline, "kernels": kernels, "measured_tf32_peak": tf32, "eager_gpu_baseline": eager, "cpu_baseline": cpu_baseline,
             "loss": float(loss.item()),
@@ -858,6 +880,8 @@ def main():
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU comparator")
     ap.add_argument("--u8-frames", action="store_true", help="host batch holds raw uint8 frames (half the H2D bytes); converted in the crop kernel")
     ap.add_argument("--paper-dropout", action="store_true", help="train with the paper's dropouts (view 0.6 / gaze 0.2 / feature 0.05)")
+    ap.add_argument("--async-loss", action="store_true", help="e2e leg experiment: read each step's loss one step behind instead of a blocking .item().  Measured SLOWER (2 210 vs 3 113 "
+                         "clips/s): with the host a step ahead, the next step's small H2D copies queue behind the 529 MB staging transfer")
     ap.add_argument("--bf16", action="store_true", help="bf16 operand mode (ops.bf16_operands): bf16 patch embedding; in inference also bf16-stored "
                                                         "patch features into the token convolution.  Tolerance: waypoints 4e-3 (tests)")
     args = ap.parse_args()

@@ -6,6 +6,7 @@ run bench_train                                   # default: training step, pari
 run bench_train_paper_dropout --paper-dropout --no-eager-baseline --no-cpu-baseline
 run bench_train_u8_frames --u8-frames --no-eager-baseline --no-cpu-baseline
 run bench_fwd --mode fwd --no-eager-baseline --no-cpu-baseline
+run bench_fwd_bf16 --mode fwd --bf16 --no-eager-baseline --no-cpu-baseline
 run bench_eval_step --mode eval_step
 run bench_dreyeve_sweep --mode dreyeve_sweep --no-eager-baseline --no-cpu-baseline
 run bench_crop_micro --mode crop_micro
