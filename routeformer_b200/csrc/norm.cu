@@ -65,6 +65,64 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __
   }
 }
 
+// Rows of D <= 128 (every Perceive layer: D = 128): a warp takes R rows per pass, one float4 per lane and row.  All R loads are
+// issued before the first use (R x 512 B in flight per warp instead of one row behind a chain of two shuffle reductions), the
+// row stays in registers for the three passes, and the R butterfly reductions interleave.  Per-row arithmetic -- lane partial
+// (x + y) + (z + w), butterfly, centred second pass -- is exactly that of the generic kernel above: results are bit-identical.
+template <int R>
+__global__ void __launch_bounds__(WARPS * 32, 3)
+layernorm_fwd_rows_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          float* __restrict__ y, long long ldy, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int d = lane * 4;
+  const bool valid = d < D;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 g = valid ? *reinterpret_cast<const float4*>(gamma + d) : zero4;
+  const float4 b = valid ? *reinterpret_cast<const float4*>(beta + d) : zero4;
+  for (long long row0 = (static_cast<long long>(blockIdx.x) * WARPS + warp) * R; row0 < M; row0 += static_cast<long long>(gridDim.x) * WARPS * R) {
+    float4 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = (valid && row0 + r < M) ? *reinterpret_cast<const float4*>(x + (row0 + r) * ldx + d) : zero4;
+    float s[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) s[r] = (v[r].x + v[r].y) + (v[r].z + v[r].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+    float mean[R], q[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mean[r] = s[r] / D;
+      const float a0 = v[r].x - mean[r], a1 = v[r].y - mean[r], a2 = v[r].z - mean[r], a3 = v[r].w - mean[r];
+      q[r] = valid ? (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3) : 0.f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float rstd = rsqrtf(q[r] / D + 1e-5f);
+      if (valid && row0 + r < M) {
+        float4 o4;
+        o4.x = (v[r].x - mean[r]) * rstd * g.x + b.x;
+        o4.y = (v[r].y - mean[r]) * rstd * g.y + b.y;
+        o4.z = (v[r].z - mean[r]) * rstd * g.z + b.z;
+        o4.w = (v[r].w - mean[r]) * rstd * g.w + b.w;
+        *reinterpret_cast<float4*>(y + (row0 + r) * ldy + d) = o4;
+      }
+      if (lane == 0 && row0 + r < M) {
+        if (mean_out) mean_out[row0 + r] = mean[r];
+        if (rstd_out) rstd_out[row0 + r] = rstd;
+      }
+    }
+  }
+}
+
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma;  dgamma += sum dy*xhat;  dbeta += sum dy.
 // A lane owns the same columns (lane, lane+32, ...) for every row its warp processes, so the dgamma/dbeta partials live in
 // registers across rows (CPL = columns per lane, template) and leave the CTA as one shared-memory reduction + one global
@@ -288,6 +346,17 @@ using namespace rf::norm;
 extern "C" int rf_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float* y, long long ldy,
                                 float* mean, float* rstd, int M, int D, void* stream) {
   RF_CHECK_ARG(x && gamma && beta && y && M > 0 && D > 0 && ldx >= D && ldy >= D, "rf_layernorm_fwd: bad arguments");
+  const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+                      reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+  static const bool rows_kernel = [] { const char* e = getenv("RF_LN_ROWS"); return !(e && e[0] == '0'); }();
+  if (rows_kernel && D <= 128 && (D & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0 && al16 && M >= 4 * WARPS) {
+    constexpr int R = 4;
+    int grid = ceil_div(M, WARPS * R);
+    grid = grid > 148 * 8 ? 148 * 8 : grid;
+    RF_CUDA_OK(launch_pdl(layernorm_fwd_rows_kernel<R>, dim3(grid), dim3(WARPS * 32), 0, static_cast<cudaStream_t>(stream), x, ldx, gamma, beta, y,
+                          ldy, mean, rstd, M, D));
+    return RF_OK;
+  }
   int grid = ceil_div(M, WARPS);
   grid = grid > 148 * 8 ? 148 * 8 : grid;
   RF_CUDA_OK(launch_pdl(layernorm_fwd_kernel, dim3(grid), dim3(WARPS * 32), 0, static_cast<cudaStream_t>(stream), x, ldx, gamma, beta, y, ldy, mean, rstd,
