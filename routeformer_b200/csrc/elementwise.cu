@@ -456,12 +456,32 @@ __global__ void discounted_loss_bwd_kernel(const float* __restrict__ pred, long 
   }
 }
 
-__global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+// (both kernels below stream flat arenas: 16-byte loads, several of them in flight per thread -- the scalar grid-stride versions
+//  ran at 1.8 TB/s (sum of squares) and 2.9 TB/s (AdamW) of the 6.5 TB/s the copy kernel reaches)
+__global__ void __launch_bounds__(TPB) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   float acc = 0.f;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float v = x[i];
-    acc += v * v;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const long long n4 = n >> 2;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    long long i = tid;
+    for (; i + 3 * stride < n4; i += 4 * stride) {  // four independent 16 B loads per thread and pass
+      const float4 u0 = x4[i], u1 = x4[i + stride], u2 = x4[i + 2 * stride], u3 = x4[i + 3 * stride];
+      a0 += (u0.x * u0.x + u0.y * u0.y) + (u0.z * u0.z + u0.w * u0.w);
+      a1 += (u1.x * u1.x + u1.y * u1.y) + (u1.z * u1.z + u1.w * u1.w);
+      a2 += (u2.x * u2.x + u2.y * u2.y) + (u2.z * u2.z + u2.w * u2.w);
+      a3 += (u3.x * u3.x + u3.y * u3.y) + (u3.z * u3.z + u3.w * u3.w);
+    }
+    for (; i < n4; i += stride) {
+      const float4 u0 = x4[i];
+      a0 += (u0.x * u0.x + u0.y * u0.y) + (u0.z * u0.z + u0.w * u0.w);
+    }
+    acc = (a0 + a1) + (a2 + a3);
+    for (long long j = (n4 << 2) + tid; j < n; j += stride) acc += x[j] * x[j];
+  } else {
+    for (long long i = tid; i < n; i += stride) acc += x[i] * x[i];
   }
   acc = warp_sum(acc);
   __shared__ float part[32];
@@ -474,27 +494,52 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __
   }
 }
 
-__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-                             float grad_scale, const float* __restrict__ gnorm_sq, float max_norm) {
-  float gs = grad_scale;
+struct AdamW {
+  float lr, b1, b2, eps, wd, bc1, bc2_sqrt, gs;
+  __device__ __forceinline__ void update(float& p, float g, float& m, float& v) const {
+    const float gi = g * gs;
+    float pi = p * (1.f - lr * wd);
+    const float mi = b1 * m + (1.f - b1) * gi;
+    const float vi = b2 * v + (1.f - b2) * gi * gi;
+    m = mi;
+    v = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p = pi;
+  }
+};
+
+__global__ void __launch_bounds__(TPB) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                    long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                                                    float grad_scale, const float* __restrict__ gnorm_sq, float max_norm, int vec) {
+  AdamW a;
+  a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = wd; a.bc1 = bc1; a.bc2_sqrt = bc2_sqrt; a.gs = grad_scale;
   if (gnorm_sq) {
     const float norm = sqrtf(gnorm_sq[0]) * grad_scale;
     const float clip = max_norm / (norm + 1e-6f);  // torch.nn.utils.clip_grad_norm_
-    if (clip < 1.f) gs *= clip;
+    if (clip < 1.f) a.gs *= clip;
   }
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gi = g[i] * gs;
-    float pi = p[i] * (1.f - lr * wd);
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= (lr / bc1) * (mi / denom);
-    p[i] = pi;
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long done = 0;
+  if (vec) {  // all four arenas 16-byte aligned: one float4 of each per thread and pass (same per-element arithmetic)
+    const long long n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (long long i = tid; i < n4; i += stride) {
+      float4 pv = p4[i], mv = m4[i], vv = v4[i];
+      const float4 gv = g4[i];
+      a.update(pv.x, gv.x, mv.x, vv.x);
+      a.update(pv.y, gv.y, mv.y, vv.y);
+      a.update(pv.z, gv.z, mv.z, vv.z);
+      a.update(pv.w, gv.w, mv.w, vv.w);
+      p4[i] = pv; m4[i] = mv; v4[i] = vv;
+    }
+    done = n4 << 2;
   }
+  for (long long i = done + tid; i < n; i += stride) a.update(p[i], g[i], m[i], v[i]);
 }
 
 }  // namespace ew
@@ -719,7 +764,7 @@ extern "C" int rf_colsum_accumulate(const float* src, long long ld, int M, int N
 
 extern "C" int rf_sumsq_accumulate(const float* x, long long n, float* out, void* stream) {
   RF_CHECK_ARG(x && out && n > 0, "rf_sumsq_accumulate: bad arguments");
-  sumsq_kernel<<<blocks_for(n, TPB, 148 * 4), TPB, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out);
+  sumsq_kernel<<<blocks_for((n + 15) / 16, TPB, 148 * 8), TPB, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out);
   RF_LAUNCH_OK();
   return RF_OK;
 }
@@ -730,9 +775,11 @@ extern "C" int rf_adamw_step(float* param, const float* grad, float* exp_avg, fl
   RF_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "rf_adamw_step: bad arguments");
   const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
   const float bc2_sqrt = sqrtf(1.0f - powf(beta2, static_cast<float>(step)));
-  adamw_kernel<<<blocks_for(n, TPB, 148 * 8), TPB, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
-                                                                                         beta2, eps, weight_decay, bc1, bc2_sqrt,
-                                                                                         grad_scale, gnorm_sq, max_norm);
+  const int vec = ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+                    reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0;
+  adamw_kernel<<<blocks_for((n + 3) / 4, TPB, 148 * 8), TPB, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                                                   beta2, eps, weight_decay, bc1, bc2_sqrt,
+                                                                                                   grad_scale, gnorm_sq, max_norm, vec);
   RF_LAUNCH_OK();
   return RF_OK;
 }

@@ -371,6 +371,7 @@ extern "C" int rf_layernorm_bwd(const float* dy, long long lddy, const float* x,
   grid = grid < 1 ? 1 : (grid > 148 * 4 ? 148 * 4 : grid);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t sm = 2 * D * sizeof(float);
+  // (a float4 / four-rows-per-pass variant like the forward's was measured: 43.0 vs 44.1 us on [99840, 128], not kept)
   if (D <= 64) RF_CUDA_OK(launch_pdl(layernorm_bwd_kernel<2>, dim3(grid), dim3(WARPS * 32), sm, st, dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D));
   else if (D <= 128) RF_CUDA_OK(launch_pdl(layernorm_bwd_kernel<4>, dim3(grid), dim3(WARPS * 32), sm, st, dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D));
   else if (D <= 256) RF_CUDA_OK(launch_pdl(layernorm_bwd_kernel<8>, dim3(grid), dim3(WARPS * 32), sm, st, dy, lddy, x, ldx, gamma, mean, rstd, dx, lddx, dgamma, dbeta, M, D));
