@@ -52,35 +52,61 @@ def build_model(fov, shapes: str = "gem", dropout: bool = False):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: through NVML in-process every 25 ms (nvidia_ml_py), or --
+    if NVML cannot be initialised -- through `nvidia-smi` every 200 ms (one call takes ~0.3 s: one or two samples per run)."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    MASKS = [0x8, 0x40, 0x20, 0x4]  # nvmlClocksEventReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self._halt = index, [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if visible and all(v.strip().isdigit() for v in visible.split(",")):
+                phys = int(visible.split(",")[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(self.handle))
+        self.samples.append([str(mhz), str(self.max_mhz)] + [("Active" if mask & m else "Not Active") for m in self.MASKS])
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.025 if self.nvml is not None else 0.2)
 
     def stop(self):
         self._halt.set()
         self.join(2)
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for s in self.samples for n, v in zip(self.NAMES, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "source": "nvml, every 25 ms" if self.nvml is not None else "nvidia-smi, every 200 ms"}
 
 
 def measured_peaks():
@@ -885,6 +911,94 @@ def run_crop_micro(args):
                       "crop": rows, "patch_embed_gemm": gemm_row}), flush=True)
 
 
+def run_stage_micro(args):
+    """the loader's video scaling (cv2.resize INTER_AREA, io/dataset.py:1440-1501) on the device, on the frame sizes
+    and factors of the reference's experiments (full_comparison.py:107-110,124-125).  HBM GB/s of rf_area_resize_u8 (algorithmic
+    bytes: every source byte of the scaled rows once + every output byte once) against the measured copy peak, the same call from
+    pinned host frames (H2D + kernel + D2H of the scaled frames), and OpenCV on the host cores beside it."""
+    from routeformer_b200 import ops
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    peaks, peak_src = measured_peaks()
+    flush = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    cases = [("GEM GoPro 2160x3840, rows 648..1512, x0.1 -> 86x384", (2160, 3840), 0.1, True, 24),
+             ("GEM front 1080x1088 x0.3 -> 324x326", (1080, 1088), 0.3, False, 96),
+             ("DR(eye)VE GoPro 1080x1920, rows 324..756, x0.4 -> 172x768", (1080, 1920), 0.4, True, 96),
+             ("DR(eye)VE front 720x960 x1/3 -> 240x320", (720, 960), 1 / 3.0, False, 192)]
+    rows_out = []
+    for name, (H, W), f, crop, n in cases:
+        frames = torch.randint(0, 256, (n, 3, H, W), device=dev, dtype=torch.uint8, generator=g)
+        rows = (int(0.3 * H), int(0.7 * H)) if crop else None
+        Hc = rows[1] - rows[0] if crop else H
+        out = ops.area_resize_u8(frames, f, rows=rows)
+        work = n * 3 * (Hc * W + out.shape[-2] * out.shape[-1])
+        for _ in range(3):
+            ops.area_resize_u8(frames, f, rows=rows, out=out)
+        tot, reps = 0.0, 10
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.area_resize_u8(frames, f, rows=rows, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        ms = tot / reps
+        # end to end: pinned raw frames -> device -> scaled frames back on the host
+        host = frames.cpu().pin_memory()
+        host_out = torch.empty(out.shape, dtype=torch.uint8).pin_memory()
+        stage = torch.empty_like(frames)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(4):
+            if it == 1:
+                e0.record()
+            stage.copy_(host, non_blocking=True)
+            ops.area_resize_u8(stage, f, rows=rows, out=out)
+            host_out.copy_(out, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e2e = e0.elapsed_time(e1) / 3
+        # host baseline on a bounded sample: OpenCV itself where importable (it IS the reference's implementation), else the oracle port
+        sample = host[:min(n, 8)].numpy()
+        if crop:
+            sample = sample[:, :, rows[0]:rows[1], :]
+        try:
+            import cv2
+
+            size = (int(W * f), int(Hc * f))
+            t0 = time.time()
+            for fr in sample:
+                cv2.resize(fr.transpose(1, 2, 0), size, None, None, None, cv2.INTER_AREA)
+            cpu_s, cpu_kind, cores = time.time() - t0, f"reference (cv2 {cv2.__version__}.resize INTER_AREA per frame, as io/dataset.py:1473-1482)", cv2.getNumThreads()
+        except ImportError:
+            from oracle import area_resize as A
+
+            t0 = time.time()
+            A.scale_video(sample, f)
+            cpu_s, cpu_kind, cores = time.time() - t0, "port (oracle/area_resize.py, numpy)", 1
+        src_bytes = n * 3 * Hc * W
+        rows_out.append({"case": name, "frames": n, "ms": round(ms, 4), "algorithmic_mb": round(work / 1e6, 1), "gbs": round(work / ms / 1e6, 1),
+                         "frac_of_hbm_peak": round(work / ms / 1e6 / peaks["hbm_gbs"], 4), "frames_per_s": round(n / ms * 1e3),
+                         "e2e": {"ms": round(ms_e2e, 3), "frames_per_s": round(n / ms_e2e * 1e3), "h2d_bytes": int(frames.numel()),
+                                 "d2h_bytes": int(out.numel())},
+                         "cpu_baseline": {"frames_per_s": round(len(sample) / cpu_s, 1), "kind": cpu_kind, "cores": cores,
+                                          "sample": f"{len(sample)} frames"},
+                         "source_gbs": round(src_bytes / ms / 1e6, 1)})
+        del frames, stage, host, host_out, out
+    head = rows_out[0]
+    print(json.dumps({"metric": "area_resize_hbm_gbs", "mode": "stage_micro", "value": head["gbs"], "unit": "GB/s", "n_gpus": 1,
+                      "higher_is_better": True, "data": "synthetic", "dtype": "u8 (float32 cell sums, int32 box sums: bit-exact with OpenCV)",
+                      "config": {"workload": "SURVEY 8(f) N4: the loader's cv2.resize(INTER_AREA) video scaling on the device, frame sizes and factors of "
+                                             "experiments/full_comparison.py:107-110,124-125", "l2": "1 GiB flush write between timed launches"},
+                      "roofline": {"bound": "hbm", "achieved": head["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": head["frac_of_hbm_peak"], "traffic": None, "peak_source": f"{peak_src} HBM copy bandwidth"},
+                      "e2e": {"value": head["e2e"]["frames_per_s"], "unit": "frames/s", "h2d_bytes_per_step": head["e2e"]["h2d_bytes"],
+                              "d2h_bytes_per_step": head["e2e"]["d2h_bytes"]},
+                      "cpu_baseline": head["cpu_baseline"], "cases": rows_out}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -898,7 +1012,7 @@ def main():
     ap.add_argument("--no-wgrad-overlap", action="store_true", help="keep the weight-gradient GEMMs on the main stream")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one captured CUDA graph")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up + --steps steps, no e2e / roofline / CPU legs")
-    ap.add_argument("--mode", default="train", choices=["train", "fwd", "eval_step", "dreyeve_sweep", "crop_micro"],
+    ap.add_argument("--mode", default="train", choices=["train", "fwd", "eval_step", "dreyeve_sweep", "crop_micro", "stage_micro"],
                     help="train = the headline metric (BASELINE configs[2], default); fwd = configs[1]; dreyeve_sweep = configs[3]; "
                          "crop_micro = configs[4]; eval_step = the _eval_step caller (SURVEY 8(f) N2)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU comparator")
@@ -926,6 +1040,8 @@ def main():
         run_dreyeve_sweep(args)
     elif args.mode == "crop_micro":
         run_crop_micro(args)
+    elif args.mode == "stage_micro":
+        run_stage_micro(args)
     else:
         run_train(args)
 

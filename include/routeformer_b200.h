@@ -48,7 +48,7 @@ extern "C" {
 
 int rf_abi_version(void);
 const char* rf_last_error(void);
-/* sizeof() of the parameter structs below, in declaration order (0 = RfFovCropParams ... 7 = RfDistilBwdParams);
+/* sizeof() of the parameter structs below, in declaration order (0 = RfFovCropParams ... 7 = RfDistilBwdParams, 8 = RfAreaResizeParams);
  * lets a foreign-language binding verify its struct mirror.  Returns -1 for an unknown index. */
 int rf_struct_size(int which);
 
@@ -316,6 +316,22 @@ int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
  * ---------------------------------------------------------------------------------------------- */
 int rf_stage_frames_h2d(void* dst_dev, const void* src_host, int B, int T, const int* times, int n_sel,
                         long long frame_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (10) Dataset-side video down-scaling on the device (raw uint8 frames are uploaded once at camera resolution)
+ * replaces: routeformer/io/dataset.py:1440-1501 (`_apply_scaling`: cv2.resize(frame, (int(W*f), int(H*f)), INTER_AREA) per
+ *           frame) -- bit-exact for uint8 (OpenCV's resizeAreaFast_ / resizeArea_); the row crop of the GoPro views
+ *           (:1324-1338, rows [int(0.3 H), int(0.7 H))) is expressed by the caller through `src` / `H` / `src_plane_stride`;
+ *           the conversion `astype(float16) / 255` (:1503-1523) is RF_U8_F16 of rf_fov_crop.
+ * Planes are independent (cv2 treats the channels of an HWC image independently): src is [n_planes] planes of H rows of W
+ * bytes, dst dense [n_planes, dH, dW].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const unsigned char* src; long long src_plane_stride; long long src_row_pitch; /* bytes */
+  int n_planes, H, W;
+  unsigned char* dst; int dH, dW;
+} RfAreaResizeParams;
+int rf_area_resize_u8(const RfAreaResizeParams* p, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,9 @@ against the unmodified reference modules imported from ``/root/reference`` throu
 ``oracle/reference_shim.py`` (tests/test_oracle_vs_reference.py, runs only where the
 reference is mounted) and (b) against golden vectors generated from that reference
 by ``oracle/make_golden.py`` and committed under ``tests/golden/``.
+``oracle/area_resize.py`` (the loader's cv2.resize INTER_AREA scaling) restates
+OpenCV's published algorithm and is pinned bit-exactly against cv2 itself and against
+``tests/golden/area_resize.npz`` (generated with cv2 by ``oracle/make_golden_resize.py``).
 The visual backbone (timm SwinV2, un-vendored, needs downloaded weights) is the one
 boundary that is "parity unpinned": it is replaced by a build-defined patch-embed
 encoder whose oracle is the plain-PyTorch twin in this package.

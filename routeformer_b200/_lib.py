@@ -93,9 +93,17 @@ class RfDistilBwdParams(C.Structure):
     ]
 
 
+class RfAreaResizeParams(C.Structure):
+    _fields_ = [
+        ("src", c_fp), ("src_plane_stride", c_ll), ("src_row_pitch", c_ll),
+        ("n_planes", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("dst", c_fp), ("dH", C.c_int), ("dW", C.c_int),
+    ]
+
+
 STRUCTS = {
     0: RfFovCropParams, 1: RfGemmParams, 2: RfConv3AssembleParams, 3: RfConv3AssembleBwdParams,
-    4: RfAttnParams, 5: RfAttnBwdParams, 6: RfDistilParams, 7: RfDistilBwdParams,
+    4: RfAttnParams, 5: RfAttnBwdParams, 6: RfDistilParams, 7: RfDistilBwdParams, 8: RfAreaResizeParams,
 }
 
 _I, _F, _P, _L = C.c_int, C.c_float, c_fp, c_ll
@@ -129,6 +137,7 @@ SIGNATURES = {
     "rf_colsum_accumulate": [_P, _L, _I, _I, _P, _P],
     "rf_sumsq_accumulate": [_P, _L, _P, _P],
     "rf_adamw_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P, _F, _P],
+    "rf_area_resize_u8": [C.POINTER(RfAreaResizeParams), _P],
     "rf_struct_size": [_I],
     "rf_debug_gemm_stamps": [_P],
     "rf_debug_gemm_probe": [C.c_int],

@@ -25,6 +25,7 @@ extern "C" int rf_struct_size(int which) {
     case 5: return sizeof(RfAttnBwdParams);
     case 6: return sizeof(RfDistilParams);
     case 7: return sizeof(RfDistilBwdParams);
+    case 8: return sizeof(RfAreaResizeParams);
     default: return -1;
   }
 }

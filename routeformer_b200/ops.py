@@ -92,6 +92,33 @@ def fov_crop(frames: torch.Tensor, centers: torch.Tensor, windows: torch.Tensor,
     return out
 
 
+def area_resize_u8(frames: torch.Tensor, factor: Optional[float] = None, out_hw=None, rows=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Dataset-side down-scaling on the device: uint8 [..., H, W] -> uint8 [..., H', W'], bit-exact with the reference loader's
+    `cv2.resize(frame, (int(W * factor), int(H * factor)), interpolation=cv2.INTER_AREA)` (io/dataset.py:1440-1501).
+    rows = (r0, r1): scale only rows [r0, r1) of every plane (the GoPro row crop of dataset.py:1324-1338, no copy)."""
+    lib = _lib.load()
+    if frames.dtype != torch.uint8 or not frames.is_contiguous():
+        raise TypeError("area_resize_u8: contiguous uint8 frames expected")
+    H, W = frames.shape[-2:]
+    r0, r1 = (0, H) if rows is None else rows
+    Hc = r1 - r0
+    if out_hw is None:
+        if factor is None or not factor < 1:
+            raise ValueError("area_resize_u8: give out_hw or a factor < 1 (the reference takes INTER_LINEAR for factor > 1)")
+        out_hw = (int(Hc * factor), int(W * factor))
+    dH, dW = out_hw
+    n_planes = frames.numel() // (H * W)
+    if out is None:
+        out = torch.empty(*frames.shape[:-2], dH, dW, device=frames.device, dtype=torch.uint8)
+    p = _lib.RfAreaResizeParams()
+    p.src, p.src_plane_stride, p.src_row_pitch = _ptr(frames) + r0 * W, H * W, W
+    p.n_planes, p.H, p.W = n_planes, Hc, W
+    p.dst, p.dH, p.dW = _ptr(out), dH, dW
+    check(lib.rf_area_resize_u8(C.byref(p), _stream()), "rf_area_resize_u8")
+    _count()
+    return out
+
+
 # ---- precise mode (parity instrument) ------------------------------------------------------------
 # RF_PRECISE=1 (or `with ops.precise():`) runs every fp32 GEMM as a 3xTF32 split on the SAME tcgen05 kernel:
 #   A = A_hi + A_lo, B = B_hi + B_lo (hi = operand rounded to tf32, lo = the remainder),

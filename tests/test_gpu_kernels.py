@@ -766,3 +766,52 @@ def test_reductions_and_adamw(ops):
         ops.sumsq_accumulate(gd, gn)
         ops.adamw_step(pd, gd, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-2, step, 1.0, gn, 2.5)
         assert rel_err(pd.cpu(), ref_p.detach()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ N4: dataset-side scaling
+def test_area_resize_bit_exact(ops):
+    """rf_area_resize_u8 against the golden vectors produced by cv2.resize(INTER_AREA) (tests/golden/area_resize.npz) and against
+    the oracle on the reference's frame sizes: BIT-EXACT uint8 (integral scales: box sums; otherwise OpenCV's float32 cell sums
+    in OpenCV's order, no fused multiply-add)."""
+    import os
+    import numpy as np
+    from oracle import area_resize as A
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "area_resize.npz"))
+    names = sorted({k.split("/")[0] for k in z.files if "/" in k})
+    for name in names:
+        x, y, f = z[name + "/x"], z[name + "/y"], float(z[name + "/factor"])
+        got = ops.area_resize_u8(torch.from_numpy(x).to(DEV), f).cpu().numpy()
+        assert got.shape == y.shape and np.array_equal(got, y), (name, int((got != y).sum()))
+    # the reference's own frame sizes (the GoPro views with their row crop expressed as a row range, no copy)
+    rng = np.random.default_rng(3)
+    for (H, W), f, crop in (((2160, 3840), 0.1, True), ((1080, 1088), 0.3, False), ((1080, 1920), 0.4, True), ((720, 960), 1 / 3.0, False)):
+        x = rng.integers(0, 256, size=(2, 3, H, W), dtype=np.uint8)
+        rows = (int(0.3 * H), int(0.7 * H)) if crop else None
+        want = A.scale_video(np.ascontiguousarray(A.crop_gopro_rows(x)) if crop else x, f)
+        got = ops.area_resize_u8(torch.from_numpy(x).to(DEV), f, rows=rows).cpu().numpy()
+        assert got.shape == want.shape and np.array_equal(got, want), (H, W, f, int((got != want).sum()))
+    with pytest.raises(RuntimeError):
+        ops.area_resize_u8(torch.zeros(1, 3, 8, 8, dtype=torch.uint8, device=DEV), out_hw=(16, 16))
+    with pytest.raises(TypeError):
+        ops.area_resize_u8(torch.zeros(1, 3, 8, 8, device=DEV), 0.5)
+
+
+def test_area_resize_then_crop_equals_the_host_pipeline(ops):
+    """SURVEY 8(f) N4 end to end: raw uint8 camera frames -> device area-resize -> FoV crop with the loader's fp16(v / 255)
+    conversion, against the host pipeline of the reference (cv2.resize INTER_AREA -> astype(float16) / 255 -> crop): bit-equal."""
+    import numpy as np
+    from oracle import area_resize as A
+
+    rng = np.random.default_rng(5)
+    raw = rng.integers(0, 256, size=(3, 3, 360, 362), dtype=np.uint8)            # front camera at a third of its size
+    host_small = A.scale_video(raw, 0.3)                                         # what the loader keeps ...
+    host_f16 = torch.from_numpy(host_small.astype(np.float16) / 255.0)           # ... and hands to the model
+    dev_small = ops.area_resize_u8(torch.from_numpy(raw).to(DEV), 0.3)
+    assert np.array_equal(dev_small.cpu().numpy(), host_small)
+    centers = torch.tensor([[0.5, 0.5], [0.3, 0.6], [0.7, 0.4]], device=DEV)
+    windows = torch.full((3, 2), 0.5, device=DEV)
+    spec = O.BackboneSpec()
+    a = ops.fov_crop(dev_small, centers, windows, 32, spec.mean, spec.std, patch=8, out_dtype=torch.float16, u8_as_f16=True)
+    b = ops.fov_crop(host_f16.to(DEV), centers, windows, 32, spec.mean, spec.std, patch=8, out_dtype=torch.float16)
+    assert torch.equal(a, b)

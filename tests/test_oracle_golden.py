@@ -1,4 +1,6 @@
 """CPU: the oracle restatement reproduces the golden vectors generated from the unmodified reference."""
+import os
+
 import pytest
 import torch
 
@@ -157,3 +159,45 @@ def test_eval_step_matches_reference():
     assert rel_err(samples, e["samples"]) < 2e-6 and rel_err(mean, e["mean_prediction"]) < 2e-6
     assert torch.allclose(losses, e["losses"], rtol=1e-5) and torch.allclose(ades, e["ades"], rtol=1e-5)
     assert torch.allclose(fdes, e["fdes"], rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ N4: dataset-side scaling
+def _resize_cases():
+    import numpy as np
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "area_resize.npz"))
+    names = sorted({k.split("/")[0] for k in z.files if "/" in k})
+    return z, names
+
+
+def test_area_resize_oracle_matches_the_cv2_golden_vectors():
+    """oracle/area_resize.py (numpy restatement of OpenCV's INTER_AREA for uint8) against outputs of cv2.resize itself, committed
+    as tests/golden/area_resize.npz by oracle/make_golden_resize.py: BIT-EXACT on every case (integral and non-integral scales,
+    the reference's four experiment factors)."""
+    import numpy as np
+    from oracle import area_resize as A
+
+    z, names = _resize_cases()
+    assert len(names) >= 9
+    for name in names:
+        x, y, f = z[name + "/x"], z[name + "/y"], float(z[name + "/factor"])
+        got = A.scale_video(x, f)
+        assert got.shape == y.shape and got.dtype == np.uint8, name
+        assert np.array_equal(got, y), (name, int((got != y).sum()))
+
+
+def test_area_resize_oracle_matches_cv2_at_the_reference_frame_sizes():
+    """Where OpenCV is importable (the build container): the oracle against cv2.resize on the frame sizes and factors of
+    experiments/full_comparison.py:107-110,124-125, including the GoPro row crop of io/dataset.py:1324-1338."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    from oracle import area_resize as A
+
+    rng = np.random.default_rng(1)
+    for (H, W), f, crop in (((2160, 3840), 0.1, True), ((1080, 1088), 0.3, False), ((1080, 1920), 0.4, True), ((720, 960), 1 / 3.0, False)):
+        x = rng.integers(0, 256, size=(1, 3, H, W), dtype=np.uint8)
+        if crop:
+            x = np.ascontiguousarray(A.crop_gopro_rows(x))
+        size = (int(x.shape[-1] * f), int(x.shape[-2] * f))
+        want = np.stack([cv2.resize(fr.transpose(1, 2, 0), size, None, None, None, cv2.INTER_AREA).transpose(2, 0, 1) for fr in x])
+        assert np.array_equal(A.scale_video(x, f), want), (H, W, f)
