@@ -10,6 +10,7 @@ run bench_fwd_bf16 --mode fwd --bf16 --no-eager-baseline --no-cpu-baseline
 run bench_eval_step --mode eval_step
 run bench_dreyeve_sweep --mode dreyeve_sweep --no-eager-baseline --no-cpu-baseline
 run bench_crop_micro --mode crop_micro
+run bench_stage_micro --mode stage_micro
 run bench_reference --impl reference
 timeout 600 python tools/microbench.py > gpurun_out/microbench.txt 2>&1; echo "microbench exit $?"
 timeout 300 python tools/attn_bench.py > gpurun_out/attn_bench.txt 2>&1; timeout 300 python tools/attn_bench.py --generic >> gpurun_out/attn_bench.txt 2>&1; echo "attn_bench exit $?"
