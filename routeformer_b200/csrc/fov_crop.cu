@@ -377,6 +377,92 @@ __device__ __forceinline__ void walk_dispatch(int mode, const Args& a, const Wal
   else walk_rows<TS, TD, WALK_EDGE, STAGED>(a, rows, ra, rb, ws, q, out0, ch_stride);
 }
 
+// Four adjacent output columns per thread (two pairs, both NARROW): the same walk with the per-row bookkeeping (row-table entry,
+// flags, branches, output addresses) paid once for twelve output values instead of six, and one 8 / 16-byte store per channel.
+template <typename TS, typename TD>
+__device__ __forceinline__ void walk_rows4(const Args& a, const WalkRow* __restrict__ rows, int ra, int rb, const WalkSrc<TS>& ws,
+                                           const WalkCols& qa, const WalkCols& qb, TD* __restrict__ out0, long long ch_stride) {
+  f32x2 ha[2][3], hb[2][3];  // pair A / pair B: [upper | lower source row][channel]
+  f32x2 shift[3], istd[3];
+  TD* oc[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    shift[c] = pk(-a.mean[c] * a.inv_std[c], -a.mean[c] * a.inv_std[c]);
+    istd[c] = pk(a.inv_std[c], a.inv_std[c]);
+    oc[c] = out0 + c * ch_stride;
+  }
+  auto load = [&](int rowoff, f32x2 (&da)[3], f32x2 (&db)[3]) {
+    walk_row<TS, WALK_NARROW, true>(ws, rowoff, qa, da);
+    walk_row<TS, WALK_NARROW, true>(ws, rowoff, qb, db);
+  };
+  auto emit = [&](const WalkRow& e, const f32x2 (&ua)[3], const f32x2 (&la)[3], const f32x2 (&ub)[3], const f32x2 (&lb)[3]) {
+    const f32x2 wy0 = pk(e.wy0, e.wy0), wy1 = pk(e.wy1, e.wy1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float2 o0 = upk(fma2(fma2(la[c], wy1, mul2(ua[c], wy0)), istd[c], shift[c]));
+      const float2 o1 = upk(fma2(fma2(lb[c], wy1, mul2(ub[c], wy0)), istd[c], shift[c]));
+      const float v[4] = {o0.x, o0.y, o1.x, o1.y};
+      store4(oc[c] + e.off, v);
+    }
+  };
+  int r = ra;
+  WalkRow e = rows[r];
+  {
+    const int rowoff = (walk_y0(e.code) - ws.y_lo) * ws.row_stride;
+    load(rowoff, ha[0], hb[0]);
+    load(rowoff + ws.row_stride, ha[1], hb[1]);
+  }
+#define RF_WALK4_BODY(A, B)                                                             \
+  for (;;) {                                                                            \
+    emit(e, ha[A], ha[B], hb[A], hb[B]);                                                \
+    if (++r >= rb) return;                                                              \
+    e = rows[r];                                                                        \
+    const int f = e.code >> 24;                                                         \
+    if (f & WALK_NEW) {                                                                 \
+      const int rowoff = (walk_y0(e.code) - ws.y_lo) * ws.row_stride;                   \
+      if (f & WALK_SHIFT) {                                                             \
+        load(rowoff + ws.row_stride, ha[A], hb[A]);                                     \
+        break;                                                                          \
+      }                                                                                 \
+      load(rowoff, ha[A], hb[A]);                                                       \
+      load(rowoff + ws.row_stride, ha[B], hb[B]);                                       \
+    }                                                                                   \
+  }
+  for (;;) {
+    RF_WALK4_BODY(0, 1)
+    RF_WALK4_BODY(1, 0)
+  }
+#undef RF_WALK4_BODY
+}
+
+// column taps of the pair (ox, ox + 1): weights, tap validity, mode; x0 = first tap column of either pixel
+template <typename FX, typename FC>
+__device__ __forceinline__ int walk_setup_pair(int ox, int W, FX sample_x, FC floor_clamped, WalkCols& q, int (&x0)[2]) {
+  float w0[2], w1[2];
+  bool interior = true;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float sx = sample_x(ox + i);
+    x0[i] = floor_clamped(sx, W);
+    w1[i] = sx - floorf(sx);
+    w0[i] = 1.0f - w1[i];
+    q.ok[2 * i] = x0[i] >= 0 && x0[i] < W;
+    q.ok[2 * i + 1] = x0[i] + 1 >= 0 && x0[i] + 1 < W;
+    interior = interior && q.ok[2 * i] && q.ok[2 * i + 1];
+  }
+  const int d = x0[1] - x0[0];
+  const bool narrow = interior && (d == 0 || d == 1) && x0[0] + 2 < W;
+  q.w[0] = w0[0]; q.w[1] = w1[0];
+  if (narrow) {
+    q.w[2] = d ? 0.0f : w0[1];
+    q.w[3] = d ? w0[1] : w1[1];
+    q.w[4] = d ? w1[1] : 0.0f;
+  } else {
+    q.w[2] = w0[1]; q.w[3] = w1[1]; q.w[4] = 0.0f;
+  }
+  return narrow ? WALK_NARROW : (interior ? WALK_WIDE : WALK_EDGE);
+}
+
 template <int IMM>
 __device__ __forceinline__ void cp_async_4(unsigned smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%2], 4;" ::"r"(smem_dst), "l"(gmem_src), "n"(IMM) : "memory");
@@ -548,6 +634,136 @@ __global__ void __launch_bounds__(WALK_THREADS, 8) fov_crop_walk_kernel(const Ar
   }
 }
 
+// The staged walk with FOUR adjacent output columns per thread (default when the output is 16-byte aligned).  A CTA is two
+// groups of `cols` threads; both share the staged window of the strip, each walks one half of its rows (warp-uniform control).
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(WALK_THREADS, 6) fov_crop_walk4_kernel(const Args a, const int strip_rows, const int cols) {
+  typedef typename RawPx<TS>::type Raw;
+  extern __shared__ __align__(16) unsigned char walk_stage[];
+  __shared__ WalkRow s_rows[WALK_MAX_ROWS];
+  const int n = blockIdx.y, r0 = blockIdx.x * strip_rows, tid = threadIdx.x;
+  const int S = a.S, H = a.H, W = a.W;
+  const int nrows = min(strip_rows, S - r0);
+  const float cx = __ldg(a.centers + 2 * n), cy = __ldg(a.centers + 2 * n + 1);
+  const float fw = __ldg(a.windows + 2 * n), fh = __ldg(a.windows + 2 * n + 1);
+  const long long src_frame = a.frame_ids ? __ldg(a.frame_ids + n) : n;
+  const int plane = H * W;
+  const Raw* src = reinterpret_cast<const Raw*>(a.frames) + src_frame * 3ll * plane;
+  const float inv_s = 1.0f / S;
+  auto sample_x = [&](int ox) { return ((fw * ((2 * ox + 1) * inv_s - 1.0f) + (2.0f * cx - 1.0f) + 1.0f) * W - 1.0f) * 0.5f; };
+  auto sample_y = [&](int oy) { return ((fh * ((2 * oy + 1) * inv_s - 1.0f) + (2.0f * cy - 1.0f) + 1.0f) * H - 1.0f) * 0.5f; };
+  auto floor_clamped = [](float v, int hi) { return static_cast<int>(fminf(fmaxf(floorf(v), -3.0f), static_cast<float>(hi))); };
+
+  if (tid < nrows) {  // the strip's row table (identical to fov_crop_walk_kernel's)
+    const int oy = r0 + tid;
+    const float sy = sample_y(oy);
+    const int y0 = floor_clamped(sy, H), yp = floor_clamped(sample_y(oy - 1), H);
+    const int flags = (y0 != yp ? WALK_NEW : 0) | (y0 == yp + 1 ? WALK_SHIFT : 0) | (y0 >= 0 && y0 < H ? WALK_A_IN : 0) |
+                      (y0 + 1 >= 0 && y0 + 1 < H ? WALK_B_IN : 0);
+    WalkRow ri;
+    ri.code = (y0 + 4) | (flags << 24);
+    ri.wy1 = sy - floorf(sy);
+    ri.wy0 = 1.0f - ri.wy1;
+    if (a.patch > 0) {
+      const int py = fast_div(oy, a.patch_magic), iy = oy - py * a.patch;
+      ri.off = py * a.G * static_cast<int>(a.out_ld) + iy * a.patch;
+    } else {
+      ri.off = oy * S;
+    }
+    s_rows[tid] = ri;
+  }
+
+  const int group = tid >= cols ? 1 : 0;
+  const int ox = 4 * (tid - group * cols);
+  WalkCols qa, qb;
+  int xa[2], xb[2];
+  const int mode_a = walk_setup_pair(ox, W, sample_x, floor_clamped, qa, xa);
+  const int mode_b = walk_setup_pair(ox + 2, W, sample_x, floor_clamped, qb, xb);
+
+  TD* out = reinterpret_cast<TD*>(a.out);
+  long long ch_stride;
+  if (a.patch > 0) {
+    const int px = fast_div(min(ox, S - 4), a.patch_magic), ix = ox - px * a.patch;
+    out += (static_cast<long long>(n) * a.G * a.G + px) * a.out_ld + ix;
+    ch_stride = static_cast<long long>(a.patch) * a.patch;
+  } else {
+    out += static_cast<long long>(n) * 3 * S * S + ox;
+    ch_stride = static_cast<long long>(S) * S;
+  }
+  const bool worker = ox < S;
+
+  constexpr int ES = sizeof(Raw), EPW = 4 / ES;
+  const int xf = floor_clamped(sample_x(0), W), xl = floor_clamped(sample_x(S - 1), W);
+  const int j_lo = (max(min(xf, xl), 0) / EPW) * EPW;
+  const int j_hi = min(max(xf, xl) + 2, W - 1);
+  const int words = j_hi >= j_lo ? (j_hi - j_lo + EPW) / EPW : 0;
+  const int pitch_b = 4 * words;
+  const int rows_fit = words > 0 ? WALK_STAGE_BYTES / (3 * pitch_b) : (1 << 20);
+  qa.k[0] = (xa[0] - j_lo) * ES; qa.k[1] = (xa[1] - j_lo) * ES;
+  qb.k[0] = (xb[0] - j_lo) * ES; qb.k[1] = (xb[1] - j_lo) * ES;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const bool cp0 = lane < words, cp1 = lane + 32 < words, cp2 = lane + 64 < words, cp3 = lane + 96 < words;
+  unsigned stage_addr = static_cast<unsigned>(__cvta_generic_to_shared(walk_stage));
+  asm volatile("" : "+r"(stage_addr));
+  __syncthreads();  // row table
+
+  int ra = 0;
+  while (ra < nrows) {  // chunks of output rows whose source rows fit the staging buffer (CTA-uniform; normally one)
+    int lo = walk_y0(s_rows[ra].code), hi = lo, rb;
+    {
+      const int ye = walk_y0(s_rows[nrows - 1].code);
+      const int l2 = min(lo, ye), h2 = max(hi, ye);
+      if (h2 + 1 - l2 + 1 <= rows_fit) {
+        lo = l2; hi = h2; rb = nrows;
+      } else {
+        rb = ra + 1;
+        while (rb < nrows) {
+          const int y = walk_y0(s_rows[rb].code);
+          const int nl = min(lo, y), nh = max(hi, y);
+          if (nh + 1 - nl + 1 > rows_fit) break;
+          lo = nl; hi = nh; ++rb;
+        }
+      }
+    }
+    const int y_lo = lo, n_src = hi + 1 - lo + 1;
+    if (words > 0) {
+      for (int c = 0; c < 3; ++c) {
+        const unsigned char* g = reinterpret_cast<const unsigned char*>(src + (c * plane + (y_lo + warp) * W + j_lo)) + 4 * lane;
+        unsigned sa = stage_addr + static_cast<unsigned>(c * n_src + warp) * pitch_b + 4 * lane;
+        for (int yr = warp; yr < n_src; yr += nwarps, g += nwarps * W * ES, sa += nwarps * pitch_b) {
+          if (y_lo + yr >= 0 && y_lo + yr < H) {  // warp-uniform
+            if (cp0) cp_async_4<0>(sa, g);
+            if (cp1) cp_async_4<128>(sa, g);
+            if (cp2) cp_async_4<256>(sa, g);
+            if (cp3) cp_async_4<384>(sa, g);
+            for (int wd = lane + 128; wd < words; wd += 32) cp_async_4<0>(sa + 4 * (wd - lane), g + 4 * (wd - lane));
+          } else {
+            for (int wd = lane; wd < words; wd += 32) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa + 4 * (wd - lane)), "r"(0) : "memory");
+          }
+        }
+      }
+      cp_async_wait_all();
+    }
+    __syncthreads();
+    if (worker) {
+      const int per = (rb - ra + 1) >> 1;  // rows of the chunk per group
+      const int ga = ra + group * per, gb = min(ga + per, rb);
+      if (ga < gb) {
+        WalkSrc<TS> ws;
+        ws.base = nullptr; ws.sbase = stage_addr; ws.y_lo = y_lo; ws.row_stride = pitch_b; ws.ch_stride = n_src * pitch_b;
+        if (mode_a == WALK_NARROW && mode_b == WALK_NARROW) {
+          walk_rows4<TS, TD>(a, s_rows, ga, gb, ws, qa, qb, out, ch_stride);
+        } else {  // a pair at the frame border / a down-sampling window: the two-column walk, once per pair
+          walk_dispatch<TS, TD, true>(mode_a, a, s_rows, ga, gb, ws, qa, out, ch_stride);
+          walk_dispatch<TS, TD, true>(mode_b, a, s_rows, ga, gb, ws, qb, out + 2, ch_stride);
+        }
+      }
+    }
+    ra = rb;
+    if (ra < nrows) __syncthreads();
+  }
+}
+
 // RF_CROP_DIRECT=1 selects the round-1 direct gather, RF_CROP_NOSTAGE=1 the walker without shared-memory staging (read per
 // call so tests and A/B runs can toggle them).
 static bool env_on(const char* name) {
@@ -565,7 +781,13 @@ static int launch_walk(const RfFovCropParams* p, const Args& a, cudaStream_t s) 
   // cp.async moves 4-byte words: frame base and row pitch must be 4-byte aligned, and two staged rows must fit
   const bool staged = !env_on("RF_CROP_NOSTAGE") && reinterpret_cast<uintptr_t>(p->frames) % 4 == 0 && (p->W * es) % 4 == 0 &&
                       6 * (p->W * es + 8) <= static_cast<size_t>(WALK_STAGE_BYTES);
-  if (staged) {
+  // four columns per thread: 16-byte aligned output rows (S and the patch size are multiples of 4 already)
+  const bool quad = staged && !env_on("RF_CROP_PAIRS") && reinterpret_cast<uintptr_t>(p->out) % 16 == 0 &&
+                    (p->patch == 0 || p->out_ld % 8 == 0);
+  if (quad) {
+    const int cols = ((S / 4 + 31) / 32) * 32;
+    fov_crop_walk4_kernel<TS, TD><<<grid, 2 * cols, WALK_STAGE_BYTES, s>>>(a, strip, cols);
+  } else if (staged) {
     RF_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(fov_crop_walk_kernel<TS, TD, true>), WALK_STAGE_BYTES));
     fov_crop_walk_kernel<TS, TD, true><<<grid, threads, WALK_STAGE_BYTES, s>>>(a, strip);
   } else {

@@ -217,14 +217,15 @@ def test_gemm_dact_and_accumulate(ops):
 
 
 # ------------------------------------------------------------------------------------------------ FoV crop
-# the three crop kernels: separable column walker with cp.async-staged source window (default), the same walk reading global
-# memory (unaligned frames), and the round-1 direct 4-tap gather (tall frames)
-CROP_KERNELS = ["staged", "walk", "direct"]
+# the crop kernels: separable column walker over a cp.async-staged source window with four (default) or two output columns per
+# thread, the same walk reading global memory (unaligned frames), and the round-1 direct 4-tap gather (tall frames)
+CROP_KERNELS = ["staged", "pairs", "walk", "direct"]
 
 
 def select_crop_kernel(monkeypatch, kernel):
     monkeypatch.setenv("RF_CROP_DIRECT", "1" if kernel == "direct" else "0")
     monkeypatch.setenv("RF_CROP_NOSTAGE", "1" if kernel == "walk" else "0")
+    monkeypatch.setenv("RF_CROP_PAIRS", "1" if kernel == "pairs" else "0")
     monkeypatch.setenv("RF_CROP_WALK", "1")  # (the walker also for tall frames, which the dispatcher would hand to the direct kernel)
 
 
