@@ -5,10 +5,13 @@
 // with zeros outside the frame, then normalised per channel, written either planar [n,3,S,S] or directly in the
 // patch-major layout the patch-embedding GEMM consumes as its A operand (no im2col pass).
 //
-// fov_crop_walk_kernel (default): the bilinear resample is SEPARABLE and its column taps are shared by the three channels.
-// A thread owns two adjacent output columns and walks down the output rows of its CTA's strip with the horizontal blends
-// of the current two source rows in registers (no shared-memory staging); see the kernel's comment.
-// fov_crop_kernel (the round-1 direct 4-tap gather, issue-bound at 0.3 of the HBM roofline) remains behind RF_CROP_DIRECT=1.
+// fov_crop_walk4_kernel / fov_crop_walk_kernel (default): the bilinear resample is SEPARABLE and its column taps are shared by the
+// three channels.  The source window of a strip of output rows is staged RAW in shared memory with cp.async; a thread owns four
+// (walk4) or two adjacent output columns and walks down the output rows of the strip with the horizontal blends of the current
+// two source rows in registers; see the kernels' comments.  Frames whose rows are not 4-byte aligned take the same walk from
+// global memory.
+// fov_crop_kernel (the round-1 direct 4-tap gather, issue-bound at 0.3 of the HBM roofline on the gaze crop) remains for frames
+// taller than twice the crop (down-sampling: no row re-use) and behind RF_CROP_DIRECT=1.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
