@@ -941,6 +941,8 @@ static int launch(const RfGemmParams* p, const Args& args, int splits, cudaStrea
   // Short reductions (<= 12 k-blocks per tile: the K=128/256/384 layers) are epilogue/latency-bound -> persistent kernel whose
   // loads run ahead across tiles.  Long reductions are L2-bandwidth-bound -> two co-resident tile-wise CTAs per SM keep more
   // bytes in flight (2 x 3 stages) and measured 25-35 % faster there (profiles/r1_microbench_gemm_*).
+  // (the persistent kernel also for launches of at most one tile per SM -- the M = 2 560 ... 10 240 layers of the gaze / video
+  //  encoders, ~200 per step: the lighter tile-wise kernel there measured +0.38 ms per step, its 4 epilogue warps take all columns)
   if (persistent && args.kb_per_split <= 12 && !f16) {
     const long long total = static_cast<long long>(tiles_n) * tiles_m * splits;
     RF_CHECK_ARG(total <= 2147483647LL, "rf_gemm_tf32: too many tiles");
