@@ -192,6 +192,10 @@ __global__ void __launch_bounds__(AREA_THREADS) area_resize_words_kernel(const A
 #pragma unroll
     for (int i = 0; i < NW; ++i) al[i] = __funnelshift_r(w[i], w[i + 1], wx.shift_bits);
   };
+  // A source row that is the partial LAST row of one destination cell is the partial FIRST row of the next one (the cells tile
+  // the axis): its horizontal cell sum is kept instead of being loaded and summed again.
+  float buf_last = 0.0f;
+  int row_last = -1;
   for (int r = 0; r < nrows; ++r) {
     int first_row, n_src;
     Cell cy;
@@ -206,7 +210,12 @@ __global__ void __launch_bounds__(AREA_THREADS) area_resize_words_kernel(const A
     const unsigned* row = base + static_cast<long long>(first_row) * pitch_w;
     float acc = 0.0f;
     int isum = 0;
-    for (int j0 = 0; j0 < n_src; j0 += RB) {
+    int j_begin = 0;
+    if (!FAST && cy.has_left && first_row == row_last) {  // CTA-uniform
+      acc = __fmul_rn(cy.a_left, buf_last);
+      j_begin = 1;
+    }
+    for (int j0 = j_begin; j0 < n_src; j0 += RB) {
       unsigned al[RB][NW];
 #pragma unroll
       for (int jj = 0; jj < RB; ++jj) load_row(row + static_cast<long long>(j0 + jj) * pitch_w, j0 + jj < n_src, al[jj]);
@@ -226,10 +235,12 @@ __global__ void __launch_bounds__(AREA_THREADS) area_resize_words_kernel(const A
             }
             const float beta = (cy.has_left && j == 0) ? cy.a_left : ((j < cy.has_left + cy.n_full) ? cy.a_full : cy.a_right);
             acc = j == 0 ? __fmul_rn(beta, buf) : __fadd_rn(acc, __fmul_rn(beta, buf));
+            buf_last = buf;  // (after the loop: the sum of the cell's last source row)
           }
         }
       }
     }
+    row_last = first_row + n_src - 1;
     int v;
     if (FAST) v = (a.iscale_x == 2 && a.iscale_y == 2) ? ((isum + 2) >> 2) : __float2int_rn(__fmul_rn(static_cast<float>(isum), inv_area));
     else v = __float2int_rn(acc);
