@@ -499,6 +499,33 @@ def test_gaze_centred_fov_and_plugin_api():
     assert rel_err(feats.float().cpu(), ref.float()) < 3e-3
 
 
+def test_uint8_frames_equal_the_loaders_fp16_frames():
+    """SURVEY 8(f) N4 at model level (`bench.py --u8-frames`): raw uint8 frames, staged by `stage_batch` (only the consumed
+    frames travel) and converted in the crop kernel, give the SAME BITS as the fp16 frames the reference's loader makes of them
+    (`astype(float16) / 255`, io/dataset.py:1522).  The frames only enter the crop kernel (frozen backbone), so identical patch
+    bits make everything downstream -- the training step included -- the same computation."""
+    gold = load_golden("full_small_eval")
+    cfg, spec, sd, batch = case_from_golden(gold)
+    raw = {k: ((v.float() * 255.0).round().clamp(0, 255).to(torch.uint8) if k.endswith("_video") else v) for k, v in batch.items()}
+    loader = {k: (torch.from_numpy(v.numpy().astype("float16") / 255.0) if k.endswith("_video") else v) for k, v in raw.items()}
+    assert all(loader[k].dtype == torch.float16 for k in loader if k.endswith("_video"))
+    model = build_product(cfg, spec, fov="gaze").to(DEV).eval()
+    model.load_state_dict(sd)
+    outs = []
+    for host in (raw, loader):
+        staged = model.stage_batch({k: v.contiguous().pin_memory() for k, v in host.items()}, torch.device(DEV))
+        torch.manual_seed(3)
+        with torch.no_grad():
+            outs.append(model(staged))
+    assert outs[0][0].dtype == torch.float32
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    # the unstaged uint8 clip (all 40 frames resident) reads the same frames
+    torch.manual_seed(3)
+    with torch.no_grad():
+        wp, dense = model(to_device(raw, DEV))
+    assert torch.equal(wp, outs[0][0]) and torch.equal(dense, outs[0][1])
+
+
 def test_target_pass_and_errors():
     """preprocess_batch(target, training=False) on the 30 target frames (full_comparison.py:482) + error behaviour."""
     gold = load_golden("full_small_eval")
