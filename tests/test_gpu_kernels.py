@@ -798,6 +798,44 @@ def test_area_resize_bit_exact(ops):
         ops.area_resize_u8(torch.zeros(1, 3, 8, 8, device=DEV), 0.5)
 
 
+def test_area_resize_random_shapes(ops):
+    """rf_area_resize_u8 against the oracle (itself equal to cv2 on thousands of random shapes) away from the reference's frame
+    sizes: every cell-width class of the word-streamed kernel (4 / 5 / 9 / 10 / 13 bytes) and the byte kernel behind it (rows that
+    are not a multiple of 4 bytes wide, cells wider than 13 bytes), integral scale on one axis only, identity on one axis,
+    one-pixel outputs, a row range; BIT-EXACT uint8."""
+    import numpy as np
+    from oracle import area_resize as A
+
+    rng = np.random.default_rng(11)
+    cases = []
+    for lo, hi in ((1.01, 2.0), (2.0, 3.0), (3.0, 7.0), (7.0, 8.0), (8.0, 11.0), (11.0, 20.0)):   # horizontal scale ranges
+        for _ in range(6):
+            dW = int(rng.integers(3, 40))
+            W = 4 * max(1, int(round(dW * rng.uniform(lo, hi) / 4)))
+            dW = min(dW, W)
+            H = int(rng.integers(5, 70))
+            cases.append((H, W, int(rng.integers(1, H + 1)), dW))
+    for _ in range(30):                                                                      # anything goes (byte kernel when W % 4 != 0)
+        H, W = int(rng.integers(2, 90)), int(rng.integers(2, 130))
+        cases.append((H, W, int(rng.integers(1, H + 1)), int(rng.integers(1, W + 1))))
+    for _ in range(12):                                                                      # integral scales: both axes / x only / y only
+        iy, ix = int(rng.integers(1, 6)), int(rng.integers(1, 14))
+        dH, dW = int(rng.integers(1, 20)), 4 * int(rng.integers(1, 12))
+        cases += [(dH * iy, dW * ix, dH, dW), (dH * iy + 3, dW * ix, dH, dW), (dH * iy, dW * ix + 4, dH, dW)]
+    cases += [(16, 64, 16, 64), (16, 64, 16, 20), (16, 64, 5, 64), (9, 12, 1, 1), (40, 128, 1, 128), (40, 128, 40, 1)]
+    for H, W, dH, dW in cases:
+        x = rng.integers(0, 256, size=(2, 2, H, W), dtype=np.uint8)
+        want = A.area_resize_u8(x, (dH, dW))
+        got = ops.area_resize_u8(torch.from_numpy(x).to(DEV), out_hw=(dH, dW)).cpu().numpy()
+        assert got.shape == want.shape and np.array_equal(got, want), (H, W, dH, dW, int((got != want).sum()))
+    # a row range (source pointer moved by r0 rows, plane stride unchanged) at a non-integral and an integral scale
+    for (H, W, r0, r1, dH, dW) in ((60, 96, 7, 51, 13, 29), (60, 96, 12, 52, 10, 24)):
+        x = rng.integers(0, 256, size=(3, H, W), dtype=np.uint8)
+        want = A.area_resize_u8(np.ascontiguousarray(x[:, r0:r1]), (dH, dW))
+        got = ops.area_resize_u8(torch.from_numpy(x).to(DEV), out_hw=(dH, dW), rows=(r0, r1)).cpu().numpy()
+        assert np.array_equal(got, want), (H, W, r0, r1, dH, dW, int((got != want).sum()))
+
+
 def test_area_resize_then_crop_equals_the_host_pipeline(ops):
     """SURVEY 8(f) N4 end to end: raw uint8 camera frames -> device area-resize -> FoV crop with the loader's fp16(v / 255)
     conversion, against the host pipeline of the reference (cv2.resize INTER_AREA -> astype(float16) / 255 -> crop): bit-equal."""
