@@ -45,6 +45,46 @@ def test_gemm_layouts(ops, a_mn, b_mn, M, N, K):
     assert rel_err(out.cpu(), ref) < 2e-3
 
 
+def test_gemm_random_shapes(ops):
+    """Random problem sizes (ragged edge tiles in M and N, one- and few-row problems, K from one MMA to the split-K range) in every
+    operand layout the pitches allow, with the epilogues of the model's layers; the output is pre-filled with NaN so that a
+    tile that is never written shows."""
+    gen = g(77)
+    ri = lambda lo, hi: int(torch.randint(lo, hi, (1,), generator=gen))
+    failures = []
+    for i in range(40):
+        M, N, K = ri(1, 2500), ri(1, 700), 4 * ri(1, 375)
+        if i % 8 == 0:
+            M, N = ri(1, 9), ri(1, 9)
+        a_mn, b_mn = bool(ri(0, 2)) and M % 4 == 0, bool(ri(0, 2)) and N % 4 == 0
+        A, B = torch.randn(M, K, generator=gen), torch.randn(N, K, generator=gen) / math.sqrt(K)
+        bias, res, c0 = torch.randn(N, generator=gen), torch.randn(M, N, generator=gen), torch.randn(M, N, generator=gen)
+        Ad = (A.t().contiguous() if a_mn else A).to(DEV)
+        Bd = (B.t().contiguous() if b_mn else B).to(DEV)
+        prod = (A.double() @ B.double().t()).float()
+        epi = i % 4
+        if epi == 0:
+            out = torch.full((M, N), float("nan"), device=DEV)
+            ops.gemm(Ad, Bd, out, a_mn=a_mn, b_mn=b_mn)
+            ref = prod
+        elif epi == 1:
+            out = torch.full((M, N), float("nan"), device=DEV)
+            ops.gemm(Ad, Bd, out, a_mn=a_mn, b_mn=b_mn, bias=bias.to(DEV), residual=res.to(DEV))
+            ref = prod + bias + res
+        elif epi == 2:
+            out = c0.clone().to(DEV)
+            ops.gemm(Ad, Bd, out, a_mn=a_mn, b_mn=b_mn, accumulate=True)
+            ref = prod + c0
+        else:
+            out = torch.full((M, N), float("nan"), device=DEV)
+            ops.gemm(Ad, Bd, out, a_mn=a_mn, b_mn=b_mn, bias=bias.to(DEV), act=ops.ACT_GELU)
+            ref = F.gelu(prod + bias)
+        got = out.cpu()
+        if not (torch.isfinite(got).all() and (got - ref).norm() < 2e-3 * max(float(ref.norm()), 1e-3 * math.sqrt(M * N))):
+            failures.append((i, M, N, K, a_mn, b_mn, epi, rel_err(got, ref)))
+    assert not failures, failures
+
+
 def test_gemm_epilogue_forward(ops):
     gen = g(1)
     M, N, K, period = 260, 136, 72, 65
@@ -636,6 +676,36 @@ def test_layernorm(ops, M, D):
     dx, dg, db = torch.empty(M, D, device=DEV), torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
     ops.layernorm_bwd(dy.to(DEV), xd, gd, mean, rstd, dx, dg, db)
     assert rel_err(dx.cpu(), x.grad) < 1e-5 and rel_err(dg.cpu(), gamma.grad) < 1e-5 and rel_err(db.cpu(), beta.grad) < 1e-5
+
+
+def test_layernorm_random_shapes(ops):
+    """Row counts that leave partial warp passes (the rows kernel takes four rows per warp for D <= 128), widths from 1 to
+    the kernels' limit of 1 024 including odd ones, single rows."""
+    gen = g(31)
+    ri = lambda lo, hi: int(torch.randint(lo, hi, (1,), generator=gen))
+    failures = []
+    for i in range(24):
+        M = ri(1, 8) if i % 6 == 0 else ri(1, 700)
+        D = [ri(1, 130), ri(1, 130), ri(130, 1025), 4 * ri(1, 33)][i % 4]  # (the kernels take D <= 1024)
+        x = (torch.randn(M, D, generator=gen) * 3 + 1).requires_grad_()
+        gamma, beta = (1 + 0.1 * torch.randn(D, generator=gen)).requires_grad_(), torch.randn(D, generator=gen).requires_grad_()
+        ref = F.layer_norm(x, (D,), gamma, beta, 1e-5)
+        dy = torch.randn(M, D, generator=gen)
+        ref.backward(dy)
+        y, mean, rstd = torch.empty(M, D, device=DEV), torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+        xd, gd, bd = x.detach().to(DEV), gamma.detach().to(DEV), beta.detach().to(DEV)
+        ops.layernorm_fwd(xd, gd, bd, y, mean, rstd)
+        dx, dg, db = torch.empty(M, D, device=DEV), torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+        ops.layernorm_bwd(dy.to(DEV), xd, gd, mean, rstd, dx, dg, db)
+        if D == 1:  # one channel: y = beta, dx = 0 exactly; nothing relative to compare
+            ok = torch.allclose(y.cpu(), ref.detach(), atol=2e-5) and float(dx.abs().max()) < 1e-4
+        else:
+            ok = ((y.cpu() - ref.detach()).abs().max() < 5e-5 and rel_err(dx.cpu(), x.grad) < 2e-5 and
+                  rel_err(dg.cpu(), gamma.grad) < 2e-5 and rel_err(db.cpu(), beta.grad) < 2e-5)
+        if not ok:
+            failures.append((i, M, D, float((y.cpu() - ref.detach()).abs().max()), rel_err(dx.cpu(), x.grad), rel_err(dg.cpu(), gamma.grad),
+                             rel_err(db.cpu(), beta.grad)))
+    assert not failures, failures
 
 
 @pytest.mark.parametrize("training", [True, False])
