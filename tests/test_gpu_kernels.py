@@ -449,6 +449,12 @@ ATTN_CASES = [
     (5, 8, 33, 33, 16, 4, "prob", "blhd"),
     (3, 2, 79, 79, 16, 5, "prob", "bhld"),
     (7, 4, 48, 48, 16, 5, "prob", "blhd"),
+    # head sizes outside the model's own (8 / 16 / 104): the generic kernels with a run-time head dimension, every mode
+    (2, 4, 40, 40, 32, 5, "prob", "blhd"),
+    (3, 2, 50, 50, 64, 4, "prob_masked", "bhld"),
+    (3, 3, 24, 30, 12, 5, "full", "blhd"),
+    (2, 4, 130, 130, 20, 5, "prob", "bhld"),
+    (2, 2, 33, 70, 48, 4, "prob", "blhd"),
 ]
 
 
