@@ -557,7 +557,12 @@ class Routeformer(nn.Module):
         else:  # foreign GPS backbone plugin (routeformer.py:241)
             out = gb(x[:, :, :enc_in])
         if c.decoder_mode == "recursive":
-            out = out + (x[:, -1:, :out.shape[-1]] if c.dense_prediction else x[:, -1:, :2])
+            if c.dense_prediction and out.shape[-1] != enc_in:
+                # routeformer.py:244-245 adds the WHOLE last input row (enc_in columns) to an output of c_out = enc_in - 3 columns:
+                # the reference cannot run decoder_mode="recursive" together with dense_prediction, and neither does this
+                raise RuntimeError(f"The size of tensor a ({out.shape[-1]}) must match the size of tensor b ({enc_in}) at non-singleton "
+                                   "dimension 2 (decoder_mode='recursive' with dense_prediction, routeformer.py:245)")
+            out = out + (x[:, -1:, :enc_in] if c.dense_prediction else x[:, -1:, :2])
         return out, origin
 
     def postprocess_batch(self, last_input_gps, output, origin=None):

@@ -63,3 +63,54 @@ def test_target_pass_shapes():
     torch.manual_seed(1)
     _, v = O.Routeformer(sd, SMALL, SPEC).preprocess(tgt, False, O.CpuRandint())
     assert v.shape == v_ref.shape and torch.equal(v, v_ref)
+
+
+def test_random_configurations_against_the_reference():
+    """The oracle against the unmodified reference away from the golden configurations: random draws over decoder_mode (vanilla /
+    recursive / smart), modalities (GPS only, scene, gaze, both), dense prediction, rotate / normalise, distillation, activation,
+    layer / head counts, history and horizon lengths, batch sizes.  Waypoints agree to 1e-6, dense features to 2e-5; where the
+    reference itself cannot run a configuration (decoder_mode="recursive" with dense_prediction adds a 37-column input row to a
+    34-column output, routeformer.py:244-245) the oracle raises the same RuntimeError."""
+    import random
+
+    rnd = random.Random(0)
+    ran = raised = 0
+    for i in range(16):
+        with_video = rnd.random() < 0.8
+        with_scene = rnd.random() < 0.7
+        with_gaze = with_video and rnd.random() < 0.7
+        if with_video and not (with_scene or with_gaze):
+            with_gaze = True
+        cfg = O.OracleConfig(
+            seq_len=rnd.choice([20, 40]), pred_len=rnd.choice([10, 30]), d_model=rnd.choice([32, 64]), n_heads=rnd.choice([2, 4]),
+            e_layers=rnd.choice([1, 2, 3]), d_layers=rnd.choice([1, 2]), d_ff=rnd.choice([64, 128]), factor=rnd.choice([3, 4, 5]),
+            distil=rnd.random() < 0.7, activation=rnd.choice(["relu", "gelu"]), decoder_mode=rnd.choice(["vanilla", "recursive", "smart"]),
+            with_video=with_video, with_scene=with_scene, with_gaze=with_gaze, dense_prediction=with_video and rnd.random() < 0.6,
+            image_embedding_size=32, encoder_hidden_size=32, encoder_heads=rnd.choice([4, 8]), encoder_layers=rnd.choice([1, 2]),
+            encoder_d_ff=64, cross_modal_decoder_heads=rnd.choice([4, 8]), cross_modal_decoder_layers=rnd.choice([1, 2]),
+            rotate_motion=rnd.random() < 0.5, normalize_motion=rnd.random() < 0.5, motion_mean=1.8, motion_std=0.9)
+        spec = SPEC if with_video else None
+        model = R.build_reference_model(cfg, spec).eval()
+        sd = O.fill_state_dict(O.state_dict_template(cfg, spec), 20 + i)
+        model.load_state_dict(sd)
+        batch = O.synthetic_batch(rnd.choice([1, 2, 3]), cfg, "tiny", seed=i)
+        torch.manual_seed(12345)
+        try:
+            with torch.no_grad():
+                ref = model(batch)
+        except RuntimeError as err:
+            assert cfg.decoder_mode == "recursive" and cfg.dense_prediction, (i, err)
+            torch.manual_seed(12345)
+            with pytest.raises(RuntimeError, match="must match the size of tensor b"):
+                O.Routeformer(sd, cfg, spec).forward(batch)
+            raised += 1
+            continue
+        torch.manual_seed(12345)
+        out = O.Routeformer(sd, cfg, spec).forward(batch)
+        ref = ref if isinstance(ref, tuple) else (ref, None)
+        out = out if isinstance(out, tuple) else (out, None)
+        assert (out[0] - ref[0]).abs().max() <= 1e-6 * ref[0].abs().max(), (i, cfg)
+        if ref[1] is not None:
+            assert (out[1] - ref[1]).abs().max() <= 2e-5 * ref[1].abs().max(), (i, cfg)
+        ran += 1
+    assert ran >= 12 and raised >= 1, (ran, raised)
