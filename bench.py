@@ -665,7 +665,7 @@ def run_fwd(args):
 
     dist, world, rank, local, dev, barrier, max_over_ranks = dist_setup(args)
     B = args.batch_per_gpu
-    host_batch, _ = build_case(B, seed=100 + rank)
+    host_batch, _ = build_case(B, seed=100 + rank, u8=args.u8_frames)
     torch.manual_seed(0)
     model = build_model(args.fov).to(dev).eval()
     run = _forward_runner(model, dev, not args.no_graph)
@@ -715,7 +715,8 @@ def run_fwd(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": _dtype_note(args, "tf32 (fp32 storage, fp32 accumulate; fp16 patch embedding)"), "data": "synthetic",
                 "config": {"workload": "BASELINE configs[1]: Routeformer GPS+scene video+gaze FoV forward (eval), paper config, random-init patch "
                                        "backbone, GEM-shaped clips", "batch_per_gpu": B, "global_batch": world * B, "fov": args.fov,
-                           "cuda_graph": not args.no_graph, "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB per step per GPU)"},
+                           "cuda_graph": not args.no_graph, "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB per step per GPU)",
+                           "frames": "raw uint8 frames, converted in the crop kernel (SURVEY 8(f) N4)" if args.u8_frames else "fp16 frames, as the reference's loader hands them over"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": round(world * B * e2e_steps / (ms_e2e / 1e3), 2), "unit": "clips/s", "h2d_bytes_per_step": int(in_bytes),
                         "d2h_bytes_per_step": int(wp_host.numel() * 4), "steps": e2e_steps},
@@ -1016,7 +1017,7 @@ def main():
                     help="train = the headline metric (BASELINE configs[2], default); fwd = configs[1]; dreyeve_sweep = configs[3]; "
                          "crop_micro = configs[4]; eval_step = the _eval_step caller (SURVEY 8(f) N2)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU comparator")
-    ap.add_argument("--u8-frames", action="store_true", help="host batch holds raw uint8 frames (half the H2D bytes); converted in the crop kernel")
+    ap.add_argument("--u8-frames", action="store_true", help="train / fwd modes: the host batch holds raw uint8 frames (half the H2D bytes); converted in the crop kernel")
     ap.add_argument("--paper-dropout", action="store_true", help="train with the paper's dropouts (view 0.6 / gaze 0.2 / feature 0.05)")
     ap.add_argument("--async-loss", action="store_true", help="e2e leg experiment: read each step's loss one step behind instead of a blocking .item().  Measured SLOWER (2 210 vs 3 113 "
                          "clips/s): with the host a step ahead, the next step's small H2D copies queue behind the 529 MB staging transfer")
