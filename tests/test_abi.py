@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from routeformer_b200 import _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -100,3 +102,31 @@ def test_patch_reference_rebinds_the_path_symbols():
         for k in [k for k in sys.modules if k == "routeformer" or k.startswith("routeformer.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No fallback: without the CUDA library the loader raises (it never degrades to a CPU / eager path)."""
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "librouteformer_b200.so"))
+    monkeypatch.setenv("RF_LIB_PATH", str(tmp_path / "librouteformer_b200.so"))  # (also keeps load() from rebuilding in-tree)
+    with pytest.raises(_lib.LibraryMissing, match="no fallback"):
+        _lib.load()
+
+
+def test_cpu_tensors_are_refused():
+    """The product path has no CPU implementation: ops and the model raise on host tensors instead of computing something."""
+    import torch
+
+    import routeformer_b200 as R
+    from routeformer_b200 import ops
+
+    a = torch.zeros(8, 8)
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        ops.gemm(a, a, torch.zeros(8, 8))
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        ops.layernorm_fwd(a, torch.ones(8), torch.zeros(8), torch.empty(8, 8), torch.empty(8), torch.empty(8))
+    g = R.GPSBackboneConfig(seq_len=40, label_len=40, pred_len=30, factor=4, distil=True, dropout=0.0, activation="relu", d_model=32,
+                            n_heads=2, e_layers=1, d_layers=1, d_ff=64)
+    model = R.Routeformer(R.RouteformerConfig(gps_backbone_config=g, decoder_mode="smart"), gps_backbone=R.Informer).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model({"gps": torch.cumsum(torch.randn(2, 40, 2), dim=1)})
