@@ -173,3 +173,30 @@ def test_early_allreduce_ranges_partition_the_gradient_arena():
             assert inside(arena.offsets[id(p)]) == name.startswith("gps_backbone."), name
     n_early = sum(hi - lo for lo, hi in early)
     assert n_early >= sum(p.numel() for n, p in model.named_parameters() if n.startswith("gps_backbone.") and p.requires_grad)
+
+
+def test_host_draw_plan_equals_the_reference_random_stream():
+    """The product's host-side plan of one eval forward (every `torch.randint` of the ProbSparse attentions, made up front and
+    uploaded as index tables) against the oracle executing the reference algorithm with the same CPU seed: the same calls in the
+    same order (the golden `draws` list) and the SAME index tables, entry for entry."""
+    import torch
+
+    from oracle import routeformer_oracle as O
+    from tests.helpers import build_product, case_from_golden, load_golden
+
+    for case in ("full_small_eval", "dreyeve_small", "no_gaze_small", "no_scene_small", "gps_only_paper"):
+        gold = load_golden(case)
+        cfg, spec, sd, batch = case_from_golden(gold)
+        torch.manual_seed(12345)
+        draw = O.CpuRandint()
+        with torch.no_grad():
+            O.Routeformer(sd, cfg, spec).forward(batch, training=False, draw=draw)
+        model = build_product(cfg, spec).eval()
+        torch.manual_seed(12345)
+        plan = model.prepare_draws(batch, False)
+        assert [(lk, (lq, u)) for lk, lq, u in model.last_draw_log] == [tuple(d) for d in gold["draws"]], case
+        tables = (list(plan["visual"]["tables"]) if plan["visual"] else []) + list(plan["backbone"][1])
+        assert len(tables) == len(draw.drawn), case
+        for i, (t, ref) in enumerate(zip(tables, draw.drawn)):
+            assert t.dtype == torch.int32 and tuple(t.shape) == (1,) + tuple(ref.shape), (case, i)
+            assert torch.equal(t[0].long(), ref), (case, i)
