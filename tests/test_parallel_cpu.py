@@ -200,3 +200,24 @@ def test_host_draw_plan_equals_the_reference_random_stream():
         for i, (t, ref) in enumerate(zip(tables, draw.drawn)):
             assert t.dtype == torch.int32 and tuple(t.shape) == (1,) + tuple(ref.shape), (case, i)
             assert torch.equal(t[0].long(), ref), (case, i)
+
+
+def test_state_dict_layout_equals_the_reference_layout():
+    """`state_dict()` of the product speaks the reference's layout -- the same keys, shapes and dtypes (persistent
+    buffers included) as recorded from the reference model in every golden file, from the small cases to the paper configuration
+    (639 entries), and `load_state_dict(strict=True)` of the reference's tensors round-trips bit for bit."""
+    import torch
+
+    from tests.helpers import build_product, case_from_golden, load_golden
+
+    for case in ("gps_only_paper", "full_small_eval", "dreyeve_small", "no_gaze_small", "no_scene_small", "sparse_small",
+                 "normalized_small", "autoregressive_small", "full_paper_eval"):
+        gold = load_golden(case)
+        cfg, spec, sd, _ = case_from_golden(gold)
+        model = build_product(cfg, spec)
+        mine = model.state_dict()
+        assert {(k, tuple(v.shape), str(v.dtype)) for k, v in mine.items()} == set(map(tuple, gold["layout"])), case
+        missing, unexpected = model.load_state_dict(sd, strict=True)
+        assert not missing and not unexpected
+        assert all(torch.equal(v, sd[k]) for k, v in model.state_dict().items()), case
+    assert len(load_golden("full_paper_eval")["layout"]) == 639
