@@ -114,3 +114,27 @@ def test_random_configurations_against_the_reference():
             assert (out[1] - ref[1]).abs().max() <= 2e-5 * ref[1].abs().max(), (i, cfg)
         ran += 1
     assert ran >= 12 and raised >= 1, (ran, raised)
+
+
+def test_product_module_tree_mirrors_the_reference():
+    """the product `Routeformer` against the imported reference model object itself -- `state_dict()` keys in the same
+    ORDER with the same shapes / dtypes, `named_parameters()` in the same order (optimizer parameter groups are built from it,
+    full_comparison.py:683-691), the reference's tensors load with strict=True, and the sub-module attribute names of the checkpoint
+    contract exist (routeformer.py:57-117)."""
+    from tests.helpers import build_product
+
+    gps_only = O.OracleConfig()  # the paper's GPS backbone, no video
+    for cfg, spec in ((SMALL, SPEC), (gps_only, None)):
+        ref = R.build_reference_model(cfg, spec)
+        mine = build_product(cfg, spec)
+        rsd, msd = ref.state_dict(), mine.state_dict()
+        assert list(rsd) == list(msd)
+        assert all(rsd[k].shape == msd[k].shape and rsd[k].dtype == msd[k].dtype for k in rsd)
+        assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
+        assert [n for n, _ in ref.named_buffers()] == [n for n, _ in mine.named_buffers()]
+        mine.load_state_dict(rsd, strict=True)
+        assert all(torch.equal(v, rsd[k]) for k, v in mine.state_dict().items())
+    full_ref, full_mine = R.build_reference_model(SMALL, SPEC), build_product(SMALL, SPEC)
+    for name in ("video_backbone", "frame_encoder", "left_video_embedding", "right_video_embedding", "gaze_video_embedding",
+                 "video_output_embedding", "video_encoder", "gaze_encoder", "gaze_video_decoder", "gps_backbone"):
+        assert hasattr(full_ref, name) and hasattr(full_mine, name), name
