@@ -221,3 +221,64 @@ def test_state_dict_layout_equals_the_reference_layout():
         assert not missing and not unexpected
         assert all(torch.equal(v, sd[k]) for k, v in model.state_dict().items()), case
     assert len(load_golden("full_paper_eval")["layout"]) == 639
+
+
+def _worker_real_model(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import routeformer_oracle as O
+        from routeformer_b200.parallel import DataParallelTrainer
+        from tests.helpers import build_product
+
+        cfg = O.OracleConfig(d_model=64, n_heads=4, e_layers=2, d_ff=128, with_video=True, with_gaze=True, dense_prediction=True,
+                             encoder_layers=1, encoder_d_ff=64, image_embedding_size=32, encoder_hidden_size=32)
+        torch.manual_seed(100 + rank)  # different initial weights per rank: broadcast_parameters must make them rank 0's
+        model = build_product(cfg, O.BackboneSpec(image_size=32, patch=8, channels=48))
+        trainer = DataParallelTrainer(model, None)
+        assert trainer.world == world
+        arena = trainer.arena
+        before = arena.param.clone()
+        trainer.broadcast_parameters()
+        gathered = [torch.empty_like(arena.param) for _ in range(world)]
+        dist.all_gather(gathered, arena.param)
+        same_params = all(torch.equal(g, gathered[0]) for g in gathered) and (rank == 0) == torch.equal(before, arena.param)
+        # the step's two all-reduce phases (GPS backbone ranges early, the rest late) over the real gradient arena == one flat
+        # all-reduce == the sum of the ranks' gradients
+        g = torch.Generator().manual_seed(7 + rank)
+        arena.grad.copy_(torch.randn(arena.grad.shape, generator=g))
+        mine = arena.grad.clone()
+        early, late = trainer._split_ranges("gps_backbone.")
+        for lo, hi in early + late:
+            dist.all_reduce(arena.grad[lo:hi], op=dist.ReduceOp.SUM)
+        flat = mine.clone()
+        for h in allreduce_flat(flat, n_buckets=4):
+            h.wait()
+        both = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(both, mine)
+        total = sum(both)
+        n = arena.n_trainable
+        ok = torch.equal(arena.grad[:n], flat[:n]) and torch.allclose(flat[:n], total[:n], rtol=0, atol=1e-6)
+        # the views the autograd blocks write through are views of that same arena
+        p = model.gps_backbone.decoder.projection.weight
+        views_ok = p.grad is not None and p.grad.data_ptr() == arena.grad.data_ptr() + 4 * arena.offsets[id(p)]
+        out.put((rank, bool(same_params), bool(ok), bool(views_ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_real_model_broadcast_and_two_phase_allreduce():
+    """World size 2 over gloo with the REAL model's flat parameter / gradient arenas: `broadcast_parameters` makes every rank hold
+    rank 0's weights, and the trainer's early (GPS backbone) + late all-reduce ranges together reproduce one flat sum-all-reduce of
+    the whole gradient arena, i.e. the sum of the ranks' gradients."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_real_model, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    results = sorted(out.get(timeout=10) for _ in range(2))
+    assert results == [(0, True, True, True), (1, True, True, True)], results
